@@ -1,0 +1,141 @@
+/*
+ * qsmrt.h -- C ABI of libqsmrt.so, the B200 (sm_100a) ray/mesh intersection
+ * engine behind pyqsm_b200.RaycastingScene.
+ *
+ * Each entry point replaces one method of open3d.t.geometry.RaycastingScene as
+ * it is called from the reference, wischmcj/pyQSM pyQSM/viz/ray_casting.py
+ * (the import at :8 binds `rcs`; the call sites are cited per function).
+ * Plain pointers and sizes only: no torch, no C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     qsmrt_last_error() then holds a thread-local message.
+ *   - "dev" pointers are CUDA device pointers on the scene's device; "host"
+ *     pointers are ordinary (ideally pinned) host memory.  Caller owns all
+ *     ray/result buffers.  A NULL result pointer skips that output.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Query entry points only enqueue work; they do not synchronise unless
+ *     they take host pointers or the documentation says so.
+ *   - rays are N x 6 float32 rows (ox,oy,oz,dx,dy,dz); directions are used
+ *     as given (not normalised), so t is in units of |d|.
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef QSMRT_H
+#define QSMRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSMRT_INVALID_ID 0xFFFFFFFFu /* RaycastingScene.INVALID_ID */
+#define QSMRT_ABI_VERSION 1
+
+typedef struct qsmrt_scene qsmrt_scene;
+
+typedef struct qsmrt_stats {
+    uint64_t num_triangles;      /* over all geometries */
+    uint64_t num_geometries;
+    uint64_t num_bvh_nodes;      /* traversal nodes emitted (after leaf collapse) */
+    uint64_t num_bvh_leaves;
+    uint64_t bvh_bytes;          /* traversal nodes + triangle records */
+    float    build_ms;           /* last commit: CUDA-event time of the whole build */
+    float    sort_ms;            /* radix sort share of build_ms */
+    float    box_pad;            /* absolute AABB padding */
+    float    scene_lo[3], scene_hi[3];
+    uint32_t leaf_max;           /* triangles per collapsed leaf */
+    uint32_t reserved;
+} qsmrt_stats;
+
+const char *qsmrt_last_error(void);
+int qsmrt_abi_version(void);
+
+/* rcs()  -- ray_casting.py:65,155,218,241,275,316 */
+int qsmrt_scene_create(int cuda_device, qsmrt_scene **out);
+int qsmrt_scene_destroy(qsmrt_scene *scene);
+
+/* scene.add_triangles(mesh)  -- ray_casting.py:66,156,219,242,276,317.
+ * Copies V x 3 float32 positions and T x 3 uint32 indices (Open3D copies
+ * too); rejects an index >= V.  geom_id_out receives 0, 1, ... */
+int qsmrt_add_triangles(qsmrt_scene *scene, const float *verts, uint64_t V,
+                        const uint32_t *idx, uint64_t T, int ptrs_on_device,
+                        uint32_t *geom_id_out);
+
+/* Embree rtcCommitScene, which Open3D runs lazily on the first query.  Builds
+ * the LBVH (Morton codes, radix sort, Karras hierarchy, refit, leaf collapse).
+ * Queries call it implicitly; calling it directly lets the build be timed.
+ * build_ms_out (may be NULL) is the device time of the build; synchronises. */
+int qsmrt_commit(qsmrt_scene *scene, void *stream, float *build_ms_out);
+
+/* scene.cast_rays(rays)  -- ray_casting.py:223,231,279,319.
+ * Closest hit.  t_hit[N] (inf on miss), geometry_ids[N], primitive_ids[N]
+ * (QSMRT_INVALID_ID on miss), primitive_uvs[N x 2], primitive_normals[N x 3]
+ * (0 on miss). */
+int qsmrt_cast_rays(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
+                    float *t_hit, uint32_t *geometry_ids, uint32_t *primitive_ids,
+                    float *primitive_uvs, float *primitive_normals, void *stream);
+
+/* Same call with HOST buffers: chunks the batch and overlaps host->device,
+ * traversal and device->host copies on three streams.  Synchronises. */
+int qsmrt_cast_rays_host(qsmrt_scene *scene, const float *rays_host, uint64_t N,
+                         float *t_hit, uint32_t *geometry_ids, uint32_t *primitive_ids,
+                         float *primitive_uvs, float *primitive_normals);
+
+/* scene.count_intersections(rays)  -- the engine under list_intersections
+ * (ray_casting.py:168) and compute_occupancy (:69).  counts[N] int32.
+ * Synchronises only when a ray overflows the in-register hit set. */
+int qsmrt_count_intersections(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
+                              int32_t *counts, void *stream);
+
+/* scene.test_occlusions(rays, tnear, tfar): out[N] = 1 iff any hit with
+ * tnear < t <= tfar. */
+int qsmrt_test_occlusions(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
+                          float tnear, float tfar, uint8_t *out, void *stream);
+
+/* scene.list_intersections(rays)  -- ray_casting.py:168.  Two phases:
+ *   _count  fills ray_splits[N+1] (int64, exclusive scan of the per-ray
+ *           counts) and returns the total K in *total_out (synchronises);
+ *   _fill   writes the K hits, per ray sorted by (t, geometry, primitive):
+ *           ray_ids[K] int64, t_hit[K], geometry_ids[K], primitive_ids[K],
+ *           primitive_uvs[K x 2]. */
+int qsmrt_list_intersections_count(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
+                                   int64_t *ray_splits, int64_t *total_out, void *stream);
+int qsmrt_list_intersections_fill(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
+                                  const int64_t *ray_splits, int64_t *ray_ids, float *t_hit,
+                                  uint32_t *geometry_ids, uint32_t *primitive_ids,
+                                  float *primitive_uvs, void *stream);
+
+/* On-device generator for the parallel-ray grids of the sun / rain drivers
+ * (the pattern of ray_casting.py:159-165): ray(i,j) has origin
+ * origin0 + i*du + j*dv (i < nu fastest) and direction dir. */
+int qsmrt_gen_parallel_rays(float *rays_dev, uint64_t nu, uint64_t nv,
+                            const float origin0[3], const float du[3], const float dv[3],
+                            const float dir[3], void *stream);
+
+/* RaycastingScene.create_rays_pinhole(intrinsic, extrinsic, w, h)
+ * -- ray_casting.py:222,230,277,318.  rays_dev[h x w x 6]. */
+int qsmrt_gen_pinhole_rays(float *rays_dev, uint32_t width_px, uint32_t height_px,
+                           const double intrinsic[9], const double extrinsic[16], void *stream);
+
+/* Post-processing of ray_casting.py:285-289 on the device: marks the
+ * primitives (and their three vertices) that own a closest hit.
+ * tri_hit[T of geometry 0..] / vert_hit[V] are uint8 flags, OR-ed in. */
+int qsmrt_mark_hit_primitives(qsmrt_scene *scene, const uint32_t *geometry_ids,
+                              const uint32_t *primitive_ids, uint64_t N,
+                              uint8_t *tri_hit, uint8_t *vert_hit, void *stream);
+
+int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
+
+/* Builder introspection (parity tests of the LBVH builder; host outputs,
+ * any may be NULL).  keys[T] uint64 sorted Morton keys; order[T] sorted
+ * position -> input triangle; nodes[(2T-1) x 8] float32/int32 words of the
+ * 32-byte binary nodes (lo.xyz,left,hi.xyz,right; internal 0..T-2, leaves
+ * after). */
+int qsmrt_debug_get_build(qsmrt_scene *scene, uint64_t *keys, uint32_t *order, void *nodes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSMRT_H */

@@ -1,0 +1,36 @@
+// build.h -- host-side interface between the scene object and the LBVH builder.
+#pragma once
+#include "common.cuh"
+
+struct BuildParams {        // device-resident; filled by the bounds kernels
+    float slo[3], shi[3];   // scene bounds over referenced vertices
+    float scale[3];         // 2^21 / extent per axis (0 for a flat axis)
+    float pad;              // absolute AABB padding
+};
+
+struct LbvhBuildArgs {
+    const float    *verts;          // [V,3] concatenated
+    const uint32_t *idx;            // [T,3] rebased into verts
+    uint64_t        ntris;
+    const uint64_t *geom_offsets;   // [ngeoms+1] first triangle of each geometry
+    uint32_t        ngeoms;
+    // outputs / scratch (device)
+    uint32_t   *bounds_ord;         // [6]
+    BuildParams *params;
+    uint64_t   *keys, *keys_tmp;    // [T]
+    uint32_t   *order, *order_tmp;  // [T]
+    uint32_t   *sort_scratch;       // lbvh_sort_scratch_bytes(T)
+    BNode      *bnodes;             // [2T-1]
+    int32_t    *parent;             // [2T-1]
+    int2       *range;              // [T-1]
+    uint32_t   *flags;              // [T-1]
+    TriRec     *tris;               // [T]
+    TNode      *tnodes;             // [max(T-1,1)]
+    unsigned long long *counters;   // [2] nodes, leaves emitted
+    cudaEvent_t ev_sort0, ev_sort1; // optional
+};
+
+size_t lbvh_sort_scratch_bytes(uint64_t n);
+int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
+                    uint64_t n, uint32_t *scratch, cudaStream_t st);
+int lbvh_build(const LbvhBuildArgs &args, cudaStream_t st);

@@ -1,0 +1,476 @@
+// qsmrt_api.cu -- the scene object and the extern "C" surface of libqsmrt.so
+// (include/qsmrt.h).  Each entry point stands in for one method of Open3D's
+// RaycastingScene as the reference calls it (pyQSM/viz/ray_casting.py; the
+// header cites the line numbers).  No CPU fallback: every path needs a CUDA
+// device and fails with an error otherwise.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/qsmrt.h"
+#include "common.cuh"
+#include "build.h"
+#include "traverse.h"
+
+static thread_local char g_err[512] = "";
+
+void qsmrt_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define FAIL(...) do { qsmrt_set_error(__VA_ARGS__); return 1; } while (0)
+
+struct Geometry {
+    float *verts = nullptr; uint32_t *idx = nullptr;
+    uint64_t V = 0, T = 0;
+};
+
+struct HostPipe {            // staging for qsmrt_cast_rays_host
+    static constexpr int NBUF = 3;
+    uint64_t chunk = 0;
+    float *rays[NBUF] = {}; float *t[NBUF] = {}; uint32_t *g[NBUF] = {}; uint32_t *p[NBUF] = {};
+    float *uv[NBUF] = {}; float *nrm[NBUF] = {};
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[NBUF] = {}, e_run[NBUF] = {}, e_out[NBUF] = {};
+};
+
+struct qsmrt_scene {
+    int device = 0;
+    std::vector<Geometry> geoms;
+    bool committed = false;
+    // concatenated mesh (aliases geoms[0] when there is a single geometry)
+    float *verts = nullptr; uint32_t *idx = nullptr; bool own_concat = false;
+    uint64_t ntris = 0, nverts = 0;
+    uint64_t *goff = nullptr, *voff = nullptr;       // device [ngeoms+1]
+    // build products kept for traversal / introspection
+    uint64_t *keys = nullptr; uint32_t *order = nullptr;
+    BNode *bnodes = nullptr; TNode *tnodes = nullptr; TriRec *tris = nullptr;
+    BuildParams *params = nullptr;
+    qsmrt_stats stats{};
+    // list_intersections cache between _count and _fill
+    const float *list_rays = nullptr; uint64_t list_n = 0;
+    int64_t *list_raw_off = nullptr; HitRec *list_raw = nullptr;
+    HostPipe pipe;
+};
+
+namespace {
+
+template <class T> int dmalloc(T **p, uint64_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
+    if (e != cudaSuccess) { qsmrt_set_error("cudaMalloc(%llu bytes): %s", (unsigned long long)(count * sizeof(T)), cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+template <class T> void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+void free_build(qsmrt_scene *s)
+{
+    if (s->own_concat) { dfree(s->verts); dfree(s->idx); }
+    s->verts = nullptr; s->idx = nullptr; s->own_concat = false;
+    dfree(s->goff); dfree(s->voff); dfree(s->keys); dfree(s->order);
+    dfree(s->bnodes); dfree(s->tnodes); dfree(s->tris); dfree(s->params);
+    dfree(s->list_raw_off); dfree(s->list_raw);
+    s->list_rays = nullptr; s->list_n = 0;
+    s->committed = false;
+}
+
+void free_pipe(HostPipe &hp)
+{
+    for (int b = 0; b < HostPipe::NBUF; ++b) {
+        dfree(hp.rays[b]); dfree(hp.t[b]); dfree(hp.g[b]); dfree(hp.p[b]); dfree(hp.uv[b]); dfree(hp.nrm[b]);
+        if (hp.e_in[b]) cudaEventDestroy(hp.e_in[b]);
+        if (hp.e_run[b]) cudaEventDestroy(hp.e_run[b]);
+        if (hp.e_out[b]) cudaEventDestroy(hp.e_out[b]);
+        hp.e_in[b] = hp.e_run[b] = hp.e_out[b] = nullptr;
+    }
+    if (hp.s_in) cudaStreamDestroy(hp.s_in);
+    if (hp.s_run) cudaStreamDestroy(hp.s_run);
+    if (hp.s_out) cudaStreamDestroy(hp.s_out);
+    hp.s_in = hp.s_run = hp.s_out = nullptr;
+    hp.chunk = 0;
+}
+
+__global__ void k_rebase_idx(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t n3, uint32_t add)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = in[i] + add;
+}
+
+__global__ void k_max_index(const uint32_t *__restrict__ in, uint64_t n3, uint32_t *out)
+{
+    uint32_t m = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n3; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, in[i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+int use_device(qsmrt_scene *s)
+{
+    if (!s) FAIL("null scene");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return 0;
+}
+
+int check_rays(const float *rays, uint64_t N)
+{
+    if (N && !rays) FAIL("rays pointer is null");
+    if (reinterpret_cast<uintptr_t>(rays) & 7u) FAIL("rays must be 8-byte aligned");
+    return 0;
+}
+
+SceneView view_of(const qsmrt_scene *s)
+{
+    SceneView v;
+    v.nodes = s->tnodes; v.tris = s->tris; v.ntris = (uint32_t)s->ntris;
+    return v;
+}
+
+int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
+{
+    if (s->committed) { if (build_ms_out) *build_ms_out = s->stats.build_ms; return 0; }
+    free_build(s);
+    const uint32_t G = (uint32_t)s->geoms.size();
+    uint64_t T = 0, V = 0;
+    std::vector<uint64_t> goff(G + 1, 0), voff(G + 1, 0);
+    for (uint32_t g = 0; g < G; ++g) { goff[g] = T; voff[g] = V; T += s->geoms[g].T; V += s->geoms[g].V; }
+    goff[G] = T; voff[G] = V;
+    if (T >= (1ull << 29)) FAIL("scene has %llu triangles; the leaf encoding holds 2^29", (unsigned long long)T);
+    if (V >= (1ull << 32)) FAIL("scene has %llu vertices; indices are 32-bit", (unsigned long long)V);
+    s->ntris = T; s->nverts = V;
+    memset(&s->stats, 0, sizeof(s->stats));
+    s->stats.num_triangles = T; s->stats.num_geometries = G; s->stats.leaf_max = QSMRT_LEAF_MAX;
+    s->committed = true;
+    if (T == 0) { if (build_ms_out) *build_ms_out = 0.0f; return 0; }
+
+    cudaEvent_t e0, e1, es0, es1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventCreate(&es0)); CUDA_TRY(cudaEventCreate(&es1));
+
+    if (dmalloc(&s->goff, G + 1) || dmalloc(&s->voff, G + 1)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(s->goff, goff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->voff, voff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    // allocate everything before the timed region
+    uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr, *bounds = nullptr, *flags = nullptr;
+    int32_t *parent = nullptr; int2 *range = nullptr; unsigned long long *counters = nullptr;
+    if (dmalloc(&s->keys, T) || dmalloc(&keys_tmp, T) || dmalloc(&s->order, T) || dmalloc(&order_tmp, T) ||
+        dmalloc(&sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&bounds, 8) ||
+        dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&parent, 2 * T - 1) ||
+        dmalloc(&range, T) || dmalloc(&flags, T) || dmalloc(&s->tris, T) ||
+        dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&counters, 2))
+        return 1;
+    if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
+    else {
+        if (dmalloc(&s->verts, 3 * V) || dmalloc(&s->idx, 3 * T)) return 1;
+        s->own_concat = true;
+    }
+
+    CUDA_TRY(cudaEventRecord(e0, st));
+    if (G > 1) {
+        for (uint32_t g = 0; g < G; ++g) {
+            const Geometry &ge = s->geoms[g];
+            if (ge.V) CUDA_TRY(cudaMemcpyAsync(s->verts + 3 * voff[g], ge.verts, 3 * ge.V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (ge.T) k_rebase_idx<<<(unsigned)((3 * ge.T + 255) / 256), 256, 0, st>>>(ge.idx, s->idx + 3 * goff[g], 3 * ge.T, (uint32_t)voff[g]);
+        }
+    }
+    LbvhBuildArgs A{};
+    A.verts = s->verts; A.idx = s->idx; A.ntris = T; A.geom_offsets = s->goff; A.ngeoms = G;
+    A.bounds_ord = bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = keys_tmp;
+    A.order = s->order; A.order_tmp = order_tmp; A.sort_scratch = sort_scratch;
+    A.bnodes = s->bnodes; A.parent = parent; A.range = range; A.flags = flags;
+    A.tris = s->tris; A.tnodes = s->tnodes; A.counters = counters; A.ev_sort0 = es0; A.ev_sort1 = es1;
+    int rc = lbvh_build(A, st);
+    if (!rc) {
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&s->stats.build_ms, e0, e1));
+        CUDA_TRY(cudaEventElapsedTime(&s->stats.sort_ms, es0, es1));
+        BuildParams bp; unsigned long long cnt[2];
+        CUDA_TRY(cudaMemcpy(&bp, s->params, sizeof(bp), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+        for (int a = 0; a < 3; ++a) { s->stats.scene_lo[a] = bp.slo[a]; s->stats.scene_hi[a] = bp.shi[a]; }
+        s->stats.box_pad = bp.pad;
+        s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1];
+        s->stats.bvh_bytes = cnt[0] * sizeof(TNode) + T * sizeof(TriRec);
+    }
+    dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags);
+    dfree(parent); dfree(range); dfree(counters);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(es0); cudaEventDestroy(es1);
+    if (rc) { s->committed = false; return 1; }
+    if (build_ms_out) *build_ms_out = s->stats.build_ms;
+    return 0;
+}
+
+int ensure_pipe(qsmrt_scene *s, uint64_t chunk)
+{
+    HostPipe &hp = s->pipe;
+    if (hp.chunk >= chunk) return 0;
+    free_pipe(hp);
+    for (int b = 0; b < HostPipe::NBUF; ++b) {
+        if (dmalloc(&hp.rays[b], 6 * chunk) || dmalloc(&hp.t[b], chunk) || dmalloc(&hp.g[b], chunk) ||
+            dmalloc(&hp.p[b], chunk) || dmalloc(&hp.uv[b], 2 * chunk) || dmalloc(&hp.nrm[b], 3 * chunk))
+            return 1;
+        CUDA_TRY(cudaEventCreateWithFlags(&hp.e_in[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&hp.e_run[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&hp.e_out[b], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    hp.chunk = chunk;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *qsmrt_last_error(void) { return g_err; }
+int qsmrt_abi_version(void) { return QSMRT_ABI_VERSION; }
+
+int qsmrt_scene_create(int cuda_device, qsmrt_scene **out)
+{
+    if (!out) FAIL("null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        FAIL("no CUDA device (%s); libqsmrt has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (cuda_device < 0 || cuda_device >= ndev) FAIL("cuda_device %d out of range (0..%d)", cuda_device, ndev - 1);
+    CUDA_TRY(cudaSetDevice(cuda_device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cuda_device));
+    if (prop.major != 10) FAIL("device %d is sm_%d%d; libqsmrt is built for sm_100a only", cuda_device, prop.major, prop.minor);
+    qsmrt_scene *s = new qsmrt_scene();
+    s->device = cuda_device;
+    *out = s;
+    return 0;
+}
+
+int qsmrt_scene_destroy(qsmrt_scene *s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    free_build(s);
+    free_pipe(s->pipe);
+    for (Geometry &g : s->geoms) { dfree(g.verts); dfree(g.idx); }
+    delete s;
+    return 0;
+}
+
+int qsmrt_add_triangles(qsmrt_scene *s, const float *verts, uint64_t V, const uint32_t *idx, uint64_t T,
+                        int on_device, uint32_t *geom_id_out)
+{
+    if (use_device(s)) return 1;
+    if ((V && !verts) || (T && !idx)) FAIL("null vertex or index pointer");
+    if (V >= (1ull << 32)) FAIL("too many vertices");
+    Geometry g;
+    g.V = V; g.T = T;
+    if (dmalloc(&g.verts, 3 * V) || dmalloc(&g.idx, 3 * T)) { dfree(g.verts); dfree(g.idx); return 1; }
+    cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (V) CUDA_TRY(cudaMemcpy(g.verts, verts, 3 * V * sizeof(float), kind));
+    if (T) CUDA_TRY(cudaMemcpy(g.idx, idx, 3 * T * sizeof(uint32_t), kind));
+    // Embree would read out of bounds; reject instead
+    uint32_t maxi = 0;
+    if (T) {
+        uint32_t *d = nullptr;
+        if (dmalloc(&d, 1)) { dfree(g.verts); dfree(g.idx); return 1; }
+        cudaMemset(d, 0, sizeof(uint32_t));
+        k_max_index<<<(unsigned)std::min<uint64_t>((3 * T + 255) / 256, 1184), 256>>>(g.idx, 3 * T, d);
+        cudaError_t e = cudaMemcpy(&maxi, d, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        dfree(d);
+        if (e != cudaSuccess) { dfree(g.verts); dfree(g.idx); FAIL("index check failed: %s", cudaGetErrorString(e)); }
+        if (maxi >= V) { dfree(g.verts); dfree(g.idx); FAIL("triangle index %u out of range (%llu vertices)", maxi, (unsigned long long)V); }
+    }
+    if (s->committed || s->verts) free_build(s);
+    s->geoms.push_back(g);
+    if (geom_id_out) *geom_id_out = (uint32_t)(s->geoms.size() - 1);
+    return 0;
+}
+
+int qsmrt_commit(qsmrt_scene *s, void *stream, float *build_ms_out)
+{
+    if (use_device(s)) return 1;
+    return do_commit(s, static_cast<cudaStream_t>(stream), build_ms_out);
+}
+
+int qsmrt_cast_rays(qsmrt_scene *s, const float *rays, uint64_t N, float *t_hit, uint32_t *geom, uint32_t *prim,
+                    float *uv, float *nrm, void *stream)
+{
+    if (use_device(s) || check_rays(rays, N)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
+    return trv_cast_rays(view_of(s), rays, N, t_hit, geom, prim, uv, nrm, st);
+}
+
+int qsmrt_cast_rays_host(qsmrt_scene *s, const float *rays, uint64_t N, float *t_hit, uint32_t *geom,
+                         uint32_t *prim, float *uv, float *nrm)
+{
+    if (use_device(s)) return 1;
+    if (N && !rays) FAIL("rays pointer is null");
+    if (do_commit(s, nullptr, nullptr)) return 1;
+    if (N == 0) return 0;
+    const uint64_t chunk = std::min<uint64_t>(N, 1ull << 20);
+    if (ensure_pipe(s, chunk)) return 1;
+    HostPipe &hp = s->pipe;
+    SceneView sv = view_of(s);
+    uint64_t nchunks = (N + chunk - 1) / chunk;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        int b = (int)(c % HostPipe::NBUF);
+        uint64_t off = c * chunk, n = std::min(chunk, N - off);
+        if (c >= HostPipe::NBUF) CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.e_out[b], 0));   // buffer drained
+        CUDA_TRY(cudaMemcpyAsync(hp.rays[b], rays + 6 * off, 6 * n * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
+        CUDA_TRY(cudaEventRecord(hp.e_in[b], hp.s_in));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_run, hp.e_in[b], 0));
+        if (trv_cast_rays(sv, hp.rays[b], n, t_hit ? hp.t[b] : nullptr, geom ? hp.g[b] : nullptr,
+                          prim ? hp.p[b] : nullptr, uv ? hp.uv[b] : nullptr, nrm ? hp.nrm[b] : nullptr, hp.s_run))
+            return 1;
+        CUDA_TRY(cudaEventRecord(hp.e_run[b], hp.s_run));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.e_run[b], 0));
+        if (t_hit) CUDA_TRY(cudaMemcpyAsync(t_hit + off, hp.t[b], n * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+        if (geom) CUDA_TRY(cudaMemcpyAsync(geom + off, hp.g[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, hp.s_out));
+        if (prim) CUDA_TRY(cudaMemcpyAsync(prim + off, hp.p[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, hp.s_out));
+        if (uv) CUDA_TRY(cudaMemcpyAsync(uv + 2 * off, hp.uv[b], 2 * n * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+        if (nrm) CUDA_TRY(cudaMemcpyAsync(nrm + 3 * off, hp.nrm[b], 3 * n * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
+        CUDA_TRY(cudaEventRecord(hp.e_out[b], hp.s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(hp.s_out));
+    CUDA_TRY(cudaStreamSynchronize(hp.s_run));
+    CUDA_TRY(cudaStreamSynchronize(hp.s_in));
+    return 0;
+}
+
+int qsmrt_count_intersections(qsmrt_scene *s, const float *rays, uint64_t N, int32_t *counts, void *stream)
+{
+    if (use_device(s) || check_rays(rays, N)) return 1;
+    if (N && !counts) FAIL("counts pointer is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    return trv_count(view_of(s), rays, N, counts, st);
+}
+
+int qsmrt_test_occlusions(qsmrt_scene *s, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, void *stream)
+{
+    if (use_device(s) || check_rays(rays, N)) return 1;
+    if (N && !out) FAIL("output pointer is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    return trv_occluded(view_of(s), rays, N, tnear, tfar, out, st);
+}
+
+int qsmrt_list_intersections_count(qsmrt_scene *s, const float *rays, uint64_t N, int64_t *ray_splits,
+                                   int64_t *total_out, void *stream)
+{
+    if (use_device(s) || check_rays(rays, N)) return 1;
+    if (!ray_splits || !total_out) FAIL("null output pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    dfree(s->list_raw_off); dfree(s->list_raw);
+    s->list_rays = nullptr; s->list_n = 0;
+    int32_t *cnt = nullptr; void *scratch = nullptr;
+    if (dmalloc(&cnt, N) || dmalloc(&s->list_raw_off, N + 1) ||
+        dmalloc(reinterpret_cast<char **>(&scratch), trv_scan_scratch_bytes(N))) { dfree(cnt); return 1; }
+    SceneView sv = view_of(s);
+    int64_t raw_total = 0;
+    int rc = trv_raw_count(sv, rays, N, cnt, st) || trv_exclusive_scan(cnt, N, s->list_raw_off, scratch, st);
+    if (!rc && cudaMemcpyAsync(&raw_total, s->list_raw_off + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+    if (!rc) rc = dmalloc(&s->list_raw, (uint64_t)raw_total);
+    if (!rc) rc = trv_raw_fill_sort(sv, rays, N, s->list_raw_off, s->list_raw, cnt, st) ||
+                  trv_exclusive_scan(cnt, N, ray_splits, scratch, st);
+    if (!rc && cudaMemcpyAsync(total_out, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
+    dfree(cnt);
+    { char *p = reinterpret_cast<char *>(scratch); dfree(p); }
+    if (rc) { if (!g_err[0]) qsmrt_set_error("list_intersections failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    s->list_rays = rays; s->list_n = N;
+    return 0;
+}
+
+int qsmrt_list_intersections_fill(qsmrt_scene *s, const float *rays, uint64_t N, const int64_t *ray_splits,
+                                  int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (!s->list_raw_off || s->list_rays != rays || s->list_n != N)
+        FAIL("list_intersections_fill must follow list_intersections_count on the same rays");
+    if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = trv_list_compact(N, s->list_raw_off, s->list_raw, ray_splits, ray_ids, t_hit, geom, prim, uv, st);
+    if (!rc) CUDA_TRY(cudaStreamSynchronize(st));
+    dfree(s->list_raw_off); dfree(s->list_raw);
+    s->list_rays = nullptr; s->list_n = 0;
+    return rc;
+}
+
+int qsmrt_gen_parallel_rays(float *rays, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+                            const float dv[3], const float dir[3], void *stream)
+{
+    if (!rays || !o0 || !du || !dv || !dir) FAIL("null pointer");
+    if (reinterpret_cast<uintptr_t>(rays) & 7u) FAIL("rays must be 8-byte aligned");
+    return trv_gen_parallel(rays, nu, nv, o0, du, dv, dir, static_cast<cudaStream_t>(stream));
+}
+
+int qsmrt_gen_pinhole_rays(float *rays, uint32_t w, uint32_t h, const double K[9], const double E[16], void *stream)
+{
+    if (!rays || !K || !E) FAIL("null pointer");
+    if (reinterpret_cast<uintptr_t>(rays) & 7u) FAIL("rays must be 8-byte aligned");
+    // Open3D CreateRaysPinhole: C = -R^T t, direction = (K R)^-1 (x+.5, y+.5, 1)
+    double R[9], t[3], M[9], inv[9], eye[3];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[3 * r + c] = E[4 * r + c]; t[r] = E[4 * r + 3]; }
+    for (int c = 0; c < 3; ++c) eye[c] = -(R[c] * t[0] + R[3 + c] * t[1] + R[6 + c] * t[2]);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+        double a = 0; for (int k = 0; k < 3; ++k) a += K[3 * r + k] * R[3 * k + c];
+        M[3 * r + c] = a;
+    }
+    double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    if (det == 0.0 || !std::isfinite(det)) FAIL("intrinsic * rotation is singular");
+    inv[0] = (M[4] * M[8] - M[5] * M[7]) / det; inv[1] = (M[2] * M[7] - M[1] * M[8]) / det; inv[2] = (M[1] * M[5] - M[2] * M[4]) / det;
+    inv[3] = (M[5] * M[6] - M[3] * M[8]) / det; inv[4] = (M[0] * M[8] - M[2] * M[6]) / det; inv[5] = (M[2] * M[3] - M[0] * M[5]) / det;
+    inv[6] = (M[3] * M[7] - M[4] * M[6]) / det; inv[7] = (M[1] * M[6] - M[0] * M[7]) / det; inv[8] = (M[0] * M[4] - M[1] * M[3]) / det;
+    return trv_gen_pinhole(rays, w, h, inv, eye, static_cast<cudaStream_t>(stream));
+}
+
+int qsmrt_mark_hit_primitives(qsmrt_scene *s, const uint32_t *geom, const uint32_t *prim, uint64_t N,
+                              uint8_t *tri_hit, uint8_t *vert_hit, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (!prim) FAIL("primitive_ids pointer is null");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    if (s->ntris == 0) return 0;
+    return trv_mark_hits(geom, prim, N, s->goff, s->voff, (uint32_t)s->geoms.size(), s->idx, tri_hit, vert_hit, st);
+}
+
+int qsmrt_get_stats(qsmrt_scene *s, qsmrt_stats *out)
+{
+    if (!s || !out) FAIL("null pointer");
+    *out = s->stats;
+    if (!s->committed) {
+        uint64_t T = 0; for (const Geometry &g : s->geoms) T += g.T;
+        out->num_triangles = T; out->num_geometries = s->geoms.size();
+    }
+    return 0;
+}
+
+int qsmrt_debug_get_build(qsmrt_scene *s, uint64_t *keys, uint32_t *order, void *nodes)
+{
+    if (use_device(s)) return 1;
+    if (do_commit(s, nullptr, nullptr)) return 1;
+    uint64_t T = s->ntris;
+    if (T == 0) return 0;
+    if (keys) CUDA_TRY(cudaMemcpy(keys, s->keys, T * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (order) CUDA_TRY(cudaMemcpy(order, s->order, T * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (nodes) CUDA_TRY(cudaMemcpy(nodes, s->bnodes, (2 * T - 1) * sizeof(BNode), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+} // extern "C"

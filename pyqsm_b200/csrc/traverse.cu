@@ -1,0 +1,588 @@
+// traverse.cu -- BVH traversal kernels for sm_100a: closest hit (cast_rays),
+// all hits (count_intersections / list_intersections) and any hit
+// (test_occlusions), plus the ray generators.
+//
+// Replaces Embree's rtcIntersect1/rtcOccluded1 loops inside Open3D's
+// RaycastingScene::CastRays / CountIntersections / ListIntersections /
+// TestOcclusions (reference call sites: pyQSM/viz/ray_casting.py:168,223,231,
+// 279,319).  Triangle arithmetic: common.cuh::mt_test, the bit-for-bit twin
+// of oracle/qsmrt_oracle.c::mt_test.
+//
+// One thread per ray.  Each thread keeps a short traversal stack in shared
+// memory laid out [entry][thread] (bank-conflict free, no local-memory
+// traffic on the hot path) and spills to a local array only below depth
+// TR_SSTACK.  Nodes are fetched as four 16-byte loads, triangles as three.
+#include "common.cuh"
+#include "traverse.h"
+
+namespace {
+
+constexpr int TR_BLOCK  = 128;
+constexpr int TR_SSTACK = 16;     // shared-memory entries per thread
+constexpr int TR_LSTACK = 80;     // local spill; 96 total > max LBVH depth (63 key bits + 26 index bits)
+
+struct Stack {
+    int *s;                 // &smem[0][threadIdx.x]
+    int  loc[TR_LSTACK];
+    int  sp;
+    __device__ __forceinline__ void push(int v) {
+        if (sp < TR_SSTACK) s[sp * TR_BLOCK] = v; else loc[sp - TR_SSTACK] = v;
+        ++sp;
+    }
+    __device__ __forceinline__ int pop() {
+        --sp;
+        return sp < TR_SSTACK ? s[sp * TR_BLOCK] : loc[sp - TR_SSTACK];
+    }
+};
+
+// Conservative slab test (subtract first: the sign is exact; interval widened
+// by ~4 ulp).  Returns entry distance; hit iff entry <= exit.
+__device__ __forceinline__ bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                     const Ray &r, float tmax, float &tn)
+{
+    float x0 = (lox - r.O.x) * r.idx, x1 = (hix - r.O.x) * r.idx;
+    float y0 = (loy - r.O.y) * r.idy, y1 = (hiy - r.O.y) * r.idy;
+    float z0 = (loz - r.O.z) * r.idz, z1 = (hiz - r.O.z) * r.idz;
+    float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    float tfar = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    tmin *= 0.9999995f;
+    tfar *= 1.0000005f;
+    tn = tmin;
+    return tmin <= tfar;
+}
+
+__device__ __forceinline__ void load_node(const TNode *__restrict__ nodes, int i, float4 &a, float4 &b, float4 &c, int4 &d)
+{
+    const float4 *p = reinterpret_cast<const float4 *>(nodes + i);
+    a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2);
+    d = __ldg(reinterpret_cast<const int4 *>(p + 3));
+}
+
+__device__ __forceinline__ void load_tri(const TriRec *__restrict__ tris, uint32_t i, float4 &p0, float4 &p1, float4 &p2)
+{
+    const float4 *p = reinterpret_cast<const float4 *>(tris + i);
+    p0 = __ldg(p); p1 = __ldg(p + 1); p2 = __ldg(p + 2);
+}
+
+// Generic stack traversal.  V::tmax() bounds the interval (shrinks for closest
+// hit), V::leaf(first, count) tests triangles and returns true to stop.
+template <bool ORDERED, class V>
+__device__ __forceinline__ void traverse(const SceneView &sc, const Ray &r, Stack &st, V &vis)
+{
+    st.sp = 0;
+    int cur = 0;                         // root
+    for (;;) {
+        if (cur >= 0) {
+            float4 a, b, c; int4 d;
+            load_node(sc.nodes, cur, a, b, c, d);
+            float t0, t1;
+            const float tm = vis.tmax();
+            bool h0 = slab(a.x, a.y, a.z, a.w, c.x, c.y, r, tm, t0);
+            bool h1 = slab(b.x, b.y, b.z, b.w, c.z, c.w, r, tm, t1);
+            if (h0 & h1) {
+                bool swap = ORDERED && (t1 < t0);
+                st.push(swap ? d.x : d.y);
+                cur = swap ? d.y : d.x;
+                continue;
+            }
+            if (h0) { cur = d.x; continue; }
+            if (h1) { cur = d.y; continue; }
+        } else {
+            uint32_t ref = (uint32_t)~cur;
+            if (vis.leaf(ref >> 2, (ref & 3u) + 1u)) return;
+        }
+        if (st.sp == 0) return;
+        cur = st.pop();
+    }
+}
+
+// ------------------------------------------------------------ closest hit
+struct ClosestVis {
+    const SceneView &sc; const Ray &r;
+    float t; uint32_t geom, prim, tri;
+    __device__ __forceinline__ float tmax() const { return t; }
+    __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, first + k, p0, p1, p2);
+            MtHit h;
+            if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                float tt = __fdiv_rn(h.T, h.absDen);
+                uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
+                // exact ties go to the lowest (geometry, primitive)
+                bool better = (tt < t) | ((tt == t) & ((pg < geom) | ((pg == geom) & (pp < prim))));
+                if (better) { t = tt; geom = pg; prim = pp; tri = first + k; }
+            }
+        }
+        return false;
+    }
+};
+
+__global__ void __launch_bounds__(TR_BLOCK)
+k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N,
+            float *__restrict__ t_hit, uint32_t *__restrict__ geom, uint32_t *__restrict__ prim,
+            float2 *__restrict__ uv, float *__restrict__ nrm)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+    if (i >= N) return;
+    Ray r = load_ray(rays, i);
+    Stack st; st.s = sstack + threadIdx.x;
+    ClosestVis vis{ sc, r, INFINITY, QSMRT_INVALID, QSMRT_INVALID, 0u };
+    if (sc.ntris) traverse<true>(sc, r, st, vis);
+    if (t_hit) t_hit[i] = vis.t;
+    if (geom) geom[i] = vis.geom;
+    if (prim) prim[i] = vis.prim;
+    if (uv || nrm) {
+        float u = 0.0f, v = 0.0f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (vis.prim != QSMRT_INVALID) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, vis.tri, p0, p1, p2);
+            MtHit h;
+            mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h);
+            u = __fdiv_rn(h.U, h.absDen); v = __fdiv_rn(h.V, h.absDen);
+            float inv = __fdiv_rn(1.0f, __fsqrt_rn(f3dot(h.Ng, h.Ng)));
+            nx = __fmul_rn(h.Ng.x, inv); ny = __fmul_rn(h.Ng.y, inv); nz = __fmul_rn(h.Ng.z, inv);
+        }
+        if (uv) uv[i] = make_float2(u, v);
+        if (nrm) { nrm[3 * i] = nx; nrm[3 * i + 1] = ny; nrm[3 * i + 2] = nz; }
+    }
+}
+
+// ---------------------------------------------------------------- any hit
+struct AnyVis {
+    const SceneView &sc; const Ray &r; float tnear, tfar; bool hit;
+    __device__ __forceinline__ float tmax() const { return tfar; }
+    __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, first + k, p0, p1, p2);
+            MtHit h;
+            if (mt_test(p0, p1, p2, r.O, r.D, tnear, tfar, h)) { hit = true; return true; }
+        }
+        return false;
+    }
+};
+
+__global__ void __launch_bounds__(TR_BLOCK)
+k_test_occlusions(SceneView sc, const float *__restrict__ rays, uint64_t N, float tnear, float tfar,
+                  uint8_t *__restrict__ out)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+    if (i >= N) return;
+    Ray r = load_ray(rays, i);
+    Stack st; st.s = sstack + threadIdx.x;
+    AnyVis vis{ sc, r, tnear, tfar, false };
+    if (sc.ntris) traverse<false>(sc, r, st, vis);
+    out[i] = vis.hit ? 1 : 0;
+}
+
+// --------------------------------------------------------------- all hits
+// count_intersections: Open3D's CountIntersectionsFunc counts a hit unless it
+// repeats the previous callback's geometry with an equal t; restated
+// order-independently as "distinct (geometry, t) pairs".  Fast path: a small
+// per-thread set; a ray with more distinct hits than the set holds falls
+// through to next_distinct(), which enumerates the pairs in increasing order
+// with one traversal each (exact, no storage, no host round trip).
+constexpr int CNT_CAP = 24;
+
+struct CountVis {
+    const SceneView &sc; const Ray &r;
+    float ts[CNT_CAP]; uint32_t gs[CNT_CAP]; int n; bool overflow;
+    __device__ __forceinline__ float tmax() const { return INFINITY; }
+    __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, first + k, p0, p1, p2);
+            MtHit h;
+            if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                float tt = __fdiv_rn(h.T, h.absDen);
+                uint32_t pg = __float_as_uint(p1.w);
+                bool dup = false;
+                for (int q = 0; q < n; ++q) dup |= (ts[q] == tt) & (gs[q] == pg);
+                if (!dup) {
+                    if (n < CNT_CAP) { ts[n] = tt; gs[n] = pg; ++n; }
+                    else { overflow = true; return true; }
+                }
+            }
+        }
+        return false;
+    }
+};
+
+// smallest (t, geom) pair strictly greater than (pt, pg) among accepted hits
+struct NextVis {
+    const SceneView &sc; const Ray &r;
+    float pt; uint32_t pg; bool have_prev;
+    float bt; uint32_t bg; bool found;
+    __device__ __forceinline__ float tmax() const { return bt; }
+    __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, first + k, p0, p1, p2);
+            MtHit h;
+            if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                float tt = __fdiv_rn(h.T, h.absDen);
+                uint32_t g = __float_as_uint(p1.w);
+                bool after = !have_prev || (tt > pt) || (tt == pt && g > pg);
+                bool better = !found || (tt < bt) || (tt == bt && g < bg);
+                if (after && better) { bt = tt; bg = g; found = true; }
+            }
+        }
+        return false;
+    }
+};
+
+__global__ void __launch_bounds__(TR_BLOCK)
+k_count_intersections(SceneView sc, const float *__restrict__ rays, uint64_t N, int32_t *__restrict__ out)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+    if (i >= N) return;
+    Ray r = load_ray(rays, i);
+    Stack st; st.s = sstack + threadIdx.x;
+    int result = 0;
+    if (sc.ntris) {
+        CountVis vis{ sc, r };
+        vis.n = 0; vis.overflow = false;
+        traverse<false>(sc, r, st, vis);
+        result = vis.n;
+        if (vis.overflow) {
+            result = 0;
+            NextVis nv{ sc, r, 0.0f, 0u, false, INFINITY, 0u, false };
+            for (;;) {
+                nv.bt = INFINITY; nv.bg = 0u; nv.found = false;
+                traverse<true>(sc, r, st, nv);
+                if (!nv.found) break;
+                ++result;
+                nv.pt = nv.bt; nv.pg = nv.bg; nv.have_prev = true;
+            }
+        }
+    }
+    out[i] = result;
+}
+
+// list_intersections, phase 1a: raw (un-deduplicated) hit count per ray
+struct RawCountVis {
+    const SceneView &sc; const Ray &r; int n;
+    __device__ __forceinline__ float tmax() const { return INFINITY; }
+    __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, first + k, p0, p1, p2);
+            MtHit h;
+            n += mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h) ? 1 : 0;
+        }
+        return false;
+    }
+};
+
+__global__ void __launch_bounds__(TR_BLOCK)
+k_raw_count(SceneView sc, const float *__restrict__ rays, uint64_t N, int32_t *__restrict__ out)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+    if (i >= N) return;
+    Ray r = load_ray(rays, i);
+    Stack st; st.s = sstack + threadIdx.x;
+    RawCountVis vis{ sc, r, 0 };
+    if (sc.ntris) traverse<false>(sc, r, st, vis);
+    out[i] = vis.n;
+}
+
+// phase 1b: write every raw hit of ray i at raw[raw_off[i] ...]
+struct RawFillVis {
+    const SceneView &sc; const Ray &r; HitRec *dst;
+    __device__ __forceinline__ float tmax() const { return INFINITY; }
+    __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, first + k, p0, p1, p2);
+            MtHit h;
+            if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                HitRec hr;
+                hr.t = __fdiv_rn(h.T, h.absDen); hr.u = __fdiv_rn(h.U, h.absDen); hr.v = __fdiv_rn(h.V, h.absDen);
+                hr.geom = __float_as_uint(p1.w); hr.prim = __float_as_uint(p0.w);
+                *dst++ = hr;
+            }
+        }
+        return false;
+    }
+};
+
+__device__ __forceinline__ bool hit_less(const HitRec &a, const HitRec &b)
+{
+    if (a.t != b.t) return a.t < b.t;
+    if (a.geom != b.geom) return a.geom < b.geom;
+    return a.prim < b.prim;
+}
+
+// phase 1b+1c fused: fill, then per ray shell-sort by (t, geom, prim) and drop
+// hits repeating the previous (t, geom); deduplicated count -> cnt[i]
+__global__ void __launch_bounds__(TR_BLOCK)
+k_raw_fill_sort(SceneView sc, const float *__restrict__ rays, uint64_t N,
+                const int64_t *__restrict__ raw_off, HitRec *__restrict__ raw, int32_t *__restrict__ cnt)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+    if (i >= N) return;
+    Ray r = load_ray(rays, i);
+    Stack st; st.s = sstack + threadIdx.x;
+    HitRec *seg = raw + raw_off[i];
+    int n = (int)(raw_off[i + 1] - raw_off[i]);
+    RawFillVis vis{ sc, r, seg };
+    if (sc.ntris && n) traverse<false>(sc, r, st, vis);
+    for (int gap = n / 2; gap > 0; gap /= 2)
+        for (int a = gap; a < n; ++a) {
+            HitRec x = seg[a];
+            int b = a;
+            for (; b >= gap && hit_less(x, seg[b - gap]); b -= gap) seg[b] = seg[b - gap];
+            seg[b] = x;
+        }
+    int m = 0;
+    for (int a = 0; a < n; ++a) {
+        HitRec x = seg[a];
+        if (m > 0 && seg[m - 1].t == x.t && seg[m - 1].geom == x.geom) continue;
+        seg[m++] = x;
+    }
+    cnt[i] = m;
+}
+
+__global__ void __launch_bounds__(256)
+k_list_compact(uint64_t N, const int64_t *__restrict__ raw_off, const HitRec *__restrict__ raw,
+               const int64_t *__restrict__ splits, int64_t *__restrict__ ray_ids, float *__restrict__ t_hit,
+               uint32_t *__restrict__ geom, uint32_t *__restrict__ prim, float2 *__restrict__ uv)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int64_t o = splits[i];
+    int m = (int)(splits[i + 1] - o);
+    const HitRec *seg = raw + raw_off[i];
+    for (int k = 0; k < m; ++k) {
+        HitRec x = seg[k];
+        if (ray_ids) ray_ids[o + k] = (int64_t)i;
+        if (t_hit) t_hit[o + k] = x.t;
+        if (geom) geom[o + k] = x.geom;
+        if (prim) prim[o + k] = x.prim;
+        if (uv) uv[o + k] = make_float2(x.u, x.v);
+    }
+}
+
+// ------------------------------------------- exclusive scan int32 -> int64
+constexpr int SC_THREADS = 256, SC_ITEMS = 16, SC_TILE = SC_THREADS * SC_ITEMS;
+
+__device__ __forceinline__ long long block_excl_scan(long long v, long long *total)
+{
+    __shared__ long long ws[SC_THREADS / 32];
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long x = v;
+    for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (l >= o) x += y; }
+    if (l == 31) ws[w] = x;
+    __syncthreads();
+    long long off = 0, tot = 0;
+    for (int k = 0; k < SC_THREADS / 32; ++k) { if (k < w) off += ws[k]; tot += ws[k]; }
+    __syncthreads();
+    *total = tot;
+    return off + x - v;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_scan_tile_sums(const int32_t *__restrict__ in, uint64_t n, long long *__restrict__ tile_sum)
+{
+    uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+    long long s = 0;
+    for (int k = 0; k < SC_ITEMS; ++k) if (base + k < n) s += in[base + k];
+    long long tot;
+    block_excl_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_scan_tile_offsets(long long *tile_sum, uint32_t ntiles)   // single block, in place -> exclusive
+{
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < ntiles; b += SC_THREADS) {
+        uint32_t i = b + threadIdx.x;
+        long long v = i < ntiles ? tile_sum[i] : 0, tot;
+        long long e = block_excl_scan(v, &tot);
+        if (i < ntiles) tile_sum[i] = carry + e;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_scan_final(const int32_t *__restrict__ in, uint64_t n, const long long *__restrict__ tile_off,
+             int64_t *__restrict__ out /* n+1 */)
+{
+    uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+    int32_t v[SC_ITEMS];
+    long long s = 0;
+    for (int k = 0; k < SC_ITEMS; ++k) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+    long long tot;
+    long long run = block_excl_scan(s, &tot) + tile_off[blockIdx.x];
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+        if (base + k + 1 == n) out[n] = run;
+    }
+}
+
+// ---------------------------------------------------------- ray generators
+__global__ void __launch_bounds__(256)
+k_gen_parallel(float *__restrict__ rays, uint64_t nu, uint64_t nv, f3 o0, f3 du, f3 dv, f3 dir)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= nu * nv) return;
+    float fu = (float)(i % nu), fv = (float)(i / nu);
+    float2 *p = reinterpret_cast<float2 *>(rays + 6 * i);
+    float ox = __fmaf_rn(fu, du.x, __fmaf_rn(fv, dv.x, o0.x));
+    float oy = __fmaf_rn(fu, du.y, __fmaf_rn(fv, dv.y, o0.y));
+    float oz = __fmaf_rn(fu, du.z, __fmaf_rn(fv, dv.z, o0.z));
+    p[0] = make_float2(ox, oy); p[1] = make_float2(oz, dir.x); p[2] = make_float2(dir.y, dir.z);
+}
+
+struct PinholeArgs { double m[9]; double eye[3]; };
+
+__global__ void __launch_bounds__(256)
+k_gen_pinhole(float *__restrict__ rays, uint32_t w, uint32_t h, PinholeArgs pa)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)w * h) return;
+    double x = (double)(i % w) + 0.5, y = (double)(i / w) + 0.5;
+    float2 *p = reinterpret_cast<float2 *>(rays + 6 * i);
+    float dx = (float)(pa.m[0] * x + pa.m[1] * y + pa.m[2]);
+    float dy = (float)(pa.m[3] * x + pa.m[4] * y + pa.m[5]);
+    float dz = (float)(pa.m[6] * x + pa.m[7] * y + pa.m[8]);
+    p[0] = make_float2((float)pa.eye[0], (float)pa.eye[1]);
+    p[1] = make_float2((float)pa.eye[2], dx);
+    p[2] = make_float2(dy, dz);
+}
+
+// hit-primitive marking (ray_casting.py:285-289): flags are OR-ed, benign races
+__global__ void __launch_bounds__(256)
+k_mark_hits(const uint32_t *__restrict__ geom, const uint32_t *__restrict__ prim, uint64_t N,
+            const uint64_t *__restrict__ goff, const uint64_t *__restrict__ voff, uint32_t ngeoms,
+            const uint32_t *__restrict__ idx, uint8_t *__restrict__ tri_hit, uint8_t *__restrict__ vert_hit)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t p = prim[i];
+    if (p == QSMRT_INVALID) return;
+    uint32_t g = geom ? geom[i] : 0u;
+    if (g >= ngeoms) return;
+    uint64_t t = goff[g] + p;
+    if (tri_hit) tri_hit[t] = 1;
+    if (vert_hit) { vert_hit[idx[3 * t]] = 1; vert_hit[idx[3 * t + 1]] = 1; vert_hit[idx[3 * t + 2]] = 1; }
+    (void)voff;
+}
+
+inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+} // namespace
+
+// --------------------------------------------------------------- launchers
+int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, float *t_hit, uint32_t *geom,
+                  uint32_t *prim, float *uv, float *nrm, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_cast_rays<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, t_hit, geom, prim,
+                                                            reinterpret_cast<float2 *>(uv), nrm);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_count_intersections<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_test_occlusions<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, tnear, tfar, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_raw_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_raw_count<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_raw_fill_sort(const SceneView &sc, const float *rays, uint64_t N, const int64_t *raw_off,
+                      HitRec *raw, int32_t *cnt, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_raw_fill_sort<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, raw_off, raw, cnt);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_list_compact(uint64_t N, const int64_t *raw_off, const HitRec *raw, const int64_t *splits,
+                     int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_list_compact<<<grid_for(N, 256), 256, 0, st>>>(N, raw_off, raw, splits, ray_ids, t_hit, geom, prim,
+                                                     reinterpret_cast<float2 *>(uv));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+size_t trv_scan_scratch_bytes(uint64_t n) { return ((n + SC_TILE - 1) / SC_TILE + 1) * sizeof(long long); }
+
+// out[0..n] = exclusive scan of in[0..n), out[n] = total
+int trv_exclusive_scan(const int32_t *in, uint64_t n, int64_t *out, void *scratch, cudaStream_t st)
+{
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(int64_t), st)); return 0; }
+    uint32_t ntiles = (uint32_t)((n + SC_TILE - 1) / SC_TILE);
+    long long *ts = reinterpret_cast<long long *>(scratch);
+    k_scan_tile_sums<<<ntiles, SC_THREADS, 0, st>>>(in, n, ts);
+    k_scan_tile_offsets<<<1, SC_THREADS, 0, st>>>(ts, ntiles);
+    k_scan_final<<<ntiles, SC_THREADS, 0, st>>>(in, n, ts, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_gen_parallel(float *rays, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+                     const float dv[3], const float dir[3], cudaStream_t st)
+{
+    uint64_t n = nu * nv;
+    if (n == 0) return 0;
+    f3 a = { o0[0], o0[1], o0[2] }, b = { du[0], du[1], du[2] }, c = { dv[0], dv[1], dv[2] }, d = { dir[0], dir[1], dir[2] };
+    k_gen_parallel<<<grid_for(n, 256), 256, 0, st>>>(rays, nu, nv, a, b, c, d);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_gen_pinhole(float *rays, uint32_t w, uint32_t h, const double minv[9], const double eye[3], cudaStream_t st)
+{
+    uint64_t n = (uint64_t)w * h;
+    if (n == 0) return 0;
+    PinholeArgs pa;
+    for (int k = 0; k < 9; ++k) pa.m[k] = minv[k];
+    for (int k = 0; k < 3; ++k) pa.eye[k] = eye[k];
+    k_gen_pinhole<<<grid_for(n, 256), 256, 0, st>>>(rays, w, h, pa);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_mark_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const uint64_t *goff,
+                  const uint64_t *voff, uint32_t ngeoms, const uint32_t *idx, uint8_t *tri_hit,
+                  uint8_t *vert_hit, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_mark_hits<<<grid_for(N, 256), 256, 0, st>>>(geom, prim, N, goff, voff, ngeoms, idx, tri_hit, vert_hit);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

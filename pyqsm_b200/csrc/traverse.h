@@ -1,0 +1,23 @@
+// traverse.h -- launchers of the traversal / scan / ray-generator kernels.
+#pragma once
+#include "common.cuh"
+
+struct HitRec { float t, u, v; uint32_t geom, prim; };   // 20-byte raw hit (list_intersections scratch)
+
+int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, float *t_hit, uint32_t *geom,
+                  uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
+int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st);
+int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st);
+int trv_raw_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st);
+int trv_raw_fill_sort(const SceneView &sc, const float *rays, uint64_t N, const int64_t *raw_off,
+                      HitRec *raw, int32_t *cnt, cudaStream_t st);
+int trv_list_compact(uint64_t N, const int64_t *raw_off, const HitRec *raw, const int64_t *splits,
+                     int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st);
+size_t trv_scan_scratch_bytes(uint64_t n);
+int trv_exclusive_scan(const int32_t *in, uint64_t n, int64_t *out, void *scratch, cudaStream_t st);
+int trv_gen_parallel(float *rays, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+                     const float dv[3], const float dir[3], cudaStream_t st);
+int trv_gen_pinhole(float *rays, uint32_t w, uint32_t h, const double minv[9], const double eye[3], cudaStream_t st);
+int trv_mark_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const uint64_t *goff,
+                  const uint64_t *voff, uint32_t ngeoms, const uint32_t *idx, uint8_t *tri_hit,
+                  uint8_t *vert_hit, cudaStream_t st);

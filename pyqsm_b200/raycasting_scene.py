@@ -1,0 +1,331 @@
+"""``RaycastingScene`` -- drop-in for ``open3d.t.geometry.RaycastingScene`` on the
+ray-casting path of wischmcj/pyQSM (``pyQSM/viz/ray_casting.py``).
+
+The reference binds the class at import (``ray_casting.py:8``,
+``from open3d.t.geometry import RaycastingScene as rcs``) and then uses
+``rcs()`` (:65,155,218,241,275,316), ``add_triangles`` (:66,156,219,242,276,
+317), ``create_rays_pinhole`` (:222,230,277,318), ``cast_rays`` (:223,231,279,
+319), ``list_intersections`` (:168) and ``compute_occupancy`` (:69).  Same
+names, argument meaning, result keys/dtypes/shapes and ``RuntimeError``s here;
+the arithmetic runs in ``libqsmrt.so`` (hand-written sm_100a kernels) through
+its C ABI with torch tensors as the zero-copy ray and hit buffers.
+
+Results are ``torch`` tensors: on the CPU by default (so ``.numpy()``,
+``.isfinite()``, mask indexing and ``.reshape`` behave as the reference
+expects), or left on the GPU with ``output_device='cuda'``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+INVALID_ID = 0xFFFFFFFF
+
+
+def _unwrap(x):
+    """numpy / torch / Open3D tensor / list -> numpy or torch, dtype preserved."""
+    if isinstance(x, (torch.Tensor, np.ndarray)):
+        return x
+    if hasattr(x, "numpy") and callable(x.numpy):          # open3d.core.Tensor
+        return x.numpy()
+    return None
+
+
+def _to_torch(x, want: torch.dtype, name: str, device: torch.device, strict=True) -> torch.Tensor:
+    y = _unwrap(x)
+    if y is None:                                           # python list / scalar: no dtype to check
+        y = np.asarray(x, dtype={torch.float32: np.float32, torch.uint32: np.uint32}[want])
+    if isinstance(y, np.ndarray):
+        if strict and y.dtype != {torch.float32: np.float32, torch.uint32: np.uint32}[want]:
+            raise RuntimeError(f"{name} has dtype {y.dtype}, but it must be {str(want).replace('torch.', '')}")
+        y = torch.from_numpy(np.ascontiguousarray(y))
+    else:
+        if strict and y.dtype != want:
+            raise RuntimeError(f"{name} has dtype {y.dtype}, but it must be {want}")
+    return y.to(device=device, dtype=want).contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+
+
+def _mesh_arrays(mesh):
+    """Duck-typed open3d.t.geometry.TriangleMesh: vertex['positions'] / triangle['indices']."""
+    def get(container, key):
+        if hasattr(container, key):
+            return getattr(container, key)
+        return container[key]
+    return get(mesh.vertex, "positions"), get(mesh.triangle, "indices")
+
+
+class RaycastingScene:
+    """Open3D-compatible ray casting scene running on one B200.
+
+    ``nthreads`` is accepted and ignored (Open3D: Embree threads).  ``device``
+    is the CUDA device (``None`` = torch's current CUDA device; Open3D-style
+    ``'CPU:0'`` is accepted and means "return CPU tensors").  There is no CPU
+    compute path.
+    """
+
+    INVALID_ID = INVALID_ID
+
+    def __init__(self, nthreads: int = 0, device=None, output_device=None):
+        self._L = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyqsm_b200.RaycastingScene needs a CUDA device (B200); there is no CPU fallback")
+        dev = None
+        if device is not None and not (isinstance(device, str) and device.upper().startswith("CPU")):
+            s = str(device).lower().replace("cuda:", "")
+            dev = int(s) if s.isdigit() else torch.device(device).index
+        if dev is None:
+            dev = torch.cuda.current_device()
+        self.device = torch.device("cuda", dev)
+        self.output_device = torch.device(output_device) if output_device is not None else torch.device("cpu")
+        if self.output_device.type == "cuda":
+            self.output_device = self.device
+        h = C.c_void_p()
+        _lib.check(self._L.qsmrt_scene_create(dev, C.byref(h)))
+        self._h = h
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.qsmrt_scene_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------- geometry
+    def add_triangles(self, vertex_positions, triangle_indices=None) -> int:
+        """``add_triangles(mesh)`` or ``add_triangles(vertex_positions, triangle_indices)``;
+        returns the geometry id (0, 1, ...).  The mesh is copied."""
+        if triangle_indices is None:
+            vertex_positions, triangle_indices = _mesh_arrays(vertex_positions)
+        v = _to_torch(vertex_positions, torch.float32, "vertex_positions", self.device)
+        t = _to_torch(triangle_indices, torch.uint32, "triangle_indices", self.device)
+        if v.ndim != 2 or v.shape[1] != 3:
+            raise RuntimeError(f"vertex_positions has shape {tuple(v.shape)}, but it must be (N, 3)")
+        if t.ndim != 2 or t.shape[1] != 3:
+            raise RuntimeError(f"triangle_indices has shape {tuple(t.shape)}, but it must be (N, 3)")
+        gid = C.c_uint32()
+        _lib.check(self._L.qsmrt_add_triangles(self._h, _ptr(v), v.shape[0], _ptr(t), t.shape[0], 1, C.byref(gid)))
+        return int(gid.value)
+
+    def commit(self) -> float:
+        """Build the LBVH now (queries do it lazily); returns the build time in ms."""
+        ms = C.c_float()
+        _lib.check(self._L.qsmrt_commit(self._h, self._stream(), C.byref(ms)))
+        return float(ms.value)
+
+    def stats(self) -> dict:
+        st = _lib.Stats()
+        _lib.check(self._L.qsmrt_get_stats(self._h, C.byref(st)))
+        d = {k: getattr(st, k) for k, _ in st._fields_ if k not in ("scene_lo", "scene_hi", "reserved")}
+        d["scene_lo"] = list(st.scene_lo)
+        d["scene_hi"] = list(st.scene_hi)
+        return d
+
+    # -------------------------------------------------------------- helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _rays(self, rays, name="rays"):
+        y = _unwrap(rays)
+        if y is None:
+            y = np.asarray(rays, dtype=np.float32)
+        if isinstance(y, np.ndarray):
+            if y.dtype != np.float32:
+                raise RuntimeError(f"{name} has dtype {y.dtype}, but it must be Float32")
+            y = torch.from_numpy(np.ascontiguousarray(y))
+        elif y.dtype != torch.float32:
+            raise RuntimeError(f"{name} has dtype {y.dtype}, but it must be Float32")
+        if y.ndim < 1 or y.shape[-1] != 6:
+            raise RuntimeError(f"{name} has shape {tuple(y.shape)}, but the last dimension must be 6")
+        return y
+
+    def _out(self, t: torch.Tensor) -> torch.Tensor:
+        if self.output_device.type == "cuda":
+            return t
+        return t.cpu()
+
+    # -------------------------------------------------------------- queries
+    def cast_rays(self, rays, nthreads: int = 0) -> dict:
+        """Closest hit per ray.  Keys: ``t_hit`` (inf on miss), ``geometry_ids``,
+        ``primitive_ids`` (INVALID_ID on miss), ``primitive_uvs``, ``primitive_normals``."""
+        r = self._rays(rays)
+        shp = tuple(r.shape[:-1])
+        n = int(np.prod(shp)) if shp else 1
+        if r.device.type == "cpu" and self.output_device.type == "cpu":
+            # host buffers in, host buffers out: chunked copy/compute overlap inside the C ABI
+            r = r.contiguous()
+            pin = n >= (1 << 16)
+            mk = lambda *s, dt: torch.empty(*s, dtype=dt, pin_memory=pin)
+            t_hit, gid, pid = mk(n, dt=torch.float32), mk(n, dt=torch.uint32), mk(n, dt=torch.uint32)
+            uv, nrm = mk(n, 2, dt=torch.float32), mk(n, 3, dt=torch.float32)
+            _lib.check(self._L.qsmrt_cast_rays_host(self._h, _ptr(r), n, _ptr(t_hit), _ptr(gid), _ptr(pid), _ptr(uv), _ptr(nrm)))
+        else:
+            with torch.cuda.device(self.device):
+                r = r.to(self.device).contiguous()
+                t_hit = torch.empty(n, dtype=torch.float32, device=self.device)
+                gid = torch.empty(n, dtype=torch.uint32, device=self.device)
+                pid = torch.empty(n, dtype=torch.uint32, device=self.device)
+                uv = torch.empty(n, 2, dtype=torch.float32, device=self.device)
+                nrm = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+                _lib.check(self._L.qsmrt_cast_rays(self._h, _ptr(r), n, _ptr(t_hit), _ptr(gid), _ptr(pid), _ptr(uv), _ptr(nrm), self._stream()))
+                t_hit, gid, pid, uv, nrm = map(self._out, (t_hit, gid, pid, uv, nrm))
+        return {
+            "t_hit": t_hit.reshape(shp), "geometry_ids": gid.reshape(shp), "primitive_ids": pid.reshape(shp),
+            "primitive_uvs": uv.reshape(shp + (2,)), "primitive_normals": nrm.reshape(shp + (3,)),
+        }
+
+    def count_intersections(self, rays, nthreads: int = 0) -> torch.Tensor:
+        """Number of intersections per ray (int32), Open3D dedup rule."""
+        r = self._rays(rays)
+        shp = tuple(r.shape[:-1])
+        with torch.cuda.device(self.device):
+            r = r.to(self.device).contiguous()
+            n = r.numel() // 6
+            out = torch.empty(n, dtype=torch.int32, device=self.device)
+            _lib.check(self._L.qsmrt_count_intersections(self._h, _ptr(r), n, _ptr(out), self._stream()))
+            return self._out(out).reshape(shp)
+
+    def test_occlusions(self, rays, tnear: float = 0.0, tfar: float = math.inf, nthreads: int = 0) -> torch.Tensor:
+        """True where any triangle is hit with tnear < t <= tfar."""
+        r = self._rays(rays)
+        shp = tuple(r.shape[:-1])
+        with torch.cuda.device(self.device):
+            r = r.to(self.device).contiguous()
+            n = r.numel() // 6
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+            _lib.check(self._L.qsmrt_test_occlusions(self._h, _ptr(r), n, float(tnear), float(tfar), _ptr(out), self._stream()))
+            return self._out(out.to(torch.bool)).reshape(shp)
+
+    def list_intersections(self, rays, nthreads: int = 0) -> dict:
+        """All intersections per ray in CSR form (Open3D >= 0.18).  Keys:
+        ``ray_splits`` [N+1], ``ray_ids``, ``t_hit``, ``geometry_ids``,
+        ``primitive_ids``, ``primitive_uvs``; hits of a ray are sorted by t."""
+        r = self._rays(rays)
+        with torch.cuda.device(self.device):
+            r = r.to(self.device).contiguous()
+            n = r.numel() // 6
+            splits = torch.empty(n + 1, dtype=torch.int64, device=self.device)
+            total = C.c_int64()
+            _lib.check(self._L.qsmrt_list_intersections_count(self._h, _ptr(r), n, _ptr(splits), C.byref(total), self._stream()))
+            k = int(total.value)
+            ray_ids = torch.empty(k, dtype=torch.int64, device=self.device)
+            t_hit = torch.empty(k, dtype=torch.float32, device=self.device)
+            gid = torch.empty(k, dtype=torch.uint32, device=self.device)
+            pid = torch.empty(k, dtype=torch.uint32, device=self.device)
+            uv = torch.empty(k, 2, dtype=torch.float32, device=self.device)
+            _lib.check(self._L.qsmrt_list_intersections_fill(self._h, _ptr(r), n, _ptr(splits), _ptr(ray_ids), _ptr(t_hit),
+                                                             _ptr(gid), _ptr(pid), _ptr(uv), self._stream()))
+            return {"ray_splits": self._out(splits), "ray_ids": self._out(ray_ids), "t_hit": self._out(t_hit),
+                    "geometry_ids": self._out(gid), "primitive_ids": self._out(pid), "primitive_uvs": self._out(uv)}
+
+    def compute_occupancy(self, query_points, nthreads: int = 0, nsamples: int = 1) -> torch.Tensor:
+        """1.0 inside / 0.0 outside (``ray_casting.py:69``): parity of the
+        intersection count of a ray from each point along (1,1,1), as Open3D's
+        ``ComputeOccupancy`` does for ``nsamples == 1``."""
+        if nsamples != 1:
+            raise RuntimeError("compute_occupancy: only nsamples == 1 is implemented")
+        p = _unwrap(query_points)
+        if p is None:
+            p = np.asarray(query_points, dtype=np.float32)
+        if isinstance(p, np.ndarray):
+            if p.dtype != np.float32:
+                raise RuntimeError(f"query_points has dtype {p.dtype}, but it must be Float32")
+            p = torch.from_numpy(np.ascontiguousarray(p))
+        if p.ndim < 1 or p.shape[-1] != 3:
+            raise RuntimeError(f"query_points has shape {tuple(p.shape)}, but the last dimension must be 3")
+        with torch.cuda.device(self.device):
+            p = p.to(self.device, torch.float32)
+            rays = torch.cat([p, torch.ones_like(p)], dim=-1)
+            saved, self.output_device = self.output_device, self.device
+            try:
+                cnt = self.count_intersections(rays)
+            finally:
+                self.output_device = saved
+            return self._out((cnt % 2 == 1).to(torch.float32))
+
+    def mark_hit_primitives(self, ans: dict):
+        """Device-side form of ``ray_casting.py:285-289``: uint8 flags of the
+        triangles (scene order) and vertices that own a closest hit."""
+        st = self.stats()
+        with torch.cuda.device(self.device):
+            gid = ans["geometry_ids"].to(self.device).contiguous().reshape(-1)
+            pid = ans["primitive_ids"].to(self.device).contiguous().reshape(-1)
+            self.commit()
+            nt = int(self.stats()["num_triangles"])
+            tri = torch.zeros(max(nt, 1), dtype=torch.uint8, device=self.device)
+            _lib.check(self._L.qsmrt_mark_hit_primitives(self._h, _ptr(gid), _ptr(pid), pid.numel(), _ptr(tri), None, self._stream()))
+            del st
+            return self._out(tri[:nt])
+
+    # ------------------------------------------------------- ray generators
+    @staticmethod
+    def create_rays_pinhole(*args, **kwargs) -> torch.Tensor:
+        """``create_rays_pinhole(intrinsic_matrix, extrinsic_matrix, width_px, height_px)`` or
+        ``create_rays_pinhole(fov_deg, center, eye, up, width_px, height_px)``
+        -> float32 ``[height_px, width_px, 6]`` (origins = eye, directions not
+        normalised), as Open3D's ``CreateRaysPinhole``.  ``device=`` keeps the
+        rays on the GPU; the default returns a CPU tensor like Open3D."""
+        device = kwargs.pop("device", None)
+        names_a = ("intrinsic_matrix", "extrinsic_matrix", "width_px", "height_px")
+        names_b = ("fov_deg", "center", "eye", "up", "width_px", "height_px")
+        if "fov_deg" in kwargs or len(args) == 6 or (len(args) > 0 and np.ndim(_np64(args[0])) == 0):
+            a = dict(zip(names_b, args)); a.update(kwargs)
+            w, h = int(a["width_px"]), int(a["height_px"])
+            K, E = _fov_to_matrices(float(a["fov_deg"]), _np64(a["center"]), _np64(a["eye"]), _np64(a["up"]), w, h)
+        else:
+            a = dict(zip(names_a, args)); a.update(kwargs)
+            w, h = int(a["width_px"]), int(a["height_px"])
+            K, E = _np64(a["intrinsic_matrix"]), _np64(a["extrinsic_matrix"])
+            if K.shape != (3, 3):
+                raise RuntimeError(f"intrinsic_matrix has shape {K.shape}, but it must be (3, 3)")
+            if E.shape != (4, 4):
+                raise RuntimeError(f"extrinsic_matrix has shape {E.shape}, but it must be (4, 4)")
+        L = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("create_rays_pinhole needs a CUDA device; there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None or torch.device(device).type != "cuda" \
+            else torch.device(device)
+        with torch.cuda.device(dev):
+            rays = torch.empty(h, w, 6, dtype=torch.float32, device=dev)
+            Kc = (C.c_double * 9)(*np.ascontiguousarray(K).reshape(-1))
+            Ec = (C.c_double * 16)(*np.ascontiguousarray(E).reshape(-1))
+            _lib.check(L.qsmrt_gen_pinhole_rays(_ptr(rays), w, h, Kc, Ec, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        if device is not None and torch.device(device).type == "cuda":
+            return rays
+        return rays.cpu()
+
+
+def _np64(x):
+    y = _unwrap(x)
+    if isinstance(y, torch.Tensor):
+        y = y.detach().cpu().numpy()
+    return np.asarray(x if y is None else y, dtype=np.float64)
+
+
+def _fov_to_matrices(fov_deg, center, eye, up, w, h):
+    """Open3D CreateRaysPinhole(fov_deg, center, eye, up, w, h): focal length
+    0.5*w/tan(0.5*fov); camera rows R2 = normalize(center-eye),
+    R0 = normalize(up x R2), R1 = R2 x R0; t = -R eye."""
+    f = 0.5 * w / math.tan(0.5 * math.radians(fov_deg))
+    K = np.array([[f, 0, 0.5 * w], [0, f, 0.5 * h], [0, 0, 1]], dtype=np.float64)
+    R = np.zeros((3, 3))
+    R[1] = up / np.linalg.norm(up)
+    R[2] = center - eye
+    R[2] /= np.linalg.norm(R[2])
+    R[0] = np.cross(R[1], R[2])
+    R[0] /= np.linalg.norm(R[0])
+    R[1] = np.cross(R[2], R[0])
+    E = np.eye(4)
+    E[:3, :3] = R
+    E[:3, 3] = -R @ eye
+    return K, E

@@ -1,0 +1,70 @@
+"""Shared checker for tests/golden/kat.json (analytic vectors)."""
+import json
+import math
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RTOL = 1e-5      # north_star: t_hit and normals within 1e-5 relative
+
+
+def load_kats():
+    with open(os.path.join(HERE, "golden", "kat.json")) as f:
+        return json.load(f)
+
+
+def _num(x):
+    a = np.array([[math.inf if v == "inf" else v for v in row] if isinstance(row, list) else (math.inf if row == "inf" else row)
+                  for row in x], dtype=np.float64)
+    return a
+
+
+def _np(x):
+    return x.numpy() if hasattr(x, "numpy") else np.asarray(x)
+
+
+def check_kat(kat, scene_factory):
+    """scene_factory() -> object with the RaycastingScene query API."""
+    if "mesh" not in kat:
+        return
+    s = scene_factory()
+    gid = s.add_triangles(np.asarray(kat["mesh"]["v"], np.float32), np.asarray(kat["mesh"]["t"], np.uint32))
+    assert gid == 0
+    rays = np.asarray(kat["rays"], np.float32)
+    if "cast" in kat:
+        ans = s.cast_rays(rays)
+        exp = kat["cast"]
+        t = _np(ans["t_hit"]).astype(np.float64)
+        et = _num(exp["t_hit"])
+        assert np.array_equal(np.isfinite(t), np.isfinite(et)), (kat["name"], t, et)
+        m = np.isfinite(et)
+        np.testing.assert_allclose(t[m], et[m], rtol=RTOL, err_msg=kat["name"])
+        assert np.all(np.isposinf(t[~m]))
+        for key in ("geometry_ids", "primitive_ids"):
+            if key in exp:
+                assert np.array_equal(_np(ans[key]).astype(np.int64), np.asarray(exp[key], np.int64)), (kat["name"], key)
+        if "primitive_uvs" in exp:
+            np.testing.assert_allclose(_np(ans["primitive_uvs"]), np.asarray(exp["primitive_uvs"]), rtol=RTOL, atol=1e-7)
+        if "primitive_normals" in exp:
+            np.testing.assert_allclose(_np(ans["primitive_normals"]), np.asarray(exp["primitive_normals"]), rtol=RTOL, atol=1e-7)
+        # hits are misses-or-valid: ids are INVALID exactly on misses, uv/normals zero there
+        miss = ~np.isfinite(t)
+        assert np.all(_np(ans["primitive_ids"])[miss] == 0xFFFFFFFF)
+        assert np.all(_np(ans["geometry_ids"])[miss] == 0xFFFFFFFF)
+        assert np.all(_np(ans["primitive_uvs"])[miss] == 0) and np.all(_np(ans["primitive_normals"])[miss] == 0)
+    if "count" in kat:
+        c = _np(s.count_intersections(rays))
+        assert c.dtype == np.int32
+        assert c.tolist() == kat["count"], (kat["name"], c.tolist())
+    if "occluded" in kat:
+        o = _np(s.test_occlusions(rays))
+        assert o.tolist() == kat["occluded"], (kat["name"], o.tolist())
+    if "list" in kat:
+        l = s.list_intersections(rays)
+        assert _np(l["ray_splits"]).tolist() == kat["list"]["ray_splits"], kat["name"]
+        np.testing.assert_allclose(_np(l["t_hit"]), np.asarray(kat["list"]["t_hit"]), rtol=RTOL, err_msg=kat["name"])
+        k = len(kat["list"]["t_hit"])
+        assert _np(l["ray_ids"]).shape == (k,) and _np(l["primitive_uvs"]).shape == (k, 2)
+        splits = _np(l["ray_splits"])
+        assert np.array_equal(_np(l["ray_ids"]), np.repeat(np.arange(len(rays)), np.diff(splits)))
