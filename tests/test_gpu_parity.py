@@ -1,0 +1,300 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through
+the C ABI / RaycastingScene against the CPU oracle on identical inputs.
+Bit-exact for hit/miss, ids, counts, and (because the arithmetic is shared
+op for op) for t/uv/normals too; the north_star tolerance of 1e-5 relative
+on t and normals is asserted as the contract."""
+import numpy as np
+import pytest
+import torch
+
+from kat_util import check_kat, load_kats, RTOL
+from pyqsm_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+KATS = load_kats()
+
+
+@pytest.fixture(scope="module")
+def RS():
+    from pyqsm_b200 import RaycastingScene
+    return RaycastingScene
+
+
+def _np(x):
+    return x.numpy() if hasattr(x, "numpy") else np.asarray(x)
+
+
+def assert_cast_equal(g, o, flags=None, what=""):
+    """GPU dict vs oracle dict.  Returns number of flagged mismatching rays."""
+    gp, op_ = _np(g["primitive_ids"]).reshape(-1), o["primitive_ids"].reshape(-1)
+    gg, og = _np(g["geometry_ids"]).reshape(-1), o["geometry_ids"].reshape(-1)
+    bad = (gp != op_) | (gg != og)
+    if bad.any():
+        assert flags is not None and np.all(flags.reshape(-1)[bad] != 0), \
+            f"{what}: {bad.sum()} id mismatches outside the edge-flagged set"
+    ok = ~bad
+    gt, ot = _np(g["t_hit"]).reshape(-1)[ok], o["t_hit"].reshape(-1)[ok]
+    assert np.array_equal(np.isfinite(gt), np.isfinite(ot))
+    m = np.isfinite(ot)
+    np.testing.assert_allclose(gt[m], ot[m], rtol=RTOL)
+    np.testing.assert_allclose(_np(g["primitive_normals"]).reshape(-1, 3)[ok], o["primitive_normals"].reshape(-1, 3)[ok], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(_np(g["primitive_uvs"]).reshape(-1, 2)[ok], o["primitive_uvs"].reshape(-1, 2)[ok], rtol=1e-4, atol=1e-6)
+    # the arithmetic is shared op for op, so in fact everything is bit-identical
+    assert np.array_equal(gt, ot), f"{what}: t_hit not bit-identical"
+    assert np.array_equal(_np(g["primitive_uvs"]).reshape(-1, 2)[ok], o["primitive_uvs"].reshape(-1, 2)[ok])
+    assert np.array_equal(_np(g["primitive_normals"]).reshape(-1, 3)[ok], o["primitive_normals"].reshape(-1, 3)[ok])
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("kat", [k for k in KATS if "mesh" in k], ids=lambda k: k["name"])
+def test_golden_vectors_gpu(RS, kat):
+    check_kat(kat, RS)
+
+
+def test_pinhole_kat(RS):
+    kat = [k for k in KATS if k["name"] == "kat8_pinhole"][0]
+    rays = RS.create_rays_pinhole(**kat["pinhole"])
+    assert tuple(rays.shape) == (2, 4, 6) and rays.dtype == torch.float32
+    np.testing.assert_allclose(rays[..., 3:].numpy(), np.asarray(kat["expect_dirs"]), rtol=1e-6, atol=1e-7)
+    assert np.all(rays[..., :3].numpy() == np.asarray(kat["expect_origin"], np.float32))
+    # intrinsic/extrinsic overload gives the same rays
+    from pyqsm_b200.raycasting_scene import _fov_to_matrices, _np64
+    p = kat["pinhole"]
+    K, E = _fov_to_matrices(p["fov_deg"], _np64(p["center"]), _np64(p["eye"]), _np64(p["up"]), p["width_px"], p["height_px"])
+    r2 = RS.create_rays_pinhole(K, E, p["width_px"], p["height_px"])
+    assert torch.equal(rays, r2)
+    # reference call shape: ray_casting.py:271-277 (fov 90, 1280x950)
+    r3 = RS.create_rays_pinhole(fov_deg=90, center=[0.5, 0.2, 3.0], eye=[0.5, 0.2, 13.0], up=[0, 1, -1], width_px=1280, height_px=950)
+    assert tuple(r3.shape) == (950, 1280, 6)
+    ctr = r3[475, 640, 3:].numpy()           # pixel centre (640.5, 475.5): half a pixel off the axis
+    assert abs(ctr[0]) < 2e-3 and ctr[2] < 0
+
+
+@pytest.fixture(scope="module")
+def c1(oracle_mod, RS):
+    """BASELINE config C1: 50k-triangle cylinder-QSM tree, 1M parallel sun rays."""
+    v, t = syn.qsm_tree_mesh(seed=1)
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v, t)
+    g = RS(output_device="cuda")
+    g.add_triangles(v, t)
+    return v, t, o, g
+
+
+def test_c1_cast_rays_full(c1):
+    v, t, o, g = c1
+    assert t.shape[0] == 50000
+    grid = syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(45, 135), 1000, 1000)
+    rays = torch.from_numpy(syn.materialize_grid(*grid, 1000, 1000)).cuda()
+    ans = {k: a.cpu() for k, a in g.cast_rays(rays).items()}
+    ref = o.cast_rays(rays.cpu().numpy(), 1)
+    nbad = assert_cast_equal(ans, ref, flags=None, what="C1")
+    assert nbad == 0
+    assert 0.02 < np.isfinite(ref["t_hit"]).mean() < 0.5
+
+
+def test_c1_count_and_occlusion(c1):
+    v, t, o, g = c1
+    grid = syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(45, 135), 500, 500)
+    rays = syn.materialize_grid(*grid, 500, 500)
+    gc = g.count_intersections(torch.from_numpy(rays)).cpu().numpy()
+    oc = o.count_intersections(rays, 1)
+    assert gc.dtype == np.int32 and np.array_equal(gc, oc)
+    assert oc.max() >= 4
+    go = g.test_occlusions(torch.from_numpy(rays)).cpu().numpy()
+    assert np.array_equal(go, oc > 0)
+    go2 = g.test_occlusions(torch.from_numpy(rays), tnear=20.0, tfar=25.0).cpu().numpy()
+    assert np.array_equal(go2, o.test_occlusions(rays, 20.0, 25.0, mode=1))
+
+
+def test_c1_list_intersections(c1):
+    v, t, o, g = c1
+    rays = syn.random_rays(v.min(0), v.max(0), 20000, seed=5)
+    gl = {k: a.cpu().numpy() for k, a in g.list_intersections(rays).items()}
+    ol = o.list_intersections(rays, 1)
+    assert gl["ray_splits"].dtype == np.int64 and gl["ray_ids"].dtype == np.int64
+    assert gl["geometry_ids"].dtype == np.uint32 and gl["primitive_ids"].dtype == np.uint32
+    for k in ol:
+        assert np.array_equal(gl[k], ol[k]), k
+    assert ol["ray_splits"][-1] > 1000
+
+
+def test_c1_vs_brute_force_subsample(c1):
+    """GPU BVH traversal against the oracle's brute force (ground truth)."""
+    v, t, o, g = c1
+    rays = np.concatenate([syn.random_rays(v.min(0), v.max(0), 6000, seed=11),
+                           syn.materialize_grid(*syn.parallel_ray_grid(v.min(0), v.max(0), (0, 0, -1), 64, 64), 64, 64)])
+    ans = {k: a.cpu() for k, a in g.cast_rays(rays).items()}
+    ref = o.cast_rays(rays, 0)
+    flags = o.edge_flags(rays, mode=1)
+    assert_cast_equal(ans, ref, flags, "C1-brute")
+    assert np.array_equal(g.count_intersections(rays).cpu().numpy(), o.count_intersections(rays, 0))
+
+
+def test_builder_matches_oracle(c1):
+    """LBVH builder parity: sorted Morton keys, ordering, Karras topology and
+    refit boxes are bit-identical to the oracle's canonical LBVH."""
+    import ctypes as C
+    from pyqsm_b200 import _lib
+    v, t, o, g = c1
+    n = t.shape[0]
+    keys = np.empty(n, np.uint64)
+    order = np.empty(n, np.uint32)
+    nodes = np.empty((2 * n - 1, 8), np.float32)
+    _lib.check(g._L.qsmrt_debug_get_build(g._h, keys.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p),
+                                          nodes.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(keys, o.sorted_keys())
+    assert np.all(np.diff(keys.astype(np.uint64)) >= 0) or np.all(keys[1:] >= keys[:-1])
+    assert np.array_equal(order, o.sorted_order())
+    olo, ohi, oleft, oright = o.nodes()
+    ni = nodes.view(np.int32)
+    left, right = ni[: n - 1, 3].copy(), ni[: n - 1, 7].copy()
+    # unified index space -> oracle's ~leaf encoding
+    conv = lambda c: np.where(c >= n - 1, ~(c - (n - 1)), c)
+    assert np.array_equal(conv(left), oleft) and np.array_equal(conv(right), oright)
+    assert np.array_equal(nodes[: n - 1, 0:3], olo) and np.array_equal(nodes[: n - 1, 4:7], ohi)
+    st = g.stats()
+    assert st["num_triangles"] == n and abs(st["box_pad"] - o.box_pad()) == 0
+    lo, hi = o.scene_bounds()
+    assert np.array_equal(np.asarray(st["scene_lo"], np.float32), lo) and np.array_equal(np.asarray(st["scene_hi"], np.float32), hi)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_soup_vs_brute(RS, oracle_mod, seed):
+    """Random triangle soups with slivers, duplicates, degenerates, shared edges, two geometries."""
+    rng = np.random.default_rng(seed)
+    nv, nt = 300, 900
+    v = rng.uniform(-2, 2, size=(nv, 3)).astype(np.float32)
+    t = rng.integers(0, nv, size=(nt, 3)).astype(np.uint32)
+    t[0] = (5, 5, 9)
+    t[1] = t[2]
+    v2, t2 = syn.box_mesh((-1, -1, -1), (1, 1, 1))
+    o = oracle_mod.OracleScene()
+    g = RS()
+    for s in (o, g):
+        assert s.add_triangles(v, t) == 0
+        assert s.add_triangles(v2, t2) == 1
+    rays = np.concatenate([syn.random_rays((-2, -2, -2), (2, 2, 2), 8000, seed=seed + 100),
+                           syn.materialize_grid(*syn.parallel_ray_grid((-2, -2, -2), (2, 2, 2), (0, 0, -1), 50, 50, 0.0), 50, 50)])
+    ref = o.cast_rays(rays, 0)
+    flags = o.edge_flags(rays, mode=0)
+    ans = g.cast_rays(rays)
+    assert_cast_equal(ans, ref, flags, f"soup{seed}")
+    gc = g.count_intersections(rays).numpy()
+    oc = o.count_intersections(rays, 0)
+    bad = gc != oc
+    assert np.all(flags[bad] != 0)
+    assert oc.max() > 24, "soup should overflow the in-register hit set"   # exercises the slow exact path
+    assert bad.sum() == 0
+    gl = {k: a.numpy() for k, a in g.list_intersections(rays).items()}
+    ol = o.list_intersections(rays, 0)
+    for k in ol:
+        assert np.array_equal(gl[k], ol[k]), k
+
+
+def test_edge_cases(RS):
+    s = RS()
+    rays = np.array([[0, 0, 0, 0, 0, 1], [1, 1, 1, 1, 0, 0]], np.float32)
+    a = s.cast_rays(rays)                                         # empty scene: all miss
+    assert torch.all(torch.isinf(a["t_hit"])) and a["primitive_ids"].numpy().tolist() == [0xFFFFFFFF] * 2
+    assert s.count_intersections(rays).tolist() == [0, 0]
+    assert s.test_occlusions(rays).tolist() == [False, False]
+    l = s.list_intersections(rays)
+    assert l["ray_splits"].tolist() == [0, 0, 0] and l["t_hit"].numel() == 0
+    v, t = syn.box_mesh()
+    s.add_triangles(v, t)
+    bad = np.array([[np.nan, 0.5, -1, 0, 0, 1], [0.5, 0.5, -1, 0, np.nan, 1], [0.5, 0.5, -1, 0, 0, 0]], np.float32)
+    a = s.cast_rays(bad)
+    assert torch.all(torch.isinf(a["t_hit"])) and s.count_intersections(bad).tolist() == [0, 0, 0]
+    # zero rays, and leading shapes are preserved
+    z = s.cast_rays(np.zeros((0, 6), np.float32))
+    assert z["t_hit"].shape == (0,) and z["primitive_uvs"].shape == (0, 2)
+    r3 = np.zeros((3, 5, 6), np.float32)
+    r3[..., 0:2] = 0.4
+    r3[..., 2] = -1
+    r3[..., 5] = 1
+    a = s.cast_rays(r3)
+    assert a["t_hit"].shape == (3, 5) and a["primitive_normals"].shape == (3, 5, 3) and torch.all(a["t_hit"] == 1)
+    assert s.count_intersections(r3).shape == (3, 5) and torch.all(s.count_intersections(r3) == 2)
+    # Open3D error behaviour: dtype / shape
+    with pytest.raises(RuntimeError):
+        s.cast_rays(np.zeros((4, 6), np.float64))
+    with pytest.raises(RuntimeError):
+        s.cast_rays(np.zeros((4, 5), np.float32))
+    with pytest.raises(RuntimeError):
+        s.add_triangles(v, t.astype(np.int64))
+    with pytest.raises(RuntimeError):
+        s.add_triangles(v, np.array([[0, 1, 99]], np.uint32))
+    # single triangle scene
+    s1 = RS()
+    s1.add_triangles(np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32))
+    assert s1.cast_rays(np.array([[0.2, 0.1, 1, 0, 0, -1]], np.float32))["t_hit"].item() == 1.0
+
+
+def test_host_path_equals_device_path(c1, RS):
+    """qsmrt_cast_rays_host (chunked, 3 streams) == qsmrt_cast_rays on resident buffers."""
+    v, t, o, g = c1
+    h = RS()                       # CPU outputs
+    h.add_triangles(v, t)
+    grid = syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(30, 10), 1500, 1500)   # 2.25M rays: 3 chunks
+    rays = syn.materialize_grid(*grid, 1500, 1500)
+    a = h.cast_rays(rays)
+    b = g.cast_rays(torch.from_numpy(rays).cuda())
+    for k in a:
+        assert a[k].device.type == "cpu"
+        assert torch.equal(a[k], b[k].cpu()), k
+
+
+def test_reference_call_patterns(RS):
+    """The call shapes of pyQSM/viz/ray_casting.py run unchanged against the replacement."""
+    from pyqsm_b200.mesh import TriangleMesh
+    v, t = syn.qsm_tree_mesh(seed=2, n_cylinders=40)
+    mesh = TriangleMesh(v, t)
+    rcs = RS
+    # raycast_to_pcd, ray_casting.py:315-322
+    scene = rcs()
+    scene.add_triangles(mesh)
+    center = mesh.get_center().numpy()
+    cfg = {'fov_deg': 90, 'center': mesh.get_center(), 'eye': [center[0], center[1], center[2] + 10], 'up': [0, 1, -1],
+           'width_px': 640, 'height_px': 480}
+    rays = rcs.create_rays_pinhole(**cfg)
+    ans = scene.cast_rays(rays)
+    intersecting_rays = ans['t_hit'].isfinite()
+    hits = rays[intersecting_rays]
+    points = hits[:, :3] + hits[:, 3:] * ans['t_hit'][intersecting_rays].reshape((-1, 1))
+    assert points.shape[1] == 3 and points.shape[0] > 100
+    # cast_rays surf_2d branch, ray_casting.py:285-289
+    hit_triangle_ids = ans['primitive_ids'][intersecting_rays].numpy()
+    hit_tris = np.asarray(t)[hit_triangle_ids]
+    assert hit_tris.shape[1] == 3
+    flags = scene.mark_hit_primitives(ans).numpy()
+    assert np.array_equal(np.nonzero(flags)[0], np.unique(hit_triangle_ids))
+    # sparse_cast_w_intersections, ray_casting.py:155-180
+    scene = rcs()
+    mesh_id = scene.add_triangles(mesh)
+    assert mesh_id == 0
+    bb_min = mesh.vertex['positions'].min(dim=0).numpy()
+    bb_max = mesh.vertex['positions'].max(dim=0).numpy()
+    x, y = np.linspace(bb_min, bb_max, num=10)[:, :2].T
+    xv, yv = np.meshgrid(x, y)
+    orig = np.stack([xv, yv, np.full_like(xv, bb_min[2] - 1)], axis=-1).reshape(-1, 3)
+    dest = orig + np.full(orig.shape, (0, 0, 2 + bb_max[2] - bb_min[2]), dtype=np.float32)
+    rays = np.concatenate([orig, dest - orig], axis=-1).astype(np.float32)
+    lx = scene.list_intersections(rays)
+    lx = {k: v_.numpy() for k, v_ in lx.items()}
+    vv = mesh.vertex['positions'].numpy()
+    tt = mesh.triangle['indices'].numpy()
+    tidx = lx['primitive_ids']
+    uv = lx['primitive_uvs']
+    w = 1 - np.sum(uv, axis=1)
+    c_arr = vv[tt[tidx, 1].flatten(), :] * uv[:, 0][:, None] + vv[tt[tidx, 2].flatten(), :] * uv[:, 1][:, None] + \
+        vv[tt[tidx, 0].flatten(), :] * w[:, None]
+    c_ref = rays[lx['ray_ids']][:, :3] + rays[lx['ray_ids']][:, 3:] * lx['t_hit'][..., None]
+    assert len(c_arr) > 0
+    np.testing.assert_allclose(c_arr, c_ref, atol=1e-4)
+    # get_points_inside_mesh, ray_casting.py:53-71: occupancy of a closed cylinder
+    cv, ct = syn.cylinder_mesh(1.0, 2.0)
+    scene = rcs()
+    scene.add_triangles(TriangleMesh(cv, ct))
+    q = np.array([[0, 0, 0], [0.5, 0.2, 0.9], [2, 0, 0], [0, 0, 1.5]], np.float32)
+    assert scene.compute_occupancy(q).tolist() == [1.0, 1.0, 0.0, 0.0]
