@@ -85,7 +85,8 @@ int qsmrt_cast_rays_host(qsmrt_scene *scene, const float *rays_host, uint64_t N,
 
 /* scene.count_intersections(rays)  -- the engine under list_intersections
  * (ray_casting.py:168) and compute_occupancy (:69).  counts[N] int32.
- * Synchronises only when a ray overflows the in-register hit set. */
+ * Never synchronises: a ray with more distinct hits than the in-register set
+ * holds is finished exactly by the same thread (one traversal per hit). */
 int qsmrt_count_intersections(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
                               int32_t *counts, void *stream);
 
@@ -125,6 +126,13 @@ int qsmrt_gen_pinhole_rays(float *rays_dev, uint32_t width_px, uint32_t height_p
 int qsmrt_mark_hit_primitives(qsmrt_scene *scene, const uint32_t *geometry_ids,
                               const uint32_t *primitive_ids, uint64_t N,
                               uint8_t *tri_hit, uint8_t *vert_hit, void *stream);
+
+/* Per-triangle exposure: tri_counts[t] += number of rays whose closest hit is
+ * triangle t (scene order: geometry offsets + primitive id).  The reduction
+ * the sun-sweep driver keeps on the device instead of 32 B/ray of results. */
+int qsmrt_accumulate_hits(qsmrt_scene *scene, const uint32_t *geometry_ids,
+                          const uint32_t *primitive_ids, uint64_t N,
+                          uint32_t *tri_counts, void *stream);
 
 int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
 

@@ -338,9 +338,22 @@ k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ 
               TNode *__restrict__ tn, unsigned long long *__restrict__ counters)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int2 r = range[i];
-    if (i != 0 && (r.y - r.x + 1) <= QSMRT_LEAF_MAX) return;     // folded into a leaf above
+    bool live = i < n - 1;
+    int2 r = live ? range[i] : make_int2(0, 0);
+    if (live && i != 0 && (r.y - r.x + 1) <= QSMRT_LEAF_MAX) live = false;     // folded into a leaf above
+    // statistics: one atomic per warp, not per thread
+    unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+    int nleaf = 0;
+    if (live) {
+        BNode me0 = bn[i];
+        nleaf = (child_ref(me0.left, n, range) < 0) + (child_ref(me0.right, n, range) < 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) nleaf += __shfl_xor_sync(0xFFFFFFFFu, nleaf, o);
+    if ((threadIdx.x & 31) == 0 && m) {
+        atomicAdd(&counters[0], (unsigned long long)__popc(m));
+        atomicAdd(&counters[1], (unsigned long long)nleaf);
+    }
+    if (!live) return;
     BNode me = bn[i];
     BNode c0 = bn[me.left], c1 = bn[me.right];
     TNode o;
@@ -350,8 +363,6 @@ k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ 
     int r0 = child_ref(me.left, n, range), r1 = child_ref(me.right, n, range);
     o.d = make_int4(r0, r1, 0, 0);
     tn[i] = o;
-    atomicAdd(&counters[0], 1ull);
-    atomicAdd(&counters[1], (unsigned long long)((r0 < 0) + (r1 < 0)));
 }
 
 // single-triangle scene: one node, one real child, one empty (inverted) box

@@ -450,6 +450,17 @@ int qsmrt_mark_hit_primitives(qsmrt_scene *s, const uint32_t *geom, const uint32
     return trv_mark_hits(geom, prim, N, s->goff, s->voff, (uint32_t)s->geoms.size(), s->idx, tri_hit, vert_hit, st);
 }
 
+int qsmrt_accumulate_hits(qsmrt_scene *s, const uint32_t *geom, const uint32_t *prim, uint64_t N,
+                          uint32_t *tri_counts, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (!prim || !tri_counts) FAIL("null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    if (s->ntris == 0) return 0;
+    return trv_accumulate_hits(geom, prim, N, s->goff, (uint32_t)s->geoms.size(), tri_counts, st);
+}
+
 int qsmrt_get_stats(qsmrt_scene *s, qsmrt_stats *out)
 {
     if (!s || !out) FAIL("null pointer");

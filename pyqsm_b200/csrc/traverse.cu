@@ -481,6 +481,19 @@ k_mark_hits(const uint32_t *__restrict__ geom, const uint32_t *__restrict__ prim
     (void)voff;
 }
 
+__global__ void __launch_bounds__(256)
+k_accumulate_hits(const uint32_t *__restrict__ geom, const uint32_t *__restrict__ prim, uint64_t N,
+                  const uint64_t *__restrict__ goff, uint32_t ngeoms, uint32_t *__restrict__ tri_counts)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t p = prim[i];
+    if (p == QSMRT_INVALID) return;
+    uint32_t g = geom ? geom[i] : 0u;
+    if (g >= ngeoms) return;
+    atomicAdd(&tri_counts[goff[g] + p], 1u);
+}
+
 inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 } // namespace
@@ -583,6 +596,15 @@ int trv_mark_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const 
 {
     if (N == 0) return 0;
     k_mark_hits<<<grid_for(N, 256), 256, 0, st>>>(geom, prim, N, goff, voff, ngeoms, idx, tri_hit, vert_hit);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_accumulate_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const uint64_t *goff,
+                        uint32_t ngeoms, uint32_t *tri_counts, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_accumulate_hits<<<grid_for(N, 256), 256, 0, st>>>(geom, prim, N, goff, ngeoms, tri_counts);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -21,3 +21,5 @@ int trv_gen_pinhole(float *rays, uint32_t w, uint32_t h, const double minv[9], c
 int trv_mark_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const uint64_t *goff,
                   const uint64_t *voff, uint32_t ngeoms, const uint32_t *idx, uint8_t *tri_hit,
                   uint8_t *vert_hit, cudaStream_t st);
+int trv_accumulate_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const uint64_t *goff,
+                        uint32_t ngeoms, uint32_t *tri_counts, cudaStream_t st);
