@@ -217,7 +217,7 @@ def run_ours(args):
 
     def step(s):
         r = rays[s % nbuf]
-        _lib.check(L.qsmrt_cast_rays(scene._h, P(r), n, P(t_hit), P(gid), P(pid), P(uv), P(nrm), stream))
+        _lib.check(L.qsmrt_cast_rays_2d(scene._h, P(r), GRID, GRID, P(t_hit), P(gid), P(pid), P(uv), P(nrm), stream))
         _lib.check(L.qsmrt_accumulate_hits(scene._h, P(gid), P(pid), n, P(exposure), stream))
 
     for s in range(args.warmup):
@@ -233,7 +233,7 @@ def run_ours(args):
     ev[0].record()
     for s in range(args.steps):
         ev[1 + 2 * s].record()
-        _lib.check(L.qsmrt_cast_rays(scene._h, P(rays[(args.warmup + s) % nbuf]), n, P(t_hit), P(gid), P(pid), P(uv), P(nrm), stream))
+        _lib.check(L.qsmrt_cast_rays_2d(scene._h, P(rays[(args.warmup + s) % nbuf]), GRID, GRID, P(t_hit), P(gid), P(pid), P(uv), P(nrm), stream))
         ev[2 + 2 * s].record()
         _lib.check(L.qsmrt_accumulate_hits(scene._h, P(gid), P(pid), n, P(exposure), stream))
     if world > 1:

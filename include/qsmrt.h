@@ -77,6 +77,14 @@ int qsmrt_cast_rays(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
                     float *t_hit, uint32_t *geometry_ids, uint32_t *primitive_ids,
                     float *primitive_uvs, float *primitive_normals, void *stream);
 
+/* cast_rays for an image / grid shaped batch rays[height][width][6] (what
+ * create_rays_pinhole returns, ray_casting.py:222-223,277-279, and the
+ * parallel grids of :159-165): identical results, but warps take 8 x 4 pixel
+ * tiles instead of 32 consecutive rays, which keeps them coherent. */
+int qsmrt_cast_rays_2d(qsmrt_scene *scene, const float *rays_dev, uint32_t width, uint64_t height,
+                       float *t_hit, uint32_t *geometry_ids, uint32_t *primitive_ids,
+                       float *primitive_uvs, float *primitive_normals, void *stream);
+
 /* Same call with HOST buffers: chunks the batch and overlaps host->device,
  * traversal and device->host copies on three streams.  Synchronises. */
 int qsmrt_cast_rays_host(qsmrt_scene *scene, const float *rays_host, uint64_t N,
@@ -142,6 +150,10 @@ int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
  * 32-byte binary nodes (lo.xyz,left,hi.xyz,right; internal 0..T-2, leaves
  * after). */
 int qsmrt_debug_get_build(qsmrt_scene *scene, uint64_t *keys, uint32_t *order, void *nodes);
+
+/* Tuning hook for A/B measurements: 1 = plain per-thread loop, 2 = speculative
+ * while-while with parked leaves (default).  Results are identical. */
+int qsmrt_debug_set_variant(int variant);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ SYMBOLS = {
     "qsmrt_add_triangles": (C.c_int, [_vp, _vp, _u64, _vp, _u64, C.c_int, C.POINTER(C.c_uint32)]),
     "qsmrt_commit": (C.c_int, [_vp, _vp, C.POINTER(_f)]),
     "qsmrt_cast_rays": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qsmrt_cast_rays_2d": (C.c_int, [_vp, _vp, C.c_uint32, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qsmrt_cast_rays_host": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "qsmrt_count_intersections": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "qsmrt_test_occlusions": (C.c_int, [_vp, _vp, _u64, _f, _f, _vp, _vp]),
@@ -48,6 +49,7 @@ SYMBOLS = {
     "qsmrt_accumulate_hits": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp]),
     "qsmrt_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "qsmrt_debug_get_build": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),
 }
 
 

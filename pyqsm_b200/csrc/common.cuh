@@ -81,7 +81,7 @@ __device__ __forceinline__ bool mt_test(const float4 p0, const float4 p1, const 
     return ok;
 }
 
-struct Ray { f3 O, D; float idx, idy, idz; };
+struct Ray { f3 O, D; float idx, idy, idz, oodx, oody, oodz; };
 
 __device__ __forceinline__ float safe_inv(float d) {
     const float tiny = 8.271806125530277e-25f;   // 2^-80: 0 * inv is never NaN
@@ -96,5 +96,6 @@ __device__ __forceinline__ Ray load_ray(const float *__restrict__ rays, uint64_t
     Ray r;
     r.O = { a.x, a.y, b.x }; r.D = { b.y, c.x, c.y };
     r.idx = safe_inv(r.D.x); r.idy = safe_inv(r.D.y); r.idz = safe_inv(r.D.z);
+    r.oodx = r.O.x * r.idx; r.oody = r.O.y * r.idy; r.oodz = r.O.z * r.idz;
     return r;
 }

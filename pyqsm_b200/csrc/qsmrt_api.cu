@@ -309,7 +309,24 @@ int qsmrt_cast_rays(qsmrt_scene *s, const float *rays, uint64_t N, float *t_hit,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
     if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
-    return trv_cast_rays(view_of(s), rays, N, t_hit, geom, prim, uv, nrm, st);
+    return trv_cast_rays(view_of(s), rays, N, 0, t_hit, geom, prim, uv, nrm, st);
+}
+
+int qsmrt_cast_rays_2d(qsmrt_scene *s, const float *rays, uint32_t width, uint64_t height, float *t_hit, uint32_t *geom,
+                       uint32_t *prim, float *uv, float *nrm, void *stream)
+{
+    if (use_device(s) || check_rays(rays, (uint64_t)width * height)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
+    return trv_cast_rays(view_of(s), rays, (uint64_t)width * height, width, t_hit, geom, prim, uv, nrm, st);
+}
+
+int qsmrt_debug_set_variant(int variant)
+{
+    if (variant < 1 || variant > 3) FAIL("unknown traversal variant %d", variant);
+    g_trv_variant = variant;
+    return 0;
 }
 
 int qsmrt_cast_rays_host(qsmrt_scene *s, const float *rays, uint64_t N, float *t_hit, uint32_t *geom,
@@ -331,7 +348,7 @@ int qsmrt_cast_rays_host(qsmrt_scene *s, const float *rays, uint64_t N, float *t
         CUDA_TRY(cudaMemcpyAsync(hp.rays[b], rays + 6 * off, 6 * n * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
         CUDA_TRY(cudaEventRecord(hp.e_in[b], hp.s_in));
         CUDA_TRY(cudaStreamWaitEvent(hp.s_run, hp.e_in[b], 0));
-        if (trv_cast_rays(sv, hp.rays[b], n, t_hit ? hp.t[b] : nullptr, geom ? hp.g[b] : nullptr,
+        if (trv_cast_rays(sv, hp.rays[b], n, 0, t_hit ? hp.t[b] : nullptr, geom ? hp.g[b] : nullptr,
                           prim ? hp.p[b] : nullptr, uv ? hp.uv[b] : nullptr, nrm ? hp.nrm[b] : nullptr, hp.s_run))
             return 1;
         CUDA_TRY(cudaEventRecord(hp.e_run[b], hp.s_run));

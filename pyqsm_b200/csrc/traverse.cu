@@ -12,6 +12,7 @@
 // memory laid out [entry][thread] (bank-conflict free, no local-memory
 // traffic on the hot path) and spills to a local array only below depth
 // TR_SSTACK.  Nodes are fetched as four 16-byte loads, triangles as three.
+#include <algorithm>
 #include "common.cuh"
 #include "traverse.h"
 
@@ -96,6 +97,92 @@ __device__ __forceinline__ void traverse(const SceneView &sc, const Ray &r, Stac
     }
 }
 
+// ---- v2: speculative while-while (Aila & Laine 2009) -------------------------
+// ncu on v1 (profiles/r01_v1_*): 7-8 of 32 lanes active per instruction -- the
+// long leaf path ran with only the few lanes that happened to be at a leaf.
+// Here a lane that reaches a leaf parks it and keeps descending until every
+// lane of the warp holds a leaf; then all lanes run the triangle tests
+// together.  The slab test is the FMA form (t = lo*inv - O*inv, FMNMX3): in
+// position space its rounding moves a box face by <= ~1e-7 * max|coord|, far
+// inside the 2^-17 padding every leaf box carries, so it stays conservative.
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+}
+
+__device__ __forceinline__ bool slab_fma(float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                         const Ray &r, float tmax, float &tn)
+{
+    float x0 = fmaf(lox, r.idx, -r.oodx), x1 = fmaf(hix, r.idx, -r.oodx);
+    float y0 = fmaf(loy, r.idy, -r.oody), y1 = fmaf(hiy, r.idy, -r.oody);
+    float z0 = fmaf(loz, r.idz, -r.oodz), z1 = fmaf(hiz, r.idz, -r.oodz);
+    float tmin = fmaxf(fmax3(fminf(x0, x1), fminf(y0, y1), fminf(z0, z1)), 0.0f);
+    float tfar = fminf(fmin3(fmaxf(x0, x1), fmaxf(y0, y1), fmaxf(z0, z1)), tmax);
+    tn = tmin;
+    return tmin <= tfar;
+}
+
+constexpr int TR_SENTINEL = 0x7FFFFFFF;
+
+template <bool ORDERED, class V>
+__device__ __forceinline__ void traverse2(const SceneView &sc, const Ray &r, Stack &st, V &vis)
+{
+    st.sp = 0;
+    st.push(TR_SENTINEL);
+    int cur = 0;      // >= 0: inner node (or sentinel); < 0: leaf
+    int leaf = 0;     // < 0: a parked leaf waiting for the warp
+    while (cur != TR_SENTINEL) {
+        while ((unsigned)cur < (unsigned)TR_SENTINEL) {
+            float4 a, b, c; int4 d;
+            load_node(sc.nodes, cur, a, b, c, d);
+            float t0, t1;
+            const float tm = vis.tmax();
+            bool h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, tm, t0);
+            bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, tm, t1);
+            if (!(h0 | h1)) {
+                cur = st.pop();
+            } else {
+                cur = h0 ? d.x : d.y;
+                if (h0 & h1) {
+                    int far = d.y;
+                    if (ORDERED && t1 < t0) { far = cur; cur = d.y; }
+                    st.push(far);
+                }
+            }
+            if (cur < 0 && leaf >= 0) { leaf = cur; cur = st.pop(); }     // park the first leaf, keep going
+            if (!__any_sync(__activemask(), leaf >= 0)) break;            // every lane holds a leaf
+        }
+        while (leaf < 0) {
+            uint32_t ref = (uint32_t)~leaf;
+            if (vis.leaf(ref >> 2, (ref & 3u) + 1u)) return;
+            leaf = cur;                                                   // a second leaf reached meanwhile
+            if (cur < 0) cur = st.pop();
+        }
+    }
+}
+
+// 2-D tile mapping for image / grid shaped ray batches [rows][row_len]: a warp
+// takes an 8 x 4 tile instead of 32 consecutive rays of one row, which keeps
+// its rays in the same subtree longer.  Returns false for padding lanes.
+__device__ __forceinline__ bool ray_index(uint64_t N, uint32_t row_len, uint64_t &i)
+{
+    if (row_len == 0) {
+        i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+        return i < N;
+    }
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = blockIdx.x * (uint64_t)(TR_BLOCK / 32) + (threadIdx.x >> 5);
+    const uint32_t tiles_x = (row_len + 7u) >> 3;
+    const uint64_t ty = warp / tiles_x;
+    const uint32_t tx = (uint32_t)(warp - ty * tiles_x);
+    const uint32_t x = tx * 8u + (lane & 7u);
+    const uint64_t y = ty * 4u + (lane >> 3);
+    i = y * row_len + x;
+    return x < row_len && i < N;
+}
+
 // ------------------------------------------------------------ closest hit
 struct ClosestVis {
     const SceneView &sc; const Ray &r;
@@ -118,18 +205,22 @@ struct ClosestVis {
     }
 };
 
+template <int VARIANT>
 __global__ void __launch_bounds__(TR_BLOCK)
-k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N,
+k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t row_len,
             float *__restrict__ t_hit, uint32_t *__restrict__ geom, uint32_t *__restrict__ prim,
             float2 *__restrict__ uv, float *__restrict__ nrm)
 {
     __shared__ int sstack[TR_SSTACK * TR_BLOCK];
-    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
-    if (i >= N) return;
+    uint64_t i;
+    if (!ray_index(N, row_len, i)) return;
     Ray r = load_ray(rays, i);
     Stack st; st.s = sstack + threadIdx.x;
     ClosestVis vis{ sc, r, INFINITY, QSMRT_INVALID, QSMRT_INVALID, 0u };
-    if (sc.ntris) traverse<true>(sc, r, st, vis);
+    if (sc.ntris) {
+        if (VARIANT == 1) traverse<true>(sc, r, st, vis);
+        else traverse2<true>(sc, r, st, vis);
+    }
     if (t_hit) t_hit[i] = vis.t;
     if (geom) geom[i] = vis.geom;
     if (prim) prim[i] = vis.prim;
@@ -147,6 +238,172 @@ k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N,
         if (uv) uv[i] = make_float2(u, v);
         if (nrm) { nrm[3 * i] = nx; nrm[3 * i + 1] = ny; nrm[3 * i + 2] = nz; }
     }
+}
+
+// ---- v3: persistent, warp-uniform traversal ---------------------------------
+// Evidence (profiles/r01_v1_*): the per-thread loops spend half their issue
+// slots in leaf code with ~2.3 of 32 lanes active, and idle lanes of finished
+// rays wait for the slowest ray of the warp.  v3 keeps the whole warp on ONE
+// control path: every lane stays in the same loops and work is predicated,
+// phase changes are decided by full-mask votes, triangles are tested one per
+// lane per iteration, and lanes whose ray is finished are refilled from a
+// global cursor (ballot/popc compaction of the idle set) once REFILL lanes
+// are idle.  Lanes then only need a similar *mix* of work, not similar nodes.
+// The stack pointer lives in a register (the struct form kept it in local
+// memory), entries in shared memory [entry][thread] with a local spill.
+constexpr int TR_REFILL = 8;
+
+__device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uint32_t row_len, uint64_t &i)
+{
+    if (row_len == 0) { i = slot; return slot < N; }
+    const uint32_t lane = (uint32_t)(slot & 31u);
+    const uint64_t tile = slot >> 5;
+    const uint32_t tiles_x = (row_len + 7u) >> 3;
+    const uint64_t ty = tile / tiles_x;
+    const uint32_t tx = (uint32_t)(tile - ty * tiles_x);
+    const uint32_t x = tx * 8u + (lane & 7u);
+    const uint64_t y = ty * 4u + (lane >> 3);
+    i = y * row_len + x;
+    return x < row_len && i < N;
+}
+
+struct CastOut {
+    float *t_hit; uint32_t *geom, *prim; float2 *uv; float *nrm;
+};
+
+// MODE 0: closest hit (cast_rays).  MODE 1: any hit in (tnear, tfar] (test_occlusions).
+template <int MODE>
+__global__ void __launch_bounds__(TR_BLOCK)
+k_trace_persistent(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t row_len, uint64_t nslots,
+                   CastOut out, uint8_t *__restrict__ occluded, float tnear, float tfar_in,
+                   unsigned long long *__restrict__ cursor)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    int *const sbase = sstack + threadIdx.x;
+    int loc[TR_LSTACK];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+
+    Ray r;
+    float best_t = 0.0f; uint32_t best_geom = QSMRT_INVALID, best_prim = QSMRT_INVALID, best_tri = 0u;
+    uint64_t ray_i = 0;
+    bool have_ray = false, exhausted = false;
+    int cur = TR_SENTINEL, sp = 0;
+    uint32_t tri_i = 0, tri_end = 0;
+
+#define PUSH(v) do { if (sp < TR_SSTACK) sbase[sp * TR_BLOCK] = (v); else loc[sp - TR_SSTACK] = (v); ++sp; } while (0)
+#define POP(dst) do { --sp; (dst) = sp < TR_SSTACK ? sbase[sp * TR_BLOCK] : loc[sp - TR_SSTACK]; } while (0)
+#define PARK_LEAF() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; POP(cur); } while (0)
+
+    for (;;) {
+        // ---- retire finished rays, refill idle lanes
+        const bool idle = (cur == TR_SENTINEL) && (tri_i >= tri_end);
+        const unsigned im = __ballot_sync(FULL, idle);
+        if (im == FULL || (!exhausted && __popc(im) >= TR_REFILL)) {
+            if (idle && have_ray) {
+                have_ray = false;
+                if (MODE == 0) {
+                    if (out.t_hit) out.t_hit[ray_i] = best_t;
+                    if (out.geom) out.geom[ray_i] = best_geom;
+                    if (out.prim) out.prim[ray_i] = best_prim;
+                    if (out.uv || out.nrm) {
+                        float u = 0.0f, v = 0.0f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+                        if (best_prim != QSMRT_INVALID) {
+                            float4 p0, p1, p2;
+                            load_tri(sc.tris, best_tri, p0, p1, p2);
+                            MtHit h;
+                            mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h);
+                            u = __fdiv_rn(h.U, h.absDen); v = __fdiv_rn(h.V, h.absDen);
+                            float inv = __fdiv_rn(1.0f, __fsqrt_rn(f3dot(h.Ng, h.Ng)));
+                            nx = __fmul_rn(h.Ng.x, inv); ny = __fmul_rn(h.Ng.y, inv); nz = __fmul_rn(h.Ng.z, inv);
+                        }
+                        if (out.uv) out.uv[ray_i] = make_float2(u, v);
+                        if (out.nrm) { out.nrm[3 * ray_i] = nx; out.nrm[3 * ray_i + 1] = ny; out.nrm[3 * ray_i + 2] = nz; }
+                    }
+                } else {
+                    occluded[ray_i] = best_prim != QSMRT_INVALID ? 1 : 0;
+                }
+            }
+            if (exhausted) {
+                if (im == FULL) break;
+            } else {
+                const int need = __popc(im);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (unsigned long long)need);
+                base = __shfl_sync(FULL, base, 0);
+                exhausted = base + (unsigned long long)need >= nslots;
+                if (idle) {
+                    const uint64_t slot = base + __popc(im & lt);
+                    uint64_t i;
+                    if (slot < nslots && ray_index_of_slot(slot, N, row_len, i)) {
+                        r = load_ray(rays, i);
+                        ray_i = i; have_ray = true;
+                        best_t = MODE == 0 ? INFINITY : tfar_in;
+                        best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
+                        sbase[0] = TR_SENTINEL; sp = 1;
+                        cur = sc.ntris ? 0 : TR_SENTINEL;
+                        tri_i = tri_end = 0;
+                    }
+                }
+                continue;
+            }
+        }
+        // ---- inner-node phase: until every lane holds a leaf (or has nothing left)
+        for (;;) {
+            const bool inner = (unsigned)cur < (unsigned)TR_SENTINEL;
+            const bool parked = tri_i < tri_end;
+            if (!__any_sync(FULL, inner && !parked)) break;
+            if (inner) {
+                float4 a, b, c; int4 d;
+                load_node(sc.nodes, cur, a, b, c, d);
+                float t0, t1;
+                bool h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, best_t, t0);
+                bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, best_t, t1);
+                if (!(h0 | h1)) {
+                    POP(cur);
+                } else {
+                    cur = h0 ? d.x : d.y;
+                    if (h0 & h1) {
+                        int far = d.y;
+                        if (MODE == 0 && t1 < t0) { far = cur; cur = d.y; }
+                        PUSH(far);
+                    }
+                }
+                if (cur < 0 && !parked) PARK_LEAF();
+            }
+        }
+        // ---- triangle phase: one triangle per lane per iteration, drain parked leaves
+        for (;;) {
+            const bool has = tri_i < tri_end;
+            if (!__any_sync(FULL, has)) break;
+            if (has) {
+                float4 p0, p1, p2;
+                load_tri(sc.tris, tri_i, p0, p1, p2);
+                MtHit h;
+                if (MODE == 0) {
+                    if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                        float tt = __fdiv_rn(h.T, h.absDen);
+                        uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
+                        bool better = (tt < best_t) | ((tt == best_t) & ((pg < best_geom) | ((pg == best_geom) & (pp < best_prim))));
+                        if (better) { best_t = tt; best_geom = pg; best_prim = pp; best_tri = tri_i; }
+                    }
+                    ++tri_i;
+                    if (tri_i == tri_end && cur < 0) PARK_LEAF();
+                } else {
+                    if (mt_test(p0, p1, p2, r.O, r.D, tnear, tfar_in, h)) {
+                        best_prim = 0u; cur = TR_SENTINEL; tri_i = tri_end;       // occluded: drop the rest
+                    } else {
+                        ++tri_i;
+                        if (tri_i == tri_end && cur < 0) PARK_LEAF();
+                    }
+                }
+            }
+        }
+    }
+#undef PUSH
+#undef POP
+#undef PARK_LEAF
 }
 
 // ---------------------------------------------------------------- any hit
@@ -499,12 +756,71 @@ inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block -
 } // namespace
 
 // --------------------------------------------------------------- launchers
-int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, float *t_hit, uint32_t *geom,
+int g_trv_variant = 3;      // 1 = per-thread loop, 2 = speculative while-while, 3 = persistent warp-uniform
+
+// work cursors of the persistent kernels: a per-device ring so launches in flight never share one
+namespace {
+constexpr int CURSOR_RING = 256;
+unsigned long long *g_cursor_ring[64] = {};
+unsigned g_cursor_next[64] = {};
+int g_persistent_blocks[64][2] = {};
+
+int next_cursor(unsigned long long **out, cudaStream_t st)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { qsmrt_set_error("device index %d out of range", dev); return 1; }
+    if (!g_cursor_ring[dev]) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g_cursor_ring[dev]), CURSOR_RING * sizeof(unsigned long long)));
+    unsigned k = g_cursor_next[dev]++ % CURSOR_RING;
+    *out = g_cursor_ring[dev] + k;
+    CUDA_TRY(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
+    return 0;
+}
+
+template <int MODE> int persistent_grid(int *blocks)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!g_persistent_blocks[dev][MODE]) {
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_persistent<MODE>, TR_BLOCK, 0));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        g_persistent_blocks[dev][MODE] = per_sm * sms;
+    }
+    *blocks = g_persistent_blocks[dev][MODE];
+    return 0;
+}
+
+uint64_t slots_for(uint64_t N, uint32_t row_len)
+{
+    if (!row_len) return N;
+    uint64_t rows = N / row_len;
+    return (uint64_t)((row_len + 7u) / 8u) * ((rows + 3) / 4) * 32u;
+}
+} // namespace
+
+int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,
                   uint32_t *prim, float *uv, float *nrm, cudaStream_t st)
 {
     if (N == 0) return 0;
-    k_cast_rays<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, t_hit, geom, prim,
-                                                            reinterpret_cast<float2 *>(uv), nrm);
+    unsigned grid = grid_for(N, TR_BLOCK);
+    if (row_len) {
+        if (N % row_len) { qsmrt_set_error("ray count %llu is not a multiple of the row length %u", (unsigned long long)N, row_len); return 1; }
+        uint64_t rows = N / row_len, warps = (uint64_t)((row_len + 7u) / 8u) * ((rows + 3) / 4);
+        grid = (unsigned)((warps + TR_BLOCK / 32 - 1) / (TR_BLOCK / 32));
+    }
+    if (g_trv_variant == 3) {
+        unsigned long long *cursor = nullptr;
+        int blocks = 0;
+        if (next_cursor(&cursor, st) || persistent_grid<0>(&blocks)) return 1;
+        uint64_t nslots = slots_for(N, row_len);
+        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)blocks, (nslots + TR_BLOCK - 1) / TR_BLOCK);
+        CastOut o{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
+        k_trace_persistent<0><<<g, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, nslots, o, nullptr, 0.0f, INFINITY, cursor);
+    } else if (g_trv_variant == 1)
+        k_cast_rays<1><<<grid, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
+    else
+        k_cast_rays<2><<<grid, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

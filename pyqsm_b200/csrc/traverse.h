@@ -4,7 +4,8 @@
 
 struct HitRec { float t, u, v; uint32_t geom, prim; };   // 20-byte raw hit (list_intersections scratch)
 
-int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, float *t_hit, uint32_t *geom,
+extern int g_trv_variant;
+int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,
                   uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
 int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st);
 int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st);

@@ -155,9 +155,11 @@ class RaycastingScene:
         return t.cpu()
 
     # -------------------------------------------------------------- queries
-    def cast_rays(self, rays, nthreads: int = 0) -> dict:
+    def cast_rays(self, rays, nthreads: int = 0, grid_width: int = 0) -> dict:
         """Closest hit per ray.  Keys: ``t_hit`` (inf on miss), ``geometry_ids``,
-        ``primitive_ids`` (INVALID_ID on miss), ``primitive_uvs``, ``primitive_normals``."""
+        ``primitive_ids`` (INVALID_ID on miss), ``primitive_uvs``, ``primitive_normals``.
+        Rays shaped ``[H, W, 6]`` (or flat with ``grid_width=W``) are traversed in
+        8x4 tiles; the results are the same either way."""
         r = self._rays(rays)
         shp = tuple(r.shape[:-1])
         n = int(np.prod(shp)) if shp else 1
@@ -177,7 +179,13 @@ class RaycastingScene:
                 pid = torch.empty(n, dtype=torch.uint32, device=self.device)
                 uv = torch.empty(n, 2, dtype=torch.float32, device=self.device)
                 nrm = torch.empty(n, 3, dtype=torch.float32, device=self.device)
-                _lib.check(self._L.qsmrt_cast_rays(self._h, _ptr(r), n, _ptr(t_hit), _ptr(gid), _ptr(pid), _ptr(uv), _ptr(nrm), self._stream()))
+                width = int(grid_width) if grid_width else (int(shp[-1]) if len(shp) >= 2 else 0)
+                if width >= 8 and n % width == 0 and n // width >= 4:
+                    # image / grid shaped batch (create_rays_pinhole output): 8x4 ray tiles per warp
+                    _lib.check(self._L.qsmrt_cast_rays_2d(self._h, _ptr(r), width, n // width, _ptr(t_hit), _ptr(gid),
+                                                          _ptr(pid), _ptr(uv), _ptr(nrm), self._stream()))
+                else:
+                    _lib.check(self._L.qsmrt_cast_rays(self._h, _ptr(r), n, _ptr(t_hit), _ptr(gid), _ptr(pid), _ptr(uv), _ptr(nrm), self._stream()))
                 t_hit, gid, pid, uv, nrm = map(self._out, (t_hit, gid, pid, uv, nrm))
         return {
             "t_hit": t_hit.reshape(shp), "geometry_ids": gid.reshape(shp), "primitive_ids": pid.reshape(shp),
