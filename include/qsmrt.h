@@ -46,7 +46,7 @@ typedef struct qsmrt_stats {
     float    box_pad;            /* absolute AABB padding */
     float    scene_lo[3], scene_hi[3];
     uint32_t leaf_max;           /* triangles per collapsed leaf */
-    uint32_t reserved;
+    uint32_t bvh_height;         /* binary LBVH height (bounds the traversal stack) */
 } qsmrt_stats;
 
 const char *qsmrt_last_error(void);
@@ -152,8 +152,23 @@ int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
 int qsmrt_debug_get_build(qsmrt_scene *scene, uint64_t *keys, uint32_t *order, void *nodes);
 
 /* Tuning hook for A/B measurements: 1 = plain per-thread loop, 2 = speculative
- * while-while with parked leaves (default).  Results are identical. */
+ * while-while, 3 = persistent two-phase, 4 = persistent one-step scheduler
+ * (default).  Results are identical. */
 int qsmrt_debug_set_variant(int variant);
+
+/* Scheduler tuning of the persistent kernel (variant 4) and its fetch
+ * counters: with counters != 0 every cast_rays launch counts the node records
+ * and triangles it actually fetched; qsmrt_debug_get_counters reads the last
+ * launch's totals (synchronises). */
+int qsmrt_debug_set_tuning(int refill_thresh, int want_thresh, int speculate, int counters);
+int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out);
+/* All 16 counters of the last counted launch: [0] node fetches, [1] triangle
+ * tests, [2] node-phase iterations, [3..6] lanes per iteration that step /
+ * are idle / hold a second leaf / finished descending, [7] triangle-phase
+ * iterations, [8] lanes testing a triangle. */
+int qsmrt_debug_get_census(uint64_t out[16]);
+/* Triangles per collapsed leaf (1..4) used by the next qsmrt_commit. */
+int qsmrt_debug_set_leaf_max(int leaf_max);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ struct LbvhBuildArgs {
     uint64_t        ntris;
     const uint64_t *geom_offsets;   // [ngeoms+1] first triangle of each geometry
     uint32_t        ngeoms;
+    int             leaf_max;       // 1..QSMRT_LEAF_MAX triangles per collapsed leaf
     // outputs / scratch (device)
     uint32_t   *bounds_ord;         // [6]
     BuildParams *params;
@@ -26,7 +27,7 @@ struct LbvhBuildArgs {
     uint32_t   *flags;              // [T-1]
     TriRec     *tris;               // [T]
     TNode      *tnodes;             // [max(T-1,1)]
-    unsigned long long *counters;   // [2] nodes, leaves emitted
+    unsigned long long *counters;   // [3] nodes emitted, leaves emitted, binary tree height
     cudaEvent_t ev_sort0, ev_sort1; // optional
 };
 

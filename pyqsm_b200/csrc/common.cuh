@@ -35,6 +35,7 @@ struct SceneView {
     const TNode  *nodes;
     const TriRec *tris;
     uint32_t      ntris;
+    uint32_t      height;      // binary LBVH height: bound on the traversal stack depth
 };
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \

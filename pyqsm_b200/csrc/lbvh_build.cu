@@ -304,14 +304,19 @@ k_emit_leaves(const float *__restrict__ verts, const uint32_t *__restrict__ idx,
 // Bottom-up refit: one thread per leaf climbs; the second arrival at a node
 // (atomic flag) merges the two child boxes and continues.
 __global__ void __launch_bounds__(256)
-k_refit(int64_t n, BNode *bn, const int32_t *__restrict__ parent, uint32_t *flags)
+k_refit(int64_t n, BNode *bn, const int32_t *__restrict__ parent, uint32_t *flags, unsigned long long *counters)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int32_t p = parent[n - 1 + i];
+    uint32_t h = 0;                       // height of the subtree just finished (leaf = 0)
     while (p >= 0) {
         __threadfence();
-        if (atomicAdd(&flags[p], 1u) == 0u) return;
+        // the flag carries the first child's height + 1; 0 = nobody arrived yet
+        uint32_t other = atomicExch(&flags[p], h + 1u);
+        if (other == 0u) return;
+        h = max(h, other - 1u) + 1u;
+        if (p == 0) counters[2] = h;      // tree height (edges from the root to the deepest leaf)
         const float4 *cl = reinterpret_cast<const float4 *>(&bn[bn[p].left]);
         const float4 *cr = reinterpret_cast<const float4 *>(&bn[bn[p].right]);
         float4 llo = __ldcg(cl), lhi = __ldcg(cl + 1), rlo = __ldcg(cr), rhi = __ldcg(cr + 1);
@@ -324,29 +329,29 @@ k_refit(int64_t n, BNode *bn, const int32_t *__restrict__ parent, uint32_t *flag
 // Collapse subtrees of <= QSMRT_LEAF_MAX triangles into leaves and emit the
 // 64-byte traversal nodes (indexed like the binary internal nodes; collapsed
 // interior nodes are simply never referenced).
-__device__ __forceinline__ int child_ref(int32_t c, int64_t n, const int2 *__restrict__ range)
+__device__ __forceinline__ int child_ref(int32_t c, int64_t n, const int2 *__restrict__ range, int leaf_max)
 {
     if (c >= n - 1) return ~(int)(((uint32_t)(c - (n - 1)) << 2) | 0u);
     int2 r = range[c];
     int cnt = r.y - r.x + 1;
-    if (cnt <= QSMRT_LEAF_MAX) return ~(int)(((uint32_t)r.x << 2) | (uint32_t)(cnt - 1));
+    if (cnt <= leaf_max) return ~(int)(((uint32_t)r.x << 2) | (uint32_t)(cnt - 1));
     return c;
 }
 
 __global__ void __launch_bounds__(256)
 k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ range,
-              TNode *__restrict__ tn, unsigned long long *__restrict__ counters)
+              TNode *__restrict__ tn, unsigned long long *__restrict__ counters, int leaf_max)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool live = i < n - 1;
     int2 r = live ? range[i] : make_int2(0, 0);
-    if (live && i != 0 && (r.y - r.x + 1) <= QSMRT_LEAF_MAX) live = false;     // folded into a leaf above
+    if (live && i != 0 && (r.y - r.x + 1) <= leaf_max) live = false;     // folded into a leaf above
     // statistics: one atomic per warp, not per thread
     unsigned m = __ballot_sync(0xFFFFFFFFu, live);
     int nleaf = 0;
     if (live) {
         BNode me0 = bn[i];
-        nleaf = (child_ref(me0.left, n, range) < 0) + (child_ref(me0.right, n, range) < 0);
+        nleaf = (child_ref(me0.left, n, range, leaf_max) < 0) + (child_ref(me0.right, n, range, leaf_max) < 0);
     }
     for (int o = 16; o > 0; o >>= 1) nleaf += __shfl_xor_sync(0xFFFFFFFFu, nleaf, o);
     if ((threadIdx.x & 31) == 0 && m) {
@@ -360,7 +365,7 @@ k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ 
     o.a = make_float4(c0.lox, c0.hix, c0.loy, c0.hiy);
     o.b = make_float4(c1.lox, c1.hix, c1.loy, c1.hiy);
     o.c = make_float4(c0.loz, c0.hiz, c1.loz, c1.hiz);
-    int r0 = child_ref(me.left, n, range), r1 = child_ref(me.right, n, range);
+    int r0 = child_ref(me.left, n, range, leaf_max), r1 = child_ref(me.right, n, range, leaf_max);
     o.d = make_int4(r0, r1, 0, 0);
     tn[i] = o;
 }
@@ -376,7 +381,7 @@ __global__ void k_emit_single(const BNode *__restrict__ bn, TNode *__restrict__ 
     o.d = make_int4(~0, ~0, 0, 0);
     // second child: empty box, never entered
     tn[0] = o;
-    counters[0] = 1; counters[1] = 1;
+    counters[0] = 1; counters[1] = 1; counters[2] = 1;
 }
 
 } // namespace
@@ -422,15 +427,15 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st)) return 1;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
     k_emit_leaves<<<gN, B, 0, st>>>(A.verts, A.idx, (int64_t)n, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris);
-    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 2 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 3 * sizeof(unsigned long long), st));
     if (n == 1) {
         k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.counters);
     } else {
         const unsigned gI = (unsigned)((n - 1 + B - 1) / B);
         CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(uint32_t), st));
         k_karras<<<gI, B, 0, st>>>(A.keys, (int64_t)n, A.bnodes, A.parent, A.range);
-        k_refit<<<gN, B, 0, st>>>((int64_t)n, A.bnodes, A.parent, A.flags);
-        k_emit_tnodes<<<gI, B, 0, st>>>((int64_t)n, A.bnodes, A.range, A.tnodes, A.counters);
+        k_refit<<<gN, B, 0, st>>>((int64_t)n, A.bnodes, A.parent, A.flags, A.counters);
+        k_emit_tnodes<<<gI, B, 0, st>>>((int64_t)n, A.bnodes, A.range, A.tnodes, A.counters, A.leaf_max);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -16,6 +16,7 @@
 #include "traverse.h"
 
 static thread_local char g_err[512] = "";
+static int g_leaf_max = 2;                  // triangles per leaf (qsmrt_debug_set_leaf_max); 2 measured best on C2
 
 void qsmrt_set_error(const char *fmt, ...)
 {
@@ -130,7 +131,7 @@ int check_rays(const float *rays, uint64_t N)
 SceneView view_of(const qsmrt_scene *s)
 {
     SceneView v;
-    v.nodes = s->tnodes; v.tris = s->tris; v.ntris = (uint32_t)s->ntris;
+    v.nodes = s->tnodes; v.tris = s->tris; v.ntris = (uint32_t)s->ntris; v.height = s->stats.bvh_height;
     return v;
 }
 
@@ -147,7 +148,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
     if (V >= (1ull << 32)) FAIL("scene has %llu vertices; indices are 32-bit", (unsigned long long)V);
     s->ntris = T; s->nverts = V;
     memset(&s->stats, 0, sizeof(s->stats));
-    s->stats.num_triangles = T; s->stats.num_geometries = G; s->stats.leaf_max = QSMRT_LEAF_MAX;
+    s->stats.num_triangles = T; s->stats.num_geometries = G; s->stats.leaf_max = (uint32_t)g_leaf_max;
     s->committed = true;
     if (T == 0) { if (build_ms_out) *build_ms_out = 0.0f; return 0; }
 
@@ -165,7 +166,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         dmalloc(&sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&bounds, 8) ||
         dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&parent, 2 * T - 1) ||
         dmalloc(&range, T) || dmalloc(&flags, T) || dmalloc(&s->tris, T) ||
-        dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&counters, 2))
+        dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&counters, 3))
         return 1;
     if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
     else {
@@ -182,6 +183,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         }
     }
     LbvhBuildArgs A{};
+    A.leaf_max = g_leaf_max;
     A.verts = s->verts; A.idx = s->idx; A.ntris = T; A.geom_offsets = s->goff; A.ngeoms = G;
     A.bounds_ord = bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = keys_tmp;
     A.order = s->order; A.order_tmp = order_tmp; A.sort_scratch = sort_scratch;
@@ -193,12 +195,12 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         CUDA_TRY(cudaEventSynchronize(e1));
         CUDA_TRY(cudaEventElapsedTime(&s->stats.build_ms, e0, e1));
         CUDA_TRY(cudaEventElapsedTime(&s->stats.sort_ms, es0, es1));
-        BuildParams bp; unsigned long long cnt[2];
+        BuildParams bp; unsigned long long cnt[3];
         CUDA_TRY(cudaMemcpy(&bp, s->params, sizeof(bp), cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost));
         for (int a = 0; a < 3; ++a) { s->stats.scene_lo[a] = bp.slo[a]; s->stats.scene_hi[a] = bp.shi[a]; }
         s->stats.box_pad = bp.pad;
-        s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1];
+        s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];
         s->stats.bvh_bytes = cnt[0] * sizeof(TNode) + T * sizeof(TriRec);
     }
     dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags);
@@ -324,8 +326,39 @@ int qsmrt_cast_rays_2d(qsmrt_scene *s, const float *rays, uint32_t width, uint64
 
 int qsmrt_debug_set_variant(int variant)
 {
-    if (variant < 1 || variant > 3) FAIL("unknown traversal variant %d", variant);
+    if (variant < 1 || variant > 5) FAIL("unknown traversal variant %d", variant);
     g_trv_variant = variant;
+    return 0;
+}
+
+int qsmrt_debug_set_tuning(int refill_thresh, int want_thresh, int speculate, int counters)
+{
+    if (refill_thresh < 1 || refill_thresh > 32 || want_thresh < 1 || want_thresh > 32) FAIL("thresholds must be in 1..32");
+    g_trv_tuning[0] = refill_thresh; g_trv_tuning[1] = want_thresh; g_trv_tuning[2] = speculate != 0; g_trv_tuning[3] = counters != 0;
+    return 0;
+}
+
+int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out)
+{
+    unsigned long long h[2] = { 0, 0 };
+    if (g_trv_stats_dev) CUDA_TRY(cudaMemcpy(h, g_trv_stats_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    if (nodes_out) *nodes_out = h[0];
+    if (tris_out) *tris_out = h[1];
+    return 0;
+}
+
+int qsmrt_debug_set_leaf_max(int leaf_max)
+{
+    if (leaf_max < 1 || leaf_max > QSMRT_LEAF_MAX) FAIL("leaf_max must be in 1..%d", QSMRT_LEAF_MAX);
+    g_leaf_max = leaf_max;
+    return 0;
+}
+
+int qsmrt_debug_get_census(uint64_t out[16])
+{
+    if (!out) FAIL("null pointer");
+    memset(out, 0, 16 * sizeof(uint64_t));
+    if (g_trv_stats_dev) CUDA_TRY(cudaMemcpy(out, g_trv_stats_dev, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 

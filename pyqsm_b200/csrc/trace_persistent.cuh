@@ -1,0 +1,185 @@
+// trace_persistent.cuh -- v5 traversal kernel (sm_100a), included inside
+// traverse.cu's anonymous namespace.
+//
+// Persistent warps, warp-uniform control flow (see the v3 notes in
+// traverse.cu for the ncu evidence that motivated it), refined by what the
+// v3/v4 profiles and the tuning sweep showed:
+//   * the whole traversal stack lives in shared memory ([entry][thread],
+//     depth = LBVH height + 2 known from the build), so push/pop are single
+//     predicated STS/LDS with the stack pointer in a register -- no local
+//     spill path, no branches;
+//   * nodes are fetched with two 256-bit loads (LDG.E.256, new on sm_100);
+//   * the node phase ends once fewer than `want` lanes are still looking for
+//     a leaf (and somebody holds triangles), the triangle phase drains one
+//     triangle per lane per iteration;
+//   * finished lanes are refilled from a global cursor, compacted with
+//     ballot/popc, once `refill` lanes are idle.
+// MODE 0 closest hit (cast_rays), MODE 1 any hit (test_occlusions).
+
+__device__ __forceinline__ void ld256f(const void *p, float4 &a, float4 &b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
+struct TraceArgs {
+    SceneView sc;
+    const float *rays; uint64_t N; uint32_t row_len; uint64_t nslots;
+    CastOut out; uint8_t *occluded; float tnear, tfar;
+    unsigned long long *cursor, *stats;
+    int refill, want, tri_min;
+};
+
+template <int MODE, bool COUNTERS>
+__global__ void __launch_bounds__(TR_BLOCK)
+k_trace5(const TraceArgs A)
+{
+    extern __shared__ int sstack[];                 // [depth][TR_BLOCK]
+    int *const sbase = sstack + threadIdx.x;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    const TNode *__restrict__ nodes = A.sc.nodes;
+    const TriRec *__restrict__ tris = A.sc.tris;
+
+    Ray r;
+    float best_t = 0.0f; uint32_t best_geom = QSMRT_INVALID, best_prim = QSMRT_INVALID, best_tri = 0u;
+    uint64_t ray_i = 0;
+    bool have_ray = false, exhausted = false;
+    int cur = TR_SENTINEL, sp = 0;
+    uint32_t tri_i = 0, tri_end = 0;
+    unsigned n_node = 0, n_tri = 0;
+
+#define PARK_LEAF5() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; \
+                          --sp; cur = sbase[sp * TR_BLOCK]; } while (0)
+
+    for (;;) {
+        // ---- retire finished rays, refill idle lanes
+        const bool idle = (cur == TR_SENTINEL) && (tri_i >= tri_end);
+        const unsigned im = __ballot_sync(FULL, idle);
+        if (im == FULL || (!exhausted && __popc(im) >= A.refill)) {
+            if (idle && have_ray) {
+                have_ray = false;
+                if (MODE == 0) {
+                    if (A.out.t_hit) A.out.t_hit[ray_i] = best_t;
+                    if (A.out.geom) A.out.geom[ray_i] = best_geom;
+                    if (A.out.prim) A.out.prim[ray_i] = best_prim;
+                    if (A.out.uv || A.out.nrm) {
+                        float u = 0.0f, v = 0.0f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
+                        if (best_prim != QSMRT_INVALID) {
+                            float4 p0, p1, p2;
+                            load_tri(tris, best_tri, p0, p1, p2);
+                            MtHit h;
+                            mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h);
+                            u = __fdiv_rn(h.U, h.absDen); v = __fdiv_rn(h.V, h.absDen);
+                            float inv = __fdiv_rn(1.0f, __fsqrt_rn(f3dot(h.Ng, h.Ng)));
+                            nx = __fmul_rn(h.Ng.x, inv); ny = __fmul_rn(h.Ng.y, inv); nz = __fmul_rn(h.Ng.z, inv);
+                        }
+                        if (A.out.uv) A.out.uv[ray_i] = make_float2(u, v);
+                        if (A.out.nrm) { A.out.nrm[3 * ray_i] = nx; A.out.nrm[3 * ray_i + 1] = ny; A.out.nrm[3 * ray_i + 2] = nz; }
+                    }
+                } else {
+                    A.occluded[ray_i] = best_prim != QSMRT_INVALID ? 1 : 0;
+                }
+            }
+            if (exhausted) {
+                if (im == FULL) break;
+            } else {
+                const int need = __popc(im);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(A.cursor, (unsigned long long)need);
+                base = __shfl_sync(FULL, base, 0);
+                exhausted = base + (unsigned long long)need >= A.nslots;
+                if (idle) {
+                    const uint64_t slot = base + __popc(im & lt);
+                    uint64_t i;
+                    if (slot < A.nslots && ray_index_of_slot(slot, A.N, A.row_len, i)) {
+                        r = load_ray(A.rays, i);
+                        ray_i = i; have_ray = true;
+                        best_t = MODE == 0 ? INFINITY : A.tfar;
+                        best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
+                        sbase[0] = TR_SENTINEL; sp = 1;
+                        cur = A.sc.ntris ? 0 : TR_SENTINEL;
+                        tri_i = tri_end = 0;
+                    }
+                }
+                continue;
+            }
+        }
+        // ---- node phase
+        for (;;) {
+            const bool inner = (unsigned)cur < (unsigned)TR_SENTINEL;
+            const bool parked = tri_i < tri_end;
+            const unsigned mw = __ballot_sync(FULL, inner && !parked);
+            if (mw == 0u) break;
+            if (__popc(mw) < A.want && __popc(__ballot_sync(FULL, parked)) >= A.tri_min) break;
+            if (COUNTERS) {
+                // lane census of the node phase (stats[2..6]): who sits out and why
+                const unsigned m_in = __ballot_sync(FULL, inner);
+                const unsigned m_idle = __ballot_sync(FULL, cur == TR_SENTINEL && !parked);
+                const unsigned m_leaf2 = __ballot_sync(FULL, parked && cur < 0);
+                const unsigned m_done = __ballot_sync(FULL, parked && cur == TR_SENTINEL);
+                if (lane == 0) {
+                    atomicAdd(&A.stats[2], 1ull); atomicAdd(&A.stats[3], (unsigned long long)__popc(m_in));
+                    atomicAdd(&A.stats[4], (unsigned long long)__popc(m_idle));
+                    atomicAdd(&A.stats[5], (unsigned long long)__popc(m_leaf2));
+                    atomicAdd(&A.stats[6], (unsigned long long)__popc(m_done));
+                }
+            }
+            if (inner) {
+                float4 a, b, c, dd;
+                ld256f(nodes + cur, a, b);
+                ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
+                const int c0 = __float_as_int(dd.x), c1 = __float_as_int(dd.y);
+                float t0, t1;
+                const bool h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, best_t, t0);
+                const bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, best_t, t1);
+                if (COUNTERS) ++n_node;
+                const bool both = h0 & h1, none = !(h0 | h1);
+                const bool swap = both && MODE == 0 && (t1 < t0);
+                int nxt = (h0 && !swap) ? c0 : c1;
+                if (both) { sbase[sp * TR_BLOCK] = swap ? c0 : c1; ++sp; }
+                if (none) { --sp; nxt = sbase[sp * TR_BLOCK]; }
+                cur = nxt;
+                if (cur < 0 && !parked) PARK_LEAF5();
+            }
+        }
+        // ---- triangle phase
+        for (;;) {
+            const bool has = tri_i < tri_end;
+            const unsigned mh = __ballot_sync(FULL, has);
+            if (mh == 0u) break;
+            if (__popc(mh) < A.tri_min && __any_sync(FULL, (unsigned)cur < (unsigned)TR_SENTINEL && !has)) break;
+            if (COUNTERS && lane == 0) { atomicAdd(&A.stats[7], 1ull); atomicAdd(&A.stats[8], (unsigned long long)__popc(mh)); }
+            if (has) {
+                float4 p0, p1, p2;
+                load_tri(tris, tri_i, p0, p1, p2);
+                MtHit h;
+                if (COUNTERS) ++n_tri;
+                if (MODE == 0) {
+                    if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                        float tt = __fdiv_rn(h.T, h.absDen);
+                        uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
+                        bool better = (tt < best_t) | ((tt == best_t) & ((pg < best_geom) | ((pg == best_geom) & (pp < best_prim))));
+                        if (better) { best_t = tt; best_geom = pg; best_prim = pp; best_tri = tri_i; }
+                    }
+                    ++tri_i;
+                    if (tri_i == tri_end && cur < 0) PARK_LEAF5();
+                } else {
+                    if (mt_test(p0, p1, p2, r.O, r.D, A.tnear, A.tfar, h)) {
+                        best_prim = 0u; cur = TR_SENTINEL; tri_i = tri_end;       // occluded: drop the rest
+                    } else {
+                        ++tri_i;
+                        if (tri_i == tri_end && cur < 0) PARK_LEAF5();
+                    }
+                }
+            }
+        }
+    }
+    if (COUNTERS) {
+        for (int o = 16; o > 0; o >>= 1) { n_node += __shfl_xor_sync(FULL, n_node, o); n_tri += __shfl_xor_sync(FULL, n_tri, o); }
+        if (lane == 0) { atomicAdd(&A.stats[0], (unsigned long long)n_node); atomicAdd(&A.stats[1], (unsigned long long)n_tri); }
+    }
+#undef PARK_LEAF5
+}

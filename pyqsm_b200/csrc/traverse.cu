@@ -24,7 +24,7 @@ constexpr int TR_LSTACK = 80;     // local spill; 96 total > max LBVH depth (63 
 
 struct Stack {
     int *s;                 // &smem[0][threadIdx.x]
-    int  loc[TR_LSTACK];
+    int *loc;               // the kernel's local spill array (kept outside the struct so sp stays in a register)
     int  sp;
     __device__ __forceinline__ void push(int v) {
         if (sp < TR_SSTACK) s[sp * TR_BLOCK] = v; else loc[sp - TR_SSTACK] = v;
@@ -215,7 +215,8 @@ k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t r
     uint64_t i;
     if (!ray_index(N, row_len, i)) return;
     Ray r = load_ray(rays, i);
-    Stack st; st.s = sstack + threadIdx.x;
+    int spill[TR_LSTACK];
+    Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
     ClosestVis vis{ sc, r, INFINITY, QSMRT_INVALID, QSMRT_INVALID, 0u };
     if (sc.ntris) {
         if (VARIANT == 1) traverse<true>(sc, r, st, vis);
@@ -406,6 +407,9 @@ k_trace_persistent(SceneView sc, const float *__restrict__ rays, uint64_t N, uin
 #undef PARK_LEAF
 }
 
+#include "trace_sched.cuh"
+#include "trace_persistent.cuh"
+
 // ---------------------------------------------------------------- any hit
 struct AnyVis {
     const SceneView &sc; const Ray &r; float tnear, tfar; bool hit;
@@ -429,7 +433,8 @@ k_test_occlusions(SceneView sc, const float *__restrict__ rays, uint64_t N, floa
     uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
     if (i >= N) return;
     Ray r = load_ray(rays, i);
-    Stack st; st.s = sstack + threadIdx.x;
+    int spill[TR_LSTACK];
+    Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
     AnyVis vis{ sc, r, tnear, tfar, false };
     if (sc.ntris) traverse<false>(sc, r, st, vis);
     out[i] = vis.hit ? 1 : 0;
@@ -498,7 +503,8 @@ k_count_intersections(SceneView sc, const float *__restrict__ rays, uint64_t N, 
     uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
     if (i >= N) return;
     Ray r = load_ray(rays, i);
-    Stack st; st.s = sstack + threadIdx.x;
+    int spill[TR_LSTACK];
+    Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
     int result = 0;
     if (sc.ntris) {
         CountVis vis{ sc, r };
@@ -542,7 +548,8 @@ k_raw_count(SceneView sc, const float *__restrict__ rays, uint64_t N, int32_t *_
     uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
     if (i >= N) return;
     Ray r = load_ray(rays, i);
-    Stack st; st.s = sstack + threadIdx.x;
+    int spill[TR_LSTACK];
+    Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
     RawCountVis vis{ sc, r, 0 };
     if (sc.ntris) traverse<false>(sc, r, st, vis);
     out[i] = vis.n;
@@ -585,7 +592,8 @@ k_raw_fill_sort(SceneView sc, const float *__restrict__ rays, uint64_t N,
     uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
     if (i >= N) return;
     Ray r = load_ray(rays, i);
-    Stack st; st.s = sstack + threadIdx.x;
+    int spill[TR_LSTACK];
+    Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
     HitRec *seg = raw + raw_off[i];
     int n = (int)(raw_off[i + 1] - raw_off[i]);
     RawFillVis vis{ sc, r, seg };
@@ -756,7 +764,9 @@ inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block -
 } // namespace
 
 // --------------------------------------------------------------- launchers
-int g_trv_variant = 3;      // 1 = per-thread loop, 2 = speculative while-while, 3 = persistent warp-uniform
+int g_trv_variant = 5;      // 1 per-thread loop, 2 speculative while-while, 3 persistent two-phase (spill stack), 4 persistent scheduler, 5 persistent two-phase, smem stack + 256-bit loads
+int g_trv_tuning[4] = { 12, 12, 1, 0 }; // refill, want, tri_min (v4: speculate), counters -- tuned on C2 (profiles/r01_tuning.txt)
+unsigned long long *g_trv_stats_dev = nullptr;
 
 // work cursors of the persistent kernels: a per-device ring so launches in flight never share one
 namespace {
@@ -791,6 +801,21 @@ template <int MODE> int persistent_grid(int *blocks)
     return 0;
 }
 
+template <int MODE> int sched_grid(int *blocks)
+{
+    static int cached[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!cached[dev]) {
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_sched<MODE, false>, TR_BLOCK, 0));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cached[dev] = per_sm * sms;
+    }
+    *blocks = cached[dev];
+    return 0;
+}
+
 uint64_t slots_for(uint64_t N, uint32_t row_len)
 {
     if (!row_len) return N;
@@ -809,7 +834,46 @@ int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t r
         uint64_t rows = N / row_len, warps = (uint64_t)((row_len + 7u) / 8u) * ((rows + 3) / 4);
         grid = (unsigned)((warps + TR_BLOCK / 32 - 1) / (TR_BLOCK / 32));
     }
-    if (g_trv_variant == 3) {
+    const int depth = (int)sc.height + 2;                       // sentinel + one pending entry per level
+    if (g_trv_variant == 5 && depth * TR_BLOCK * (int)sizeof(int) <= 48 * 1024) {
+        TraceArgs a{};
+        a.sc = sc; a.rays = rays; a.N = N; a.row_len = row_len; a.nslots = slots_for(N, row_len);
+        a.out = CastOut{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
+        a.occluded = nullptr; a.tnear = 0.0f; a.tfar = INFINITY;
+        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
+        if (next_cursor(&a.cursor, st)) return 1;
+        const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
+        int dev = 0, per_sm = 0, sms = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (g_trv_tuning[3]) {
+            if (!g_trv_stats_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g_trv_stats_dev), 16 * sizeof(unsigned long long)));
+            CUDA_TRY(cudaMemsetAsync(g_trv_stats_dev, 0, 16 * sizeof(unsigned long long), st));
+            a.stats = g_trv_stats_dev;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<0, true>, TR_BLOCK, smem));
+            unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
+            k_trace5<0, true><<<g, TR_BLOCK, smem, st>>>(a);
+        } else {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<0, false>, TR_BLOCK, smem));
+            unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
+            k_trace5<0, false><<<g, TR_BLOCK, smem, st>>>(a);
+        }
+    } else if (g_trv_variant == 4) {
+        unsigned long long *cursor = nullptr;
+        int blocks = 0;
+        if (next_cursor(&cursor, st) || sched_grid<0>(&blocks)) return 1;
+        uint64_t nslots = slots_for(N, row_len);
+        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)blocks, (nslots + TR_BLOCK - 1) / TR_BLOCK);
+        CastOut o{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
+        Tuning tu{ g_trv_tuning[0], std::max(1, g_trv_tuning[1]), g_trv_tuning[2] };
+        if (g_trv_tuning[3]) {
+            if (!g_trv_stats_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g_trv_stats_dev), 16 * sizeof(unsigned long long)));
+            CUDA_TRY(cudaMemsetAsync(g_trv_stats_dev, 0, 16 * sizeof(unsigned long long), st));
+            k_trace_sched<0, true><<<g, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, nslots, o, nullptr, 0.0f, INFINITY, cursor, tu, g_trv_stats_dev);
+        } else {
+            k_trace_sched<0, false><<<g, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, nslots, o, nullptr, 0.0f, INFINITY, cursor, tu, nullptr);
+        }
+    } else if (g_trv_variant == 3 || g_trv_variant == 5) {
         unsigned long long *cursor = nullptr;
         int blocks = 0;
         if (next_cursor(&cursor, st) || persistent_grid<0>(&blocks)) return 1;
@@ -836,7 +900,24 @@ int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, 
 int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st)
 {
     if (N == 0) return 0;
-    k_test_occlusions<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, tnear, tfar, out);
+    const int depth = (int)sc.height + 2;
+    if (g_trv_variant == 5 && depth * TR_BLOCK * (int)sizeof(int) <= 48 * 1024) {
+        TraceArgs a{};
+        a.sc = sc; a.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
+        a.out = CastOut{ nullptr, nullptr, nullptr, nullptr, nullptr };
+        a.occluded = out; a.tnear = tnear; a.tfar = tfar;
+        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
+        if (next_cursor(&a.cursor, st)) return 1;
+        const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
+        int dev = 0, per_sm = 0, sms = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<1, false>, TR_BLOCK, smem));
+        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (N + TR_BLOCK - 1) / TR_BLOCK);
+        k_trace5<1, false><<<g, TR_BLOCK, smem, st>>>(a);
+    } else {
+        k_test_occlusions<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, tnear, tfar, out);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -298,3 +298,55 @@ def test_reference_call_patterns(RS):
     scene.add_triangles(TriangleMesh(cv, ct))
     q = np.array([[0, 0, 0], [0.5, 0.2, 0.9], [2, 0, 0], [0, 0, 1.5]], np.float32)
     assert scene.compute_occupancy(q).tolist() == [1.0, 1.0, 0.0, 0.0]
+
+
+def test_variants_tilings_and_leaf_sizes_agree(RS, oracle_mod):
+    """Every traversal variant (1 per-thread loop ... 5 persistent smem-stack), the 2-D tile
+    mapping and every leaf size give bit-identical cast_rays results -- and match the oracle."""
+    from pyqsm_b200 import _lib
+    L = _lib.load()
+    v, t = syn.qsm_tree_mesh(seed=9, n_cylinders=60)
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v, t)
+    grid = syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(35, 200), 301, 203)   # not multiples of the 8x4 tile
+    rays = syn.materialize_grid(*grid, 301, 203)
+    ref = o.cast_rays(rays, 1)
+    rays_img = torch.from_numpy(rays.reshape(203, 301, 6)).cuda()
+    try:
+        for leaf_max in (1, 2, 3, 4):
+            _lib.check(L.qsmrt_debug_set_leaf_max(leaf_max))
+            g = RS(output_device="cuda")
+            g.add_triangles(v, t)
+            g.commit()
+            assert g.stats()["leaf_max"] == leaf_max and g.stats()["bvh_height"] >= 10
+            for variant in (1, 2, 3, 4, 5):
+                _lib.check(L.qsmrt_debug_set_variant(variant))
+                for r in (rays_img, rays_img.reshape(-1, 6)):            # 2-D tiles / linear
+                    ans = {k: a.cpu().reshape((-1,) + tuple(a.shape[r.ndim - 1:])) for k, a in g.cast_rays(r).items()}
+                    assert_cast_equal(ans, ref, None, f"leaf{leaf_max}/v{variant}")
+            occ = g.test_occlusions(rays_img.reshape(-1, 6)).cpu().numpy()
+            assert np.array_equal(occ, np.isfinite(ref["t_hit"]))
+    finally:
+        _lib.check(L.qsmrt_debug_set_leaf_max(2))
+        _lib.check(L.qsmrt_debug_set_variant(5))
+        _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 0))
+
+
+def test_fetch_counters(RS):
+    """qsmrt_debug_set_tuning(counters=1): the kernel's own node / triangle fetch counts."""
+    import ctypes as C
+    from pyqsm_b200 import _lib
+    L = _lib.load()
+    v, t = syn.qsm_tree_mesh(seed=1)
+    g = RS(output_device="cuda")
+    g.add_triangles(v, t)
+    rays = torch.from_numpy(syn.materialize_grid(*syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(45, 135), 400, 400), 400, 400)).cuda()
+    try:
+        _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 1))
+        g.cast_rays(rays)
+        torch.cuda.synchronize()
+        nn, nt = C.c_uint64(), C.c_uint64()
+        _lib.check(L.qsmrt_debug_get_counters(C.byref(nn), C.byref(nt)))
+        assert 1 < nn.value / rays.shape[0] < 200 and 0 < nt.value / rays.shape[0] < 50
+    finally:
+        _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 0))

@@ -1,0 +1,44 @@
+"""Ad-hoc: sweep the tuning of the persistent kernels on C2 (not product code)."""
+import argparse, ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pyqsm_b200 import RaycastingScene, synthetic as syn, _lib
+ap = argparse.ArgumentParser(); ap.add_argument("--grid", type=int, default=4000); ap.add_argument("--angles", type=int, default=2)
+ap.add_argument("--combos", default="5:12,12,1,4;5:12,12,4,4;5:12,12,8,4;5:12,12,12,4;5:12,12,1,2;5:12,12,4,2;5:12,12,8,2;5:12,16,8,2;5:12,12,1,3;5:12,12,1,1")
+a = ap.parse_args()
+v, t = syn.canopy_mesh(2, 1_000_000)
+s = RaycastingScene(output_device="cuda"); s.add_triangles(v, t); s.commit(); print("stats", s.stats())
+L = _lib.load(); n = a.grid * a.grid
+rays = torch.empty(n, 6, dtype=torch.float32, device="cuda")
+o = [torch.empty(n, device="cuda"), torch.empty(n, dtype=torch.uint32, device="cuda"), torch.empty(n, dtype=torch.uint32, device="cuda"), torch.empty(n, 2, device="cuda"), torch.empty(n, 3, device="cuda")]
+P = lambda x: C.c_void_p(x.data_ptr()); F3 = lambda x: (C.c_float * 3)(*x)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+lo, hi = v.min(0), v.max(0); sweep = syn.hemisphere_sweep()
+def run():
+    _lib.check(L.qsmrt_cast_rays_2d(s._h, P(rays), a.grid, a.grid, *[P(x) for x in o], st))
+def timeit(reps=3):
+    best = 1e9
+    for _ in range(reps):
+        e0.record(); run(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+    return best
+cur_lm = 4
+for k in range(a.angles):
+    el, az = sweep[(k * 27 + 5) % 64]
+    g = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), a.grid, a.grid)
+    _lib.check(L.qsmrt_gen_parallel_rays(P(rays), a.grid, a.grid, F3(g[0]), F3(g[1]), F3(g[2]), F3(g[3]), st))
+    _lib.check(L.qsmrt_debug_set_variant(3)); _lib.check(L.qsmrt_debug_set_tuning(8, 1, 1, 0)); ms3 = timeit(); ref = (o[0].clone(), o[2].clone(), o[3].clone())
+    print(f"el {el:.0f} az {az:.0f}: v3 {ms3:.2f} ms {n/ms3/1e3:.0f} Mr/s")
+    for combo in a.combos.split(";"):
+        var, rest = combo.split(":"); rf, wt, tm, lm = map(int, rest.split(","))
+        if lm != cur_lm:
+            _lib.check(L.qsmrt_debug_set_leaf_max(lm)); cur_lm = lm
+            s = RaycastingScene(output_device="cuda"); s.add_triangles(v, t); s.commit()
+        _lib.check(L.qsmrt_debug_set_variant(int(var)))
+        _lib.check(L.qsmrt_debug_set_tuning(rf, wt, tm, 0)); ms = timeit()
+        same = torch.equal(ref[0], o[0]) and torch.equal(ref[1], o[2]) and torch.equal(ref[2], o[3])
+        _lib.check(L.qsmrt_debug_set_tuning(rf, wt, tm, 1)); run(); torch.cuda.synchronize()
+        nn, nt = C.c_uint64(), C.c_uint64(); _lib.check(L.qsmrt_debug_get_counters(C.byref(nn), C.byref(nt)))
+        cs = (C.c_uint64 * 16)(); _lib.check(L.qsmrt_debug_get_census(cs)); cs = list(cs)
+        if cs[2]: print(f"      node-phase iters/ray {cs[2]*32/n:.1f} lanes step {cs[3]/cs[2]:.1f} idle {cs[4]/cs[2]:.1f} leaf2 {cs[5]/cs[2]:.1f} done {cs[6]/cs[2]:.1f} | tri-phase iters/ray {cs[7]*32/n:.1f} lanes {cs[8]/max(cs[7],1):.1f}")
+        print(f"   v{var} refill {rf:2d} want {wt:2d} trimin {tm:2d} leafmax {lm}: {ms:.2f} ms {n/ms/1e3:.0f} Mr/s {'=' if same else 'DIFF'}  nodes/ray {nn.value/n:.1f} tris/ray {nt.value/n:.2f}", flush=True)
