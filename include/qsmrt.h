@@ -167,6 +167,9 @@ int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out);
  * are idle / hold a second leaf / finished descending, [7] triangle-phase
  * iterations, [8] lanes testing a triangle. */
 int qsmrt_debug_get_census(uint64_t out[16]);
+/* Node fetch path of the persistent kernel: 0 = 256-bit LSU loads (default),
+ * 1 = texture fetches, 2 = half and half (L1 data-pipe experiment). */
+int qsmrt_debug_set_node_path(int path);
 /* Triangles per collapsed leaf (1..4) used by the next qsmrt_commit. */
 int qsmrt_debug_set_leaf_max(int leaf_max);
 

@@ -36,6 +36,7 @@ struct SceneView {
     const TriRec *tris;
     uint32_t      ntris;
     uint32_t      height;      // binary LBVH height: bound on the traversal stack depth
+    cudaTextureObject_t node_tex;   // float4 view of nodes (TEX-path experiment), 0 if absent
 };
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \

@@ -55,6 +55,7 @@ struct qsmrt_scene {
     BNode *bnodes = nullptr; TNode *tnodes = nullptr; TriRec *tris = nullptr;
     BuildParams *params = nullptr;
     qsmrt_stats stats{};
+    cudaTextureObject_t node_tex = 0;
     // list_intersections cache between _count and _fill
     const float *list_rays = nullptr; uint64_t list_n = 0;
     int64_t *list_raw_off = nullptr; HitRec *list_raw = nullptr;
@@ -81,6 +82,7 @@ void free_build(qsmrt_scene *s)
     dfree(s->bnodes); dfree(s->tnodes); dfree(s->tris); dfree(s->params);
     dfree(s->list_raw_off); dfree(s->list_raw);
     s->list_rays = nullptr; s->list_n = 0;
+    if (s->node_tex) { cudaDestroyTextureObject(s->node_tex); s->node_tex = 0; }
     s->committed = false;
 }
 
@@ -132,6 +134,7 @@ SceneView view_of(const qsmrt_scene *s)
 {
     SceneView v;
     v.nodes = s->tnodes; v.tris = s->tris; v.ntris = (uint32_t)s->ntris; v.height = s->stats.bvh_height;
+    v.node_tex = s->node_tex;
     return v;
 }
 
@@ -202,6 +205,13 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         s->stats.box_pad = bp.pad;
         s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];
         s->stats.bvh_bytes = cnt[0] * sizeof(TNode) + T * sizeof(TriRec);
+        {   // float4 texture view of the node array (TEX-path experiment); optional
+            cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = s->tnodes;
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+            rd.res.linear.sizeInBytes = std::max<uint64_t>(T - 1, 1) * sizeof(TNode);
+            cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&s->node_tex, &rd, &td, nullptr) != cudaSuccess) { s->node_tex = 0; cudaGetLastError(); }
+        }
     }
     dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags);
     dfree(parent); dfree(range); dfree(counters);
@@ -344,6 +354,13 @@ int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out)
     if (g_trv_stats_dev) CUDA_TRY(cudaMemcpy(h, g_trv_stats_dev, sizeof(h), cudaMemcpyDeviceToHost));
     if (nodes_out) *nodes_out = h[0];
     if (tris_out) *tris_out = h[1];
+    return 0;
+}
+
+int qsmrt_debug_set_node_path(int path)
+{
+    if (path < 0 || path > 2) FAIL("node path must be 0, 1 or 2");
+    g_trv_node_path = path;
     return 0;
 }
 

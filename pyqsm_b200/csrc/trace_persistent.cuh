@@ -28,7 +28,7 @@ struct TraceArgs {
     const float *rays; uint64_t N; uint32_t row_len; uint64_t nslots;
     CastOut out; uint8_t *occluded; float tnear, tfar;
     unsigned long long *cursor, *stats;
-    int refill, want, tri_min;
+    int refill, want, tri_min, node_path;
 };
 
 template <int MODE, bool COUNTERS>
@@ -47,12 +47,13 @@ k_trace5(const TraceArgs A)
     float best_t = 0.0f; uint32_t best_geom = QSMRT_INVALID, best_prim = QSMRT_INVALID, best_tri = 0u;
     uint64_t ray_i = 0;
     bool have_ray = false, exhausted = false;
-    int cur = TR_SENTINEL, sp = 0;
+    int cur = TR_SENTINEL;
+    int *sptr = sbase;                              // next free stack slot (register; stride TR_BLOCK ints)
     uint32_t tri_i = 0, tri_end = 0;
     unsigned n_node = 0, n_tri = 0;
 
 #define PARK_LEAF5() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; \
-                          --sp; cur = sbase[sp * TR_BLOCK]; } while (0)
+                          sptr -= TR_BLOCK; cur = *sptr; } while (0)
 
     for (;;) {
         // ---- retire finished rays, refill idle lanes
@@ -99,7 +100,7 @@ k_trace5(const TraceArgs A)
                         ray_i = i; have_ray = true;
                         best_t = MODE == 0 ? INFINITY : A.tfar;
                         best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
-                        sbase[0] = TR_SENTINEL; sp = 1;
+                        sbase[0] = TR_SENTINEL; sptr = sbase + TR_BLOCK;
                         cur = A.sc.ntris ? 0 : TR_SENTINEL;
                         tri_i = tri_end = 0;
                     }
@@ -129,18 +130,27 @@ k_trace5(const TraceArgs A)
             }
             if (inner) {
                 float4 a, b, c, dd;
-                ld256f(nodes + cur, a, b);
-                ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
+                if (A.node_path == 0) {
+                    ld256f(nodes + cur, a, b);
+                    ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
+                } else if (A.node_path == 1) {         // experiment: all four 16-byte chunks through the TEX path
+                    a = tex1Dfetch<float4>(A.sc.node_tex, cur * 4);     b = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 1);
+                    c = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 2); dd = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 3);
+                } else {                               // experiment: half through TEX, half through LSU
+                    a = tex1Dfetch<float4>(A.sc.node_tex, cur * 4);     b = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 1);
+                    ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
+                }
                 const int c0 = __float_as_int(dd.x), c1 = __float_as_int(dd.y);
                 float t0, t1;
                 const bool h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, best_t, t0);
                 const bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, best_t, t1);
                 if (COUNTERS) ++n_node;
-                const bool both = h0 & h1, none = !(h0 | h1);
-                const bool swap = both && MODE == 0 && (t1 < t0);
-                int nxt = (h0 && !swap) ? c0 : c1;
-                if (both) { sbase[sp * TR_BLOCK] = swap ? c0 : c1; ++sp; }
-                if (none) { --sp; nxt = sbase[sp * TR_BLOCK]; }
+                // take child 1 first when child 0 is missed, or both are hit and 1 is nearer
+                const bool take1 = !h0 || (MODE == 0 && h1 && (t1 < t0));
+                int nxt = take1 ? c1 : c0;
+                const int other = c0 ^ c1 ^ nxt;        // the child not taken (one LOP3)
+                if (h0 && h1) { *sptr = other; sptr += TR_BLOCK; }
+                if (!h0 && !h1) { sptr -= TR_BLOCK; nxt = *sptr; }
                 cur = nxt;
                 if (cur < 0 && !parked) PARK_LEAF5();
             }

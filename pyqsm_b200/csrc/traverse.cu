@@ -767,6 +767,7 @@ inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block -
 int g_trv_variant = 5;      // 1 per-thread loop, 2 speculative while-while, 3 persistent two-phase (spill stack), 4 persistent scheduler, 5 persistent two-phase, smem stack + 256-bit loads
 int g_trv_tuning[4] = { 12, 12, 1, 0 }; // refill, want, tri_min (v4: speculate), counters -- tuned on C2 (profiles/r01_tuning.txt)
 unsigned long long *g_trv_stats_dev = nullptr;
+int g_trv_node_path = 0;                // 0 LSU 256-bit loads, 1 TEX, 2 half/half (qsmrt_debug_set_node_path)
 
 // work cursors of the persistent kernels: a per-device ring so launches in flight never share one
 namespace {
@@ -840,7 +841,7 @@ int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t r
         a.sc = sc; a.rays = rays; a.N = N; a.row_len = row_len; a.nslots = slots_for(N, row_len);
         a.out = CastOut{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
         a.occluded = nullptr; a.tnear = 0.0f; a.tfar = INFINITY;
-        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
+        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]); a.node_path = sc.node_tex ? g_trv_node_path : 0;
         if (next_cursor(&a.cursor, st)) return 1;
         const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
         int dev = 0, per_sm = 0, sms = 0;
@@ -906,7 +907,7 @@ int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear
         a.sc = sc; a.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
         a.out = CastOut{ nullptr, nullptr, nullptr, nullptr, nullptr };
         a.occluded = out; a.tnear = tnear; a.tfar = tfar;
-        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
+        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]); a.node_path = sc.node_tex ? g_trv_node_path : 0;
         if (next_cursor(&a.cursor, st)) return 1;
         const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
         int dev = 0, per_sm = 0, sms = 0;
