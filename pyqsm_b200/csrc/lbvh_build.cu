@@ -183,17 +183,36 @@ k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
     __syncthreads();
 
     uint64_t kreg[RS_ROUNDS];
+    uint32_t vreg[RS_ROUNDS];
     uint16_t rnk[RS_ROUNDS];
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * (32 * RS_ROUNDS);
     const uint32_t lt = (1u << l) - 1u;
+    // all loads first (16 + 16 independent requests in flight), then the ranking rounds
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        uint64_t i = base + r * 32 + l;
+        kreg[r] = i < n ? kin[i] : ~0ull;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        uint64_t i = base + r * 32 + l;
+        vreg[r] = i < n ? vin[i] : 0u;
+    }
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
         uint64_t i = base + r * 32 + l;
         bool valid = i < n;
-        uint64_t k = valid ? kin[i] : ~0ull;
-        kreg[r] = k;
+        uint64_t k = kreg[r];
         uint32_t d = valid ? ((uint32_t)(k >> shift) & 0xFFu) : 256u;
-        uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
+        // lanes holding the same digit: nine ballots (8 digit bits + validity) instead of MATCH.ANY,
+        // which serialises over the distinct values of the warp
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+        m = valid ? m : ~m;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
+            m &= ((d >> b) & 1u) ? bal : ~bal;
+        }
         uint32_t before = valid ? wcnt[w][d] : 0;
         __syncwarp();
         if (valid && (m & lt) == 0) wcnt[w][d] = before + __popc(m);
@@ -215,7 +234,7 @@ k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
             uint32_t d = (uint32_t)(kreg[r] >> shift) & 0xFFu;
             uint64_t dst = (uint64_t)dbase[d] + wcnt[w][d] + rnk[r];
             kout[dst] = kreg[r];
-            vout[dst] = vin[i];
+            vout[dst] = vreg[r];
         }
     }
 }
