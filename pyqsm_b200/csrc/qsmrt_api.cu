@@ -422,7 +422,7 @@ int qsmrt_count_intersections(qsmrt_scene *s, const float *rays, uint64_t N, int
     if (N && !counts) FAIL("counts pointer is null");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
-    return trv_count(view_of(s), rays, N, counts, st);
+    return trv_count(view_of(s), rays, N, counts, (uint32_t)s->geoms.size(), st);
 }
 
 int qsmrt_test_occlusions(qsmrt_scene *s, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, void *stream)

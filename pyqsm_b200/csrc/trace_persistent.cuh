@@ -14,7 +14,11 @@
 //     triangle per lane per iteration;
 //   * finished lanes are refilled from a global cursor, compacted with
 //     ballot/popc, once `refill` lanes are idle.
-// MODE 0 closest hit (cast_rays), MODE 1 any hit (test_occlusions).
+// MODE 0 closest hit (cast_rays), MODE 1 any hit (test_occlusions),
+// MODE 2 all hits (count_intersections): number of distinct (geometry, t)
+// pairs, kept per lane in a shared-memory set [slot][thread]; a ray with more
+// than CNT_SET distinct hits is marked -1 and finished exactly by k_count_fix
+// (one traversal per distinct hit, no storage, no host round trip).
 
 __device__ __forceinline__ void ld256f(const void *p, float4 &a, float4 &b)
 {
@@ -29,7 +33,13 @@ struct TraceArgs {
     CastOut out; uint8_t *occluded; float tnear, tfar;
     unsigned long long *cursor, *stats;
     int refill, want, tri_min, node_path;
+    // MODE 2 (count_intersections)
+    int32_t *counts;
+    int depth;          // stack entries per thread; the hit set starts behind the stack in shared memory
+    int multi_geom;     // > 1 geometry: the set also keeps geometry ids
 };
+
+constexpr int CNT_SET = 32;     // distinct (geometry, t) pairs a lane can hold before it defers to the exact slow path
 
 template <int MODE, bool COUNTERS>
 __global__ void __launch_bounds__(TR_BLOCK)
@@ -51,6 +61,9 @@ k_trace5(const TraceArgs A)
     int *sptr = sbase;                              // next free stack slot (register; stride TR_BLOCK ints)
     uint32_t tri_i = 0, tri_end = 0;
     unsigned n_node = 0, n_tri = 0;
+    float *const tset = reinterpret_cast<float *>(sstack + A.depth * TR_BLOCK) + threadIdx.x;      // MODE 2
+    uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + CNT_SET) * TR_BLOCK) + threadIdx.x;
+    int cnt = 0; bool overflow = false;
 
 #define PARK_LEAF5() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; \
                           sptr -= TR_BLOCK; cur = *sptr; } while (0)
@@ -80,8 +93,10 @@ k_trace5(const TraceArgs A)
                         if (A.out.uv) A.out.uv[ray_i] = make_float2(u, v);
                         if (A.out.nrm) { A.out.nrm[3 * ray_i] = nx; A.out.nrm[3 * ray_i + 1] = ny; A.out.nrm[3 * ray_i + 2] = nz; }
                     }
-                } else {
+                } else if (MODE == 1) {
                     A.occluded[ray_i] = best_prim != QSMRT_INVALID ? 1 : 0;
+                } else {
+                    A.counts[ray_i] = overflow ? -1 : cnt;           // -1: k_count_fix recounts this ray exactly
                 }
             }
             if (exhausted) {
@@ -98,7 +113,8 @@ k_trace5(const TraceArgs A)
                     if (slot < A.nslots && ray_index_of_slot(slot, A.N, A.row_len, i)) {
                         r = load_ray(A.rays, i);
                         ray_i = i; have_ray = true;
-                        best_t = MODE == 0 ? INFINITY : A.tfar;
+                        best_t = MODE == 1 ? A.tfar : INFINITY;
+                        cnt = 0; overflow = false;
                         best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
                         sbase[0] = TR_SENTINEL; sptr = sbase + TR_BLOCK;
                         cur = A.sc.ntris ? 0 : TR_SENTINEL;
@@ -176,10 +192,26 @@ k_trace5(const TraceArgs A)
                     }
                     ++tri_i;
                     if (tri_i == tri_end && cur < 0) PARK_LEAF5();
-                } else {
+                } else if (MODE == 1) {
                     if (mt_test(p0, p1, p2, r.O, r.D, A.tnear, A.tfar, h)) {
                         best_prim = 0u; cur = TR_SENTINEL; tri_i = tri_end;       // occluded: drop the rest
                     } else {
+                        ++tri_i;
+                        if (tri_i == tri_end && cur < 0) PARK_LEAF5();
+                    }
+                } else {
+                    if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                        const float tt = __fdiv_rn(h.T, h.absDen);
+                        const uint32_t pg = __float_as_uint(p1.w);
+                        bool dup = false;
+                        for (int q = 0; q < cnt; ++q)
+                            dup = dup || (tset[q * TR_BLOCK] == tt && (!A.multi_geom || gset[q * TR_BLOCK] == pg));
+                        if (!dup) {
+                            if (cnt < CNT_SET) { tset[cnt * TR_BLOCK] = tt; if (A.multi_geom) gset[cnt * TR_BLOCK] = pg; ++cnt; }
+                            else { overflow = true; cur = TR_SENTINEL; tri_i = tri_end; }   // the fix-up kernel recounts this ray
+                        }
+                    }
+                    if (!overflow) {
                         ++tri_i;
                         if (tri_i == tri_end && cur < 0) PARK_LEAF5();
                     }

@@ -526,6 +526,29 @@ k_count_intersections(SceneView sc, const float *__restrict__ rays, uint64_t N, 
     out[i] = result;
 }
 
+// exact recount of the rays the persistent count kernel marked -1 (more distinct hits than its set holds)
+__global__ void __launch_bounds__(TR_BLOCK)
+k_count_fix(SceneView sc, const float *__restrict__ rays, uint64_t N, int32_t *__restrict__ out)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    int spill[TR_LSTACK];
+    Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
+    for (uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x; i < N; i += (uint64_t)gridDim.x * TR_BLOCK) {
+        if (out[i] >= 0) continue;
+        Ray r = load_ray(rays, i);
+        int result = 0;
+        NextVis nv{ sc, r, 0.0f, 0u, false, INFINITY, 0u, false };
+        for (;;) {
+            nv.bt = INFINITY; nv.bg = 0u; nv.found = false;
+            traverse<true>(sc, r, st, nv);
+            if (!nv.found) break;
+            ++result;
+            nv.pt = nv.bt; nv.pg = nv.bg; nv.have_prev = true;
+        }
+        out[i] = result;
+    }
+}
+
 // list_intersections, phase 1a: raw (un-deduplicated) hit count per ray
 struct RawCountVis {
     const SceneView &sc; const Ray &r; int n;
@@ -890,9 +913,29 @@ int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t r
     return 0;
 }
 
-int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st)
+int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st)
 {
     if (N == 0) return 0;
+    const int depth = (int)sc.height + 2;
+    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * CNT_SET) * TR_BLOCK * sizeof(int);
+    if (g_trv_variant == 5 && sc.ntris && smem <= 96 * 1024) {
+        TraceArgs a{};
+        a.sc = sc; a.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
+        a.out = CastOut{ nullptr, nullptr, nullptr, nullptr, nullptr };
+        a.counts = out; a.depth = depth; a.multi_geom = ngeoms > 1;
+        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
+        if (next_cursor(&a.cursor, st)) return 1;
+        int dev = 0, per_sm = 0, sms = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaFuncSetAttribute(k_trace5<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<2, false>, TR_BLOCK, smem));
+        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (N + TR_BLOCK - 1) / TR_BLOCK);
+        k_trace5<2, false><<<g, TR_BLOCK, smem, st>>>(a);
+        k_count_fix<<<(unsigned)std::min<uint64_t>(grid_for(N, TR_BLOCK), (uint64_t)sms * 8), TR_BLOCK, 0, st>>>(sc, rays, N, out);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     k_count_intersections<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, out);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -10,7 +10,7 @@ extern int g_trv_tuning[4];
 extern unsigned long long *g_trv_stats_dev;
 int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,
                   uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
-int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st);
+int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st);
 int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st);
 int trv_raw_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st);
 int trv_raw_fill_sort(const SceneView &sc, const float *rays, uint64_t N, const int64_t *raw_off,
