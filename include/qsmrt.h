@@ -142,6 +142,31 @@ int qsmrt_accumulate_hits(qsmrt_scene *scene, const uint32_t *geometry_ids,
                           const uint32_t *primitive_ids, uint64_t N,
                           uint32_t *tri_counts, void *stream);
 
+/* Environmental drivers (README.md:131 "sunlight angle, cloud cover and rain
+ * angle"; data/notes/methods.md:16,53-55): the rays are generated inside the
+ * traversal kernel and the results reduced on the device, so no 24 B/ray of
+ * input or 32 B/ray of output ever touches HBM.
+ *
+ * qsmrt_sun_exposure: the parallel grid of qsmrt_gen_parallel_rays (nu x nv)
+ *   is cast and tri_counts[t] += 1 for the triangle owning each closest hit
+ *   (scene order).  Equals gen_parallel_rays + cast_rays + accumulate_hits.
+ * qsmrt_sky_visibility: for each of n_points query points (origin = point +
+ *   offset * normal; normals may be NULL) directions dir_begin ..
+ *   dir_begin+dir_count-1 of a seeded uniform sample of the upper hemisphere
+ *   (about +z) are tested for occlusion; unoccluded[p] += number of free
+ *   directions.  Gap fraction = unoccluded / directions.
+ * qsmrt_gen_hemisphere_rays materialises exactly those rays
+ *   (rays[n_points * dir_count][6]) for inspection and parity tests. */
+int qsmrt_sun_exposure(qsmrt_scene *scene, uint64_t nu, uint64_t nv, const float origin0[3],
+                       const float du[3], const float dv[3], const float dir[3],
+                       uint32_t *tri_counts, void *stream);
+int qsmrt_sky_visibility(qsmrt_scene *scene, const float *points_dev, const float *normals_dev,
+                         uint64_t n_points, uint64_t seed, float offset, uint32_t dir_begin,
+                         uint32_t dir_count, uint32_t *unoccluded, void *stream);
+int qsmrt_gen_hemisphere_rays(float *rays_dev, const float *points_dev, const float *normals_dev,
+                              uint64_t n_points, uint64_t seed, float offset, uint32_t dir_begin,
+                              uint32_t dir_count, void *stream);
+
 int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
 
 /* Builder introspection (parity tests of the LBVH builder; host outputs,

@@ -528,6 +528,35 @@ int qsmrt_accumulate_hits(qsmrt_scene *s, const uint32_t *geom, const uint32_t *
     return trv_accumulate_hits(geom, prim, N, s->goff, (uint32_t)s->geoms.size(), tri_counts, st);
 }
 
+int qsmrt_sun_exposure(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+                       const float dv[3], const float dir[3], uint32_t *tri_counts, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (!o0 || !du || !dv || !dir || !tri_counts) FAIL("null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    return trv_sun_exposure(view_of(s), nu, nv, o0, du, dv, dir, s->geoms.size() > 1 ? s->goff : nullptr, tri_counts, st);
+}
+
+int qsmrt_sky_visibility(qsmrt_scene *s, const float *points, const float *normals, uint64_t n_points,
+                         uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count,
+                         uint32_t *unoccluded, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (!points || !unoccluded) FAIL("null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    return trv_sky_visibility(view_of(s), points, normals, n_points, seed, offset, dir_begin, dir_count, unoccluded, st);
+}
+
+int qsmrt_gen_hemisphere_rays(float *rays, const float *points, const float *normals, uint64_t n_points,
+                              uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, void *stream)
+{
+    if (!rays || !points) FAIL("null pointer");
+    if (reinterpret_cast<uintptr_t>(rays) & 7u) FAIL("rays must be 8-byte aligned");
+    return trv_gen_hemisphere(rays, points, normals, n_points, seed, offset, dir_begin, dir_count, static_cast<cudaStream_t>(stream));
+}
+
 int qsmrt_get_stats(qsmrt_scene *s, qsmrt_stats *out)
 {
     if (!s || !out) FAIL("null pointer");

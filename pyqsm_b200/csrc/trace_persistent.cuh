@@ -1,5 +1,5 @@
-// trace_persistent.cuh -- v5 traversal kernel (sm_100a), included inside
-// traverse.cu's anonymous namespace.
+// trace_persistent.cuh -- the traversal kernel that ships (v5, sm_100a),
+// included inside traverse.cu's anonymous namespace.
 //
 // Persistent warps, warp-uniform control flow (see the v3 notes in
 // traverse.cu for the ncu evidence that motivated it), refined by what the
@@ -14,11 +14,21 @@
 //     triangle per lane per iteration;
 //   * finished lanes are refilled from a global cursor, compacted with
 //     ballot/popc, once `refill` lanes are idle.
-// MODE 0 closest hit (cast_rays), MODE 1 any hit (test_occlusions),
-// MODE 2 all hits (count_intersections): number of distinct (geometry, t)
-// pairs, kept per lane in a shared-memory set [slot][thread]; a ray with more
-// than CNT_SET distinct hits is marked -1 and finished exactly by k_count_fix
-// (one traversal per distinct hit, no storage, no host round trip).
+//
+// MODE (what is done with the hits)
+//   0  closest hit  -> t_hit / ids / uv / normal            (cast_rays)
+//   1  any hit      -> occluded[ray]                        (test_occlusions)
+//   2  all hits     -> number of distinct (geometry, t)     (count_intersections)
+//                      kept per lane in a shared-memory set [slot][thread]; a ray
+//                      with more than CNT_SET distinct hits is marked -1 and
+//                      finished exactly by k_count_fix
+//   3  closest hit  -> atomicAdd(accum[triangle], 1)        (sun exposure: no 32 B/ray of results)
+//   4  any hit      -> atomicAdd(accum[ray / n_dirs], !hit) (sky visibility per query point)
+// SRC (where rays come from; a uniform runtime switch, only touched at refill)
+//   0  rays[N][6] in memory
+//   1  parallel grid: origin0 + i*du + j*dv, direction dir  (same arithmetic as k_gen_parallel)
+//   2  hemisphere Monte-Carlo about +z from points[n][3] (+ offset along normals[n][3]),
+//      direction k of point p from a counter-based hash of (seed, p, k) (same as k_gen_hemisphere)
 
 __device__ __forceinline__ void ld256f(const void *p, float4 &a, float4 &b)
 {
@@ -27,15 +37,74 @@ __device__ __forceinline__ void ld256f(const void *p, float4 &a, float4 &b)
                  : "l"(p));
 }
 
+// ---- counter-based sampling of the upper hemisphere (uniform in solid angle)
+__device__ __forceinline__ uint32_t hash32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;     // lowbias32
+    return x;
+}
+
+__device__ __forceinline__ f3 hemisphere_dir(uint64_t seed, uint64_t point, uint32_t k)
+{
+    uint32_t h0 = hash32((uint32_t)point ^ hash32((uint32_t)(point >> 32) + 0x9E3779B9u) ^ hash32((uint32_t)seed));
+    uint32_t a = hash32(h0 + 2u * k + (uint32_t)(seed >> 32));
+    uint32_t b = hash32(a ^ (0x85EBCA6Bu + 2u * k + 1u));
+    float u1 = (float)(a >> 8) * 5.9604644775390625e-08f;        // [0,1), exact
+    float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;
+    float z = u1, rr = sqrtf(fmaxf(0.0f, 1.0f - z * z)), phi = 6.2831853071795864f * u2;
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    return f3{ rr * cs, rr * sn, z };
+}
+
+__device__ __forceinline__ Ray make_ray(f3 O, f3 D)
+{
+    Ray r;
+    r.O = O; r.D = D;
+    r.idx = safe_inv(D.x); r.idy = safe_inv(D.y); r.idz = safe_inv(D.z);
+    r.oodx = O.x * r.idx; r.oody = O.y * r.idy; r.oodz = O.z * r.idz;
+    return r;
+}
+
+struct RaySource {
+    int kind;                                   // SRC above
+    const float *rays;                          // 0
+    f3 o0, du, dv, dir; uint64_t nu;            // 1
+    const float *points, *normals; uint64_t seed; float offset;                     // 2
+    uint32_t dir_begin, dir_count;              // 2: this launch draws directions [dir_begin, dir_begin + dir_count) of each point
+};
+
+__device__ __forceinline__ Ray source_ray(const RaySource &S, uint64_t i)
+{
+    if (S.kind == 0) return load_ray(S.rays, i);
+    if (S.kind == 1) {
+        float fu = (float)(i % S.nu), fv = (float)(i / S.nu);
+        f3 O = { __fmaf_rn(fu, S.du.x, __fmaf_rn(fv, S.dv.x, S.o0.x)),
+                 __fmaf_rn(fu, S.du.y, __fmaf_rn(fv, S.dv.y, S.o0.y)),
+                 __fmaf_rn(fu, S.du.z, __fmaf_rn(fv, S.dv.z, S.o0.z)) };
+        return make_ray(O, S.dir);
+    }
+    const uint64_t p = i / S.dir_count;
+    const uint32_t k = S.dir_begin + (uint32_t)(i - p * S.dir_count);
+    f3 O = { S.points[3 * p], S.points[3 * p + 1], S.points[3 * p + 2] };
+    if (S.normals) {
+        O.x = __fmaf_rn(S.offset, S.normals[3 * p], O.x);
+        O.y = __fmaf_rn(S.offset, S.normals[3 * p + 1], O.y);
+        O.z = __fmaf_rn(S.offset, S.normals[3 * p + 2], O.z);
+    }
+    return make_ray(O, hemisphere_dir(S.seed, p, k));
+}
+
 struct TraceArgs {
     SceneView sc;
-    const float *rays; uint64_t N; uint32_t row_len; uint64_t nslots;
-    CastOut out; uint8_t *occluded; float tnear, tfar;
+    RaySource src;
+    uint64_t N; uint32_t row_len; uint64_t nslots;
+    CastOut out; uint8_t *occluded; float tnear, tfar;          // MODE 0 / 1
+    int32_t *counts;                                            // MODE 2
+    uint32_t *accum; const uint64_t *goff;                      // MODE 3 / 4
     unsigned long long *cursor, *stats;
     int refill, want, tri_min, node_path;
-    // MODE 2 (count_intersections)
-    int32_t *counts;
-    int depth;          // stack entries per thread; the hit set starts behind the stack in shared memory
+    int depth;          // stack entries per thread; the MODE 2 hit set starts behind the stack in shared memory
     int multi_geom;     // > 1 geometry: the set also keeps geometry ids
 };
 
@@ -45,7 +114,9 @@ template <int MODE, bool COUNTERS>
 __global__ void __launch_bounds__(TR_BLOCK)
 k_trace5(const TraceArgs A)
 {
-    extern __shared__ int sstack[];                 // [depth][TR_BLOCK]
+    constexpr bool CLOSEST = MODE == 0 || MODE == 3;
+    constexpr bool ANYHIT = MODE == 1 || MODE == 4;
+    extern __shared__ int sstack[];                 // [depth][TR_BLOCK] (+ MODE 2: [CNT_SET][TR_BLOCK] t, geometry)
     int *const sbase = sstack + threadIdx.x;
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
@@ -95,8 +166,12 @@ k_trace5(const TraceArgs A)
                     }
                 } else if (MODE == 1) {
                     A.occluded[ray_i] = best_prim != QSMRT_INVALID ? 1 : 0;
-                } else {
+                } else if (MODE == 2) {
                     A.counts[ray_i] = overflow ? -1 : cnt;           // -1: k_count_fix recounts this ray exactly
+                } else if (MODE == 3) {
+                    if (best_prim != QSMRT_INVALID) atomicAdd(&A.accum[(A.goff ? A.goff[best_geom] : 0ull) + best_prim], 1u);
+                } else {
+                    if (best_prim == QSMRT_INVALID) atomicAdd(&A.accum[ray_i / A.src.dir_count], 1u);     // unoccluded sky ray
                 }
             }
             if (exhausted) {
@@ -111,9 +186,9 @@ k_trace5(const TraceArgs A)
                     const uint64_t slot = base + __popc(im & lt);
                     uint64_t i;
                     if (slot < A.nslots && ray_index_of_slot(slot, A.N, A.row_len, i)) {
-                        r = load_ray(A.rays, i);
+                        r = source_ray(A.src, i);
                         ray_i = i; have_ray = true;
-                        best_t = MODE == 1 ? A.tfar : INFINITY;
+                        best_t = ANYHIT ? A.tfar : INFINITY;
                         cnt = 0; overflow = false;
                         best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
                         sbase[0] = TR_SENTINEL; sptr = sbase + TR_BLOCK;
@@ -162,7 +237,7 @@ k_trace5(const TraceArgs A)
                 const bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, best_t, t1);
                 if (COUNTERS) ++n_node;
                 // take child 1 first when child 0 is missed, or both are hit and 1 is nearer
-                const bool take1 = !h0 || (MODE == 0 && h1 && (t1 < t0));
+                const bool take1 = !h0 || (CLOSEST && h1 && (t1 < t0));
                 int nxt = take1 ? c1 : c0;
                 const int other = c0 ^ c1 ^ nxt;        // the child not taken (one LOP3)
                 if (h0 && h1) { *sptr = other; sptr += TR_BLOCK; }
@@ -183,7 +258,7 @@ k_trace5(const TraceArgs A)
                 load_tri(tris, tri_i, p0, p1, p2);
                 MtHit h;
                 if (COUNTERS) ++n_tri;
-                if (MODE == 0) {
+                if (CLOSEST) {
                     if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
                         float tt = __fdiv_rn(h.T, h.absDen);
                         uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
@@ -192,7 +267,7 @@ k_trace5(const TraceArgs A)
                     }
                     ++tri_i;
                     if (tri_i == tri_end && cur < 0) PARK_LEAF5();
-                } else if (MODE == 1) {
+                } else if (ANYHIT) {
                     if (mt_test(p0, p1, p2, r.O, r.D, A.tnear, A.tfar, h)) {
                         best_prim = 0u; cur = TR_SENTINEL; tri_i = tri_end;       // occluded: drop the rest
                     } else {
@@ -224,4 +299,15 @@ k_trace5(const TraceArgs A)
         if (lane == 0) { atomicAdd(&A.stats[0], (unsigned long long)n_node); atomicAdd(&A.stats[1], (unsigned long long)n_tri); }
     }
 #undef PARK_LEAF5
+}
+
+// materialise the hemisphere rays of SRC 2 (tests and small batches): rays[n_points * n_dirs][6]
+__global__ void __launch_bounds__(256)
+k_gen_hemisphere(float *__restrict__ rays, RaySource S, uint64_t n)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r = source_ray(S, i);
+    float2 *p = reinterpret_cast<float2 *>(rays + 6 * i);
+    p[0] = make_float2(r.O.x, r.O.y); p[1] = make_float2(r.O.z, r.D.x); p[2] = make_float2(r.D.y, r.D.z);
 }

@@ -840,6 +840,29 @@ template <int MODE> int sched_grid(int *blocks)
     return 0;
 }
 
+
+// common launch of the persistent kernel: tuning, work cursor, occupancy-sized grid
+template <int MODE, bool COUNTERS>
+int launch_trace5(TraceArgs &a, size_t smem, cudaStream_t st)
+{
+    a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
+    a.node_path = a.sc.node_tex ? g_trv_node_path : 0;
+    if (next_cursor(&a.cursor, st)) return 1;
+    int dev = 0, per_sm = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_trace5<MODE, COUNTERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<MODE, COUNTERS>, TR_BLOCK, smem));
+    if (per_sm < 1) { qsmrt_set_error("persistent kernel does not fit (smem %zu)", smem); return 1; }
+    unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
+    k_trace5<MODE, COUNTERS><<<g, TR_BLOCK, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+inline size_t stack_bytes(const SceneView &sc) { return (size_t)((int)sc.height + 2) * TR_BLOCK * sizeof(int); }
+inline bool use_v5(const SceneView &sc, size_t smem) { return g_trv_variant == 5 && sc.ntris && smem <= 96 * 1024; }
+
 uint64_t slots_for(uint64_t N, uint32_t row_len)
 {
     if (!row_len) return N;
@@ -858,30 +881,17 @@ int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t r
         uint64_t rows = N / row_len, warps = (uint64_t)((row_len + 7u) / 8u) * ((rows + 3) / 4);
         grid = (unsigned)((warps + TR_BLOCK / 32 - 1) / (TR_BLOCK / 32));
     }
-    const int depth = (int)sc.height + 2;                       // sentinel + one pending entry per level
-    if (g_trv_variant == 5 && depth * TR_BLOCK * (int)sizeof(int) <= 48 * 1024) {
+    if (use_v5(sc, stack_bytes(sc))) {
         TraceArgs a{};
-        a.sc = sc; a.rays = rays; a.N = N; a.row_len = row_len; a.nslots = slots_for(N, row_len);
+        a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = row_len; a.nslots = slots_for(N, row_len);
         a.out = CastOut{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
-        a.occluded = nullptr; a.tnear = 0.0f; a.tfar = INFINITY;
-        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]); a.node_path = sc.node_tex ? g_trv_node_path : 0;
-        if (next_cursor(&a.cursor, st)) return 1;
-        const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
-        int dev = 0, per_sm = 0, sms = 0;
-        CUDA_TRY(cudaGetDevice(&dev));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
         if (g_trv_tuning[3]) {
             if (!g_trv_stats_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g_trv_stats_dev), 16 * sizeof(unsigned long long)));
             CUDA_TRY(cudaMemsetAsync(g_trv_stats_dev, 0, 16 * sizeof(unsigned long long), st));
             a.stats = g_trv_stats_dev;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<0, true>, TR_BLOCK, smem));
-            unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
-            k_trace5<0, true><<<g, TR_BLOCK, smem, st>>>(a);
-        } else {
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<0, false>, TR_BLOCK, smem));
-            unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
-            k_trace5<0, false><<<g, TR_BLOCK, smem, st>>>(a);
-        }
+            if (launch_trace5<0, true>(a, stack_bytes(sc), st)) return 1;
+        } else if (launch_trace5<0, false>(a, stack_bytes(sc), st)) return 1;
     } else if (g_trv_variant == 4) {
         unsigned long long *cursor = nullptr;
         int blocks = 0;
@@ -918,20 +928,12 @@ int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, 
     if (N == 0) return 0;
     const int depth = (int)sc.height + 2;
     const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * CNT_SET) * TR_BLOCK * sizeof(int);
-    if (g_trv_variant == 5 && sc.ntris && smem <= 96 * 1024) {
+    if (use_v5(sc, smem)) {
         TraceArgs a{};
-        a.sc = sc; a.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
-        a.out = CastOut{ nullptr, nullptr, nullptr, nullptr, nullptr };
+        a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
         a.counts = out; a.depth = depth; a.multi_geom = ngeoms > 1;
-        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
-        if (next_cursor(&a.cursor, st)) return 1;
-        int dev = 0, per_sm = 0, sms = 0;
-        CUDA_TRY(cudaGetDevice(&dev));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CUDA_TRY(cudaFuncSetAttribute(k_trace5<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<2, false>, TR_BLOCK, smem));
-        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (N + TR_BLOCK - 1) / TR_BLOCK);
-        k_trace5<2, false><<<g, TR_BLOCK, smem, st>>>(a);
+        if (launch_trace5<2, false>(a, smem, st)) return 1;
+        int sms = 148;
         k_count_fix<<<(unsigned)std::min<uint64_t>(grid_for(N, TR_BLOCK), (uint64_t)sms * 8), TR_BLOCK, 0, st>>>(sc, rays, N, out);
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -944,21 +946,11 @@ int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, 
 int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st)
 {
     if (N == 0) return 0;
-    const int depth = (int)sc.height + 2;
-    if (g_trv_variant == 5 && depth * TR_BLOCK * (int)sizeof(int) <= 48 * 1024) {
+    if (use_v5(sc, stack_bytes(sc))) {
         TraceArgs a{};
-        a.sc = sc; a.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
-        a.out = CastOut{ nullptr, nullptr, nullptr, nullptr, nullptr };
-        a.occluded = out; a.tnear = tnear; a.tfar = tfar;
-        a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]); a.node_path = sc.node_tex ? g_trv_node_path : 0;
-        if (next_cursor(&a.cursor, st)) return 1;
-        const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
-        int dev = 0, per_sm = 0, sms = 0;
-        CUDA_TRY(cudaGetDevice(&dev));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<1, false>, TR_BLOCK, smem));
-        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (N + TR_BLOCK - 1) / TR_BLOCK);
-        k_trace5<1, false><<<g, TR_BLOCK, smem, st>>>(a);
+        a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
+        a.occluded = out; a.tnear = tnear; a.tfar = tfar; a.depth = (int)sc.height + 2;
+        if (launch_trace5<1, false>(a, stack_bytes(sc), st)) return 1;
     } else {
         k_test_occlusions<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, tnear, tfar, out);
     }
@@ -1046,6 +1038,52 @@ int trv_accumulate_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, 
 {
     if (N == 0) return 0;
     k_accumulate_hits<<<grid_for(N, 256), 256, 0, st>>>(geom, prim, N, goff, ngeoms, tri_counts);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Fused drivers: rays generated inside the persistent kernel, results reduced on the device.
+int trv_sun_exposure(const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+                     const float dv[3], const float dir[3], const uint64_t *goff, uint32_t *tri_counts, cudaStream_t st)
+{
+    if (nu * nv == 0 || sc.ntris == 0) return 0;
+    if (!use_v5(sc, stack_bytes(sc))) { qsmrt_set_error("sun_exposure needs the persistent kernel (BVH height %u too deep?)", sc.height); return 1; }
+    TraceArgs a{};
+    a.sc = sc; a.src.kind = 1; a.src.nu = nu;
+    a.src.o0 = f3{ o0[0], o0[1], o0[2] }; a.src.du = f3{ du[0], du[1], du[2] };
+    a.src.dv = f3{ dv[0], dv[1], dv[2] }; a.src.dir = f3{ dir[0], dir[1], dir[2] };
+    a.N = nu * nv; a.row_len = nu >= 8 && nu < (1ull << 32) ? (uint32_t)nu : 0; a.nslots = slots_for(a.N, a.row_len);
+    a.accum = tri_counts; a.goff = goff; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
+    return launch_trace5<3, false>(a, stack_bytes(sc), st);
+}
+
+static RaySource hemisphere_source(const float *points, const float *normals, uint32_t dir_begin, uint32_t dir_count,
+                                    uint64_t seed, float offset)
+{
+    RaySource s{};
+    s.kind = 2; s.points = points; s.normals = normals; s.dir_begin = dir_begin; s.dir_count = dir_count;
+    s.seed = seed; s.offset = offset;
+    return s;
+}
+
+int trv_sky_visibility(const SceneView &sc, const float *points, const float *normals, uint64_t n_points,
+                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st)
+{
+    if (n_points == 0 || dir_count == 0) return 0;
+    if (g_trv_variant != 5 || stack_bytes(sc) > 96 * 1024) { qsmrt_set_error("sky_visibility needs the persistent kernel"); return 1; }
+    TraceArgs a{};
+    a.sc = sc; a.src = hemisphere_source(points, normals, dir_begin, dir_count, seed, offset);
+    a.N = n_points * (uint64_t)dir_count; a.row_len = 0; a.nslots = a.N;
+    a.accum = unoccluded; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
+    return launch_trace5<4, false>(a, stack_bytes(sc), st);
+}
+
+int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points,
+                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, cudaStream_t st)
+{
+    uint64_t n = n_points * (uint64_t)dir_count;
+    if (n == 0) return 0;
+    k_gen_hemisphere<<<grid_for(n, 256), 256, 0, st>>>(rays, hemisphere_source(points, normals, dir_begin, dir_count, seed, offset), n);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

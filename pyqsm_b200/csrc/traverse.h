@@ -27,3 +27,9 @@ int trv_mark_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const 
                   uint8_t *vert_hit, cudaStream_t st);
 int trv_accumulate_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const uint64_t *goff,
                         uint32_t ngeoms, uint32_t *tri_counts, cudaStream_t st);
+int trv_sun_exposure(const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+                     const float dv[3], const float dir[3], const uint64_t *goff, uint32_t *tri_counts, cudaStream_t st);
+int trv_sky_visibility(const SceneView &sc, const float *points, const float *normals, uint64_t n_points,
+                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st);
+int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points,
+                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, cudaStream_t st);

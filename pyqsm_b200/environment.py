@@ -1,0 +1,147 @@
+"""Environmental ray-casting drivers: sunlight angle, rain angle and sky
+(cloud-cover / gap-fraction) simulations over a ``RaycastingScene``.
+
+The reference only states the intent -- ``README.md:131`` ("simulate ...
+sunlight angle, cloud cover and rain angle"), ``data/notes/methods.md:16,53-55``
+and ``data/notes/epiphyte_isolation_methods.md:17,43`` ("Ray casting: Parallel
+rays from nadir") -- and its only parallel-ray code is the 10 x 10 vertical
+grid of ``pyQSM/viz/ray_casting.py:159-165``.  These drivers are that pattern
+at scale: rays are generated inside the
+traversal kernel and the per-triangle / per-point results are reduced on the
+device, so neither the 24 B/ray of input nor the 32 B/ray of ``cast_rays``
+output exists.  Each function equals a composition of the ``RaycastingScene``
+queries (the tests check exactly that).
+
+Multi-GPU: pass ``shard=(rank, world)`` to take this rank's share of the
+angles / directions and all-reduce the integer results over
+``torch.distributed`` (no collective during traversal).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, synthetic as syn
+from .distributed import allreduce_sum, shard_angles, shard_range
+
+
+def _f3(x):
+    return (C.c_float * 3)(*[float(v) for v in x])
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def sun_exposure(scene, angles, grid=(4000, 4000), margin=0.05, shard=None, per_angle=False):
+    """Sunlit-ray counts per triangle for a sweep of solar ``angles`` =
+    [(elevation_deg, azimuth_deg), ...].
+
+    For every angle a ``grid = (nu, nv)`` of parallel rays covering the scene
+    bounds (as seen from the sun) is cast; a triangle's count is the number of
+    rays whose *closest* hit it owns, i.e. its sunlit projected area in units
+    of one ray cell.  Returns ``{"counts": int32 [T] (or [A, T] with
+    per_angle), "cell_area": [A] m^2 per ray, "rays": total rays cast}`` on
+    the scene's device.  Triangles are in scene order (geometry offsets +
+    primitive id)."""
+    L = _lib.load()
+    scene.commit()
+    st = scene.stats()
+    ntri = int(st["num_triangles"])
+    lo, hi = np.asarray(st["scene_lo"], np.float64), np.asarray(st["scene_hi"], np.float64)
+    angles = list(angles)
+    mine = shard_angles(list(enumerate(angles)), *shard) if shard else list(enumerate(angles))
+    nu, nv = int(grid[0]), int(grid[1])
+    dev = scene.device
+    with torch.cuda.device(dev):
+        rows = len(angles) if per_angle else 1
+        counts = torch.zeros(rows, max(ntri, 1), dtype=torch.int32, device=dev)
+        cell = torch.zeros(len(angles), dtype=torch.float64)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        for k, (el, az) in mine:
+            o0, du, dv, d = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), nu, nv, margin)
+            cell[k] = float(np.linalg.norm(du.astype(np.float64)) * np.linalg.norm(dv.astype(np.float64)))
+            row = counts[k if per_angle else 0]
+            _lib.check(L.qsmrt_sun_exposure(scene._h, nu, nv, _f3(o0), _f3(du), _f3(dv), _f3(d), _ptr(row), stream))
+        if shard:
+            allreduce_sum(counts)
+            cell_dev = cell.to(dev)
+            allreduce_sum(cell_dev)
+            cell = cell_dev.cpu()
+        counts = counts[:, :ntri]
+    return {"counts": counts if per_angle else counts[0], "cell_area": cell, "rays": nu * nv * len(angles)}
+
+
+def rain_interception(scene, angle_from_vertical_deg=20.0, azimuth_deg=0.0, grid=(10000, 10000), margin=0.05,
+                      chunk_rows=2000, shard=None):
+    """Rain at a slant: a ``grid`` of parallel rays ``angle_from_vertical_deg``
+    off nadir.  Returns ``{"intersections": int64 histogram of the per-ray
+    intersection counts, "intercepted_fraction": share of rays that hit
+    anything, "mean_layers": mean number of surfaces crossed}`` using
+    ``count_intersections`` (how many canopy layers a drop would cross)."""
+    L = _lib.load()
+    scene.commit()
+    st = scene.stats()
+    lo, hi = np.asarray(st["scene_lo"], np.float64), np.asarray(st["scene_hi"], np.float64)
+    nu, nv = int(grid[0]), int(grid[1])
+    o0, du, dv, d = syn.parallel_ray_grid(lo, hi, syn.sun_direction(90.0 - angle_from_vertical_deg, azimuth_deg), nu, nv, margin)
+    rows = shard_range(nv, *shard) if shard else (0, nv)
+    dev = scene.device
+    hist = torch.zeros(256, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        buf = torch.empty(min(chunk_rows, nv) * nu, 6, dtype=torch.float32, device=dev)
+        cnt = torch.empty(min(chunk_rows, nv) * nu, dtype=torch.int32, device=dev)
+        for r0 in range(rows[0], rows[1], chunk_rows):
+            nr = min(chunk_rows, rows[1] - r0)
+            o = (o0.astype(np.float64) + r0 * dv.astype(np.float64)).astype(np.float32)
+            _lib.check(L.qsmrt_gen_parallel_rays(_ptr(buf), nu, nr, _f3(o), _f3(du), _f3(dv), _f3(d), stream))
+            _lib.check(L.qsmrt_count_intersections(scene._h, _ptr(buf), nu * nr, _ptr(cnt), stream))
+            hist += torch.bincount(cnt[: nu * nr].clamp(max=255).to(torch.int64), minlength=256)
+        if shard:
+            allreduce_sum(hist)
+    total = int(hist.sum())
+    layers = torch.arange(256, device=dev, dtype=torch.float64)
+    return {"intersections": hist, "intercepted_fraction": float(1.0 - hist[0].item() / max(total, 1)),
+            "mean_layers": float((hist.to(torch.float64) * layers).sum().item() / max(total, 1)), "rays": total}
+
+
+def sky_gap_fraction(scene, points, normals=None, n_dirs=1000, seed=5, offset=1e-4, shard=None):
+    """Diffuse-sky (cloud cover) visibility: for each query point the share of
+    ``n_dirs`` directions, uniform over the upper hemisphere about +z, along
+    which no triangle is hit (any-hit occlusion from ``point + offset *
+    normal``).  Directions come from a counter-based hash of (seed, point,
+    k), so a point sees the same sample however the work is sharded.
+    Returns float32 ``[n_points]`` on the scene's device."""
+    L = _lib.load()
+    dev = scene.device
+    scene.commit()
+    with torch.cuda.device(dev):
+        p = torch.as_tensor(points, dtype=torch.float32).to(dev).contiguous().reshape(-1, 3)
+        nrm = None if normals is None else torch.as_tensor(normals, dtype=torch.float32).to(dev).contiguous().reshape(-1, 3)
+        free = torch.zeros(max(p.shape[0], 1), dtype=torch.int32, device=dev)
+        b, e = shard_range(int(n_dirs), *shard) if shard else (0, int(n_dirs))
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if e > b and p.shape[0]:
+            _lib.check(L.qsmrt_sky_visibility(scene._h, _ptr(p), _ptr(nrm), p.shape[0], int(seed), float(offset), b, e - b,
+                                              _ptr(free), stream))
+        if shard:
+            allreduce_sum(free)
+        return free[: p.shape[0]].to(torch.float32) / float(n_dirs)
+
+
+def hemisphere_rays(points, normals=None, n_dirs=16, seed=5, offset=1e-4, dir_begin=0, device=None):
+    """The exact rays ``sky_gap_fraction`` traces, materialised: float32 ``[n_points * n_dirs, 6]``."""
+    L = _lib.load()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        p = torch.as_tensor(points, dtype=torch.float32).to(dev).contiguous().reshape(-1, 3)
+        nrm = None if normals is None else torch.as_tensor(normals, dtype=torch.float32).to(dev).contiguous().reshape(-1, 3)
+        rays = torch.empty(p.shape[0] * int(n_dirs), 6, dtype=torch.float32, device=dev)
+        if rays.numel():
+            _lib.check(L.qsmrt_gen_hemisphere_rays(_ptr(rays), _ptr(p), _ptr(nrm), p.shape[0], int(seed), float(offset),
+                                                   int(dir_begin), int(n_dirs), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return rays
