@@ -142,6 +142,21 @@ int qsmrt_accumulate_hits(qsmrt_scene *scene, const uint32_t *geometry_ids,
                           const uint32_t *primitive_ids, uint64_t N,
                           uint32_t *tri_counts, void *stream);
 
+/* scene.compute_closest_points / compute_distance  (Open3D; the engine under
+ * compute_signed_distance, ray_casting.py:250,255).  query points [N x 3]
+ * float32 on the device.  closest[N x 3], distance[N] (inf for an empty
+ * scene), ids, uv[N x 2] (u <-> v1, v <-> v2), normals[N x 3]; any NULL. */
+int qsmrt_closest_points(qsmrt_scene *scene, const float *points_dev, uint64_t N,
+                         float *closest, float *distance, uint32_t *geometry_ids,
+                         uint32_t *primitive_ids, float *primitive_uvs,
+                         float *primitive_normals, void *stream);
+
+/* scene.compute_signed_distance(query_points)  -- ray_casting.py:250,255:
+ * distance[N], negative where compute_occupancy is 1 (odd intersection count
+ * along (1,1,1)).  Synchronises (frees its scratch). */
+int qsmrt_signed_distance(qsmrt_scene *scene, const float *points_dev, uint64_t N,
+                          float *distance, void *stream);
+
 /* Environmental drivers (README.md:131 "sunlight angle, cloud cover and rain
  * angle"; data/notes/methods.md:16,53-55): the rays are generated inside the
  * traversal kernel and the results reduced on the device, so no 24 B/ray of

@@ -53,6 +53,7 @@ def _load():
     L.orc_count_intersections.argtypes = [vp, fp, C.c_uint64, C.c_int, i32p, C.POINTER(_Counters)]
     L.orc_test_occlusions.argtypes = [vp, fp, C.c_uint64, C.c_int, C.c_float, C.c_float, u8p]
     L.orc_list_intersections.argtypes = [vp, fp, C.c_uint64, C.c_int, i64p, i64p, fp, u32p, u32p, fp]
+    L.orc_closest_points.argtypes = [vp, fp, C.c_uint64, C.c_int, fp, fp, u32p, u32p, fp, fp]
     L.orc_edge_flags.argtypes = [vp, fp, C.c_uint64, C.c_int, C.c_float, u8p]
     L.orc_num_triangles.restype = C.c_uint64
     L.orc_num_triangles.argtypes = [vp]
@@ -174,6 +175,36 @@ class OracleScene:
                                        _p(out["geometry_ids"], C.c_uint32), _p(out["primitive_ids"], C.c_uint32),
                                        _p(out["primitive_uvs"], C.c_float))
         return out
+
+    def compute_closest_points(self, query_points, mode=BVH):
+        """Open3D ComputeClosestPoints keys (points, geometry_ids, primitive_ids, primitive_uvs,
+        primitive_normals) plus ``distance``."""
+        p = _f32(query_points, 3)
+        shp = p.shape[:-1]
+        p2 = p.reshape(-1, 3)
+        n = p2.shape[0]
+        self.commit()
+        out = dict(points=np.empty((n, 3), np.float32), distance=np.empty(n, np.float32),
+                   geometry_ids=np.empty(n, np.uint32), primitive_ids=np.empty(n, np.uint32),
+                   primitive_uvs=np.empty((n, 2), np.float32), primitive_normals=np.empty((n, 3), np.float32))
+        self._L.orc_closest_points(self._s, _p(p2, C.c_float), n, mode, _p(out["points"], C.c_float), _p(out["distance"], C.c_float),
+                                   _p(out["geometry_ids"], C.c_uint32), _p(out["primitive_ids"], C.c_uint32),
+                                   _p(out["primitive_uvs"], C.c_float), _p(out["primitive_normals"], C.c_float))
+        for k in out:
+            out[k] = out[k].reshape(shp + out[k].shape[1:])
+        return out
+
+    def compute_distance(self, query_points, mode=BVH):
+        return self.compute_closest_points(query_points, mode)["distance"]
+
+    def compute_occupancy(self, query_points, mode=BVH):
+        p = _f32(query_points, 3)
+        rays = np.concatenate([p, np.ones_like(p)], axis=-1)
+        return (self.count_intersections(rays, mode) % 2 == 1).astype(np.float32)
+
+    def compute_signed_distance(self, query_points, mode=BVH):
+        d = self.compute_distance(query_points, mode)
+        return np.where(self.compute_occupancy(query_points, mode) > 0, -d, d).astype(np.float32)
 
     def edge_flags(self, rays, eps=1e-6, mode=BVH):
         """bit0: a triangle plane is crossed with a barycentric within ``eps`` of

@@ -665,6 +665,133 @@ void orc_edge_flags(const orc_scene *s, const float *rays, uint64_t N, int mode,
     }
 }
 
+/* ------------------------------------------------------- closest points
+ * Open3D RaycastingScene::ComputeClosestPoints (rtcPointQuery + ClosestPointFunc):
+ * closest point on each candidate triangle by the region test of Ericson,
+ * "Real-Time Collision Detection" 5.1.5 (the closestPointTriangle of Embree's
+ * closest_point tutorial, which Open3D uses), keep the smallest distance.
+ * Reference call sites: pyQSM/viz/ray_casting.py:250,255 (compute_signed_distance).
+ * Points whose nearest feature is an edge or vertex are equidistant to several
+ * triangles; Embree keeps whichever it meets first, here the lowest
+ * (geometry, primitive) among exactly equal squared distances wins.
+ * Triangle corners come from the 48-byte record: a = v0, ab = -e1, ac = e2. */
+typedef struct { float d2; v3 q; float u, v; uint32_t geom, prim; v3 Ng; } cp_best;
+
+static inline v3 v3add(v3 a, v3 b) { v3 r = { a.x + b.x, a.y + b.y, a.z + b.z }; return r; }
+static inline v3 v3madd(v3 a, float s, v3 b) { v3 r = { fmaf(s, b.x, a.x), fmaf(s, b.y, a.y), fmaf(s, b.z, a.z) }; return r; }
+
+static inline void cp_triangle(const orc_tri *tr, v3 p, v3 *q, float *bu, float *bv)
+{
+    v3 a = tr->v0;
+    v3 ab = { -tr->e1.x, -tr->e1.y, -tr->e1.z }, ac = tr->e2;
+    v3 b = v3add(a, ab), c = v3add(a, ac);
+    v3 ap = v3sub(p, a);
+    float d1 = v3dot(ab, ap), d2 = v3dot(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) { *q = a; *bu = 0.0f; *bv = 0.0f; return; }
+    v3 bp = v3sub(p, b);
+    float d3 = v3dot(ab, bp), d4 = v3dot(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) { *q = b; *bu = 1.0f; *bv = 0.0f; return; }
+    v3 cp = v3sub(p, c);
+    float d5 = v3dot(ab, cp), d6 = v3dot(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) { *q = c; *bu = 0.0f; *bv = 1.0f; return; }
+    float vc = fmaf(d1, d4, -(d3 * d2));
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { float v = d1 / (d1 - d3); *q = v3madd(a, v, ab); *bu = v; *bv = 0.0f; return; }
+    float vb = fmaf(d5, d2, -(d1 * d6));
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { float w = d2 / (d2 - d6); *q = v3madd(a, w, ac); *bu = 0.0f; *bv = w; return; }
+    float va = fmaf(d3, d6, -(d5 * d4));
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        *q = v3madd(b, w, v3sub(c, b)); *bu = 1.0f - w; *bv = w; return;
+    }
+    float denom = 1.0f / (va + vb + vc);
+    float v = vb * denom, w = vc * denom;
+    *q = v3madd(v3madd(a, v, ab), w, ac); *bu = v; *bv = w;
+}
+
+static inline void cp_consider(const orc_tri *tr, v3 p, cp_best *best)
+{
+    v3 q; float u, v;
+    cp_triangle(tr, p, &q, &u, &v);
+    v3 d = v3sub(q, p);
+    float d2 = v3dot(d, d);
+    int better = (d2 < best->d2) ||
+                 (d2 == best->d2 && (tr->geom < best->geom || (tr->geom == best->geom && tr->prim < best->prim)));
+    if (!better) return;
+    best->d2 = d2; best->q = q; best->u = u; best->v = v; best->geom = tr->geom; best->prim = tr->prim;
+    best->Ng = v3cross(tr->e2, tr->e1);
+}
+
+static inline float box_dist2(const float *lo, const float *hi, v3 p)
+{
+    float dx = fmaxf(fmaxf(lo[0] - p.x, p.x - hi[0]), 0.0f);
+    float dy = fmaxf(fmaxf(lo[1] - p.y, p.y - hi[1]), 0.0f);
+    float dz = fmaxf(fmaxf(lo[2] - p.z, p.z - hi[2]), 0.0f);
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+static void cp_one(const orc_scene *s, v3 p, int mode, cp_best *best)
+{
+    uint64_t n = s->ntris;
+    best->d2 = INFINITY; best->geom = best->prim = ORC_INVALID_ID; best->u = best->v = 0.0f;
+    best->q.x = best->q.y = best->q.z = 0.0f; best->Ng = best->q;
+    if (n == 0) return;
+    if (mode == 0 || n == 1) { for (uint64_t i = 0; i < n; ++i) cp_consider(&s->tris[i], p, best); return; }
+    int32_t stk[ORC_STACK]; float sd[ORC_STACK]; int sp = 0;
+    int32_t cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            const orc_node *nd = &s->nodes[cur];
+            int32_t ch[2] = { nd->left, nd->right };
+            float cd[2];
+            for (int k = 0; k < 2; ++k) {
+                const float *lo = ch[k] < 0 ? s->leaf_lo + 3 * (~ch[k]) : s->nodes[ch[k]].lo;
+                const float *hi = ch[k] < 0 ? s->leaf_hi + 3 * (~ch[k]) : s->nodes[ch[k]].hi;
+                cd[k] = box_dist2(lo, hi, p);
+            }
+            int h0 = cd[0] <= best->d2, h1 = cd[1] <= best->d2;
+            if (h0 && h1) {
+                int nearc = cd[1] < cd[0] ? 1 : 0;
+                stk[sp] = ch[1 - nearc]; sd[sp] = cd[1 - nearc]; ++sp;
+                cur = ch[nearc];
+                continue;
+            }
+            if (h0) { cur = ch[0]; continue; }
+            if (h1) { cur = ch[1]; continue; }
+        } else {
+            cp_consider(&s->stris[~cur], p, best);
+        }
+        for (;;) {
+            if (sp == 0) return;
+            --sp;
+            if (sd[sp] <= best->d2) { cur = stk[sp]; break; }
+        }
+    }
+}
+
+/* points[N][3] -> closest[N][3], distance[N], geometry/primitive ids, uv[N][2], normals[N][3] */
+void orc_closest_points(const orc_scene *s, const float *pts, uint64_t N, int mode, float *closest, float *dist,
+                        uint32_t *geom, uint32_t *prim, float *uv, float *nrm)
+{
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)N; ++i) {
+        v3 p = { pts[3 * i], pts[3 * i + 1], pts[3 * i + 2] };
+        cp_best b;
+        cp_one(s, p, mode, &b);
+        int ok = b.prim != ORC_INVALID_ID;
+        if (closest) { closest[3 * i] = b.q.x; closest[3 * i + 1] = b.q.y; closest[3 * i + 2] = b.q.z; }
+        if (dist) dist[i] = ok ? sqrtf(b.d2) : INFINITY;
+        if (geom) geom[i] = b.geom;
+        if (prim) prim[i] = b.prim;
+        if (uv) { uv[2 * i] = b.u; uv[2 * i + 1] = b.v; }
+        if (nrm) {
+            if (ok) {
+                float inv = 1.0f / sqrtf(v3dot(b.Ng, b.Ng));
+                nrm[3 * i] = b.Ng.x * inv; nrm[3 * i + 1] = b.Ng.y * inv; nrm[3 * i + 2] = b.Ng.z * inv;
+            } else { nrm[3 * i] = nrm[3 * i + 1] = nrm[3 * i + 2] = 0.0f; }
+        }
+    }
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -47,6 +47,8 @@ SYMBOLS = {
     "qsmrt_gen_pinhole_rays": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp]),
     "qsmrt_mark_hit_primitives": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "qsmrt_accumulate_hits": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "qsmrt_closest_points": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qsmrt_signed_distance": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "qsmrt_sun_exposure": (C.c_int, [_vp, _u64, _u64, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "qsmrt_sky_visibility": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp, _vp]),
     "qsmrt_gen_hemisphere_rays": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp]),

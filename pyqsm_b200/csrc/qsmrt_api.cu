@@ -528,6 +528,35 @@ int qsmrt_accumulate_hits(qsmrt_scene *s, const uint32_t *geom, const uint32_t *
     return trv_accumulate_hits(geom, prim, N, s->goff, (uint32_t)s->geoms.size(), tri_counts, st);
 }
 
+int qsmrt_closest_points(qsmrt_scene *s, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
+                         uint32_t *prim, float *uv, float *nrm, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (N && !pts) FAIL("query points pointer is null");
+    if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    return trv_closest_points(view_of(s), pts, N, closest, dist, geom, prim, uv, nrm, st);
+}
+
+int qsmrt_signed_distance(qsmrt_scene *s, const float *pts, uint64_t N, float *dist, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (N && (!pts || !dist)) FAIL("null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    if (N == 0) return 0;
+    float *rays = nullptr; int32_t *counts = nullptr;
+    if (dmalloc(&rays, 6 * N) || dmalloc(&counts, N)) { dfree(rays); dfree(counts); return 1; }
+    int rc = trv_closest_points(view_of(s), pts, N, nullptr, dist, nullptr, nullptr, nullptr, nullptr, st) ||
+             trv_points_to_rays(pts, rays, N, st) ||
+             trv_count(view_of(s), rays, N, counts, (uint32_t)s->geoms.size(), st) ||
+             trv_apply_sign(dist, counts, N, st);
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { qsmrt_set_error("signed_distance: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+    dfree(rays); dfree(counts);
+    return rc;
+}
+
 int qsmrt_sun_exposure(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
                        const float dv[3], const float dir[3], uint32_t *tri_counts, void *stream)
 {

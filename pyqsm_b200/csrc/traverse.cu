@@ -782,6 +782,137 @@ k_accumulate_hits(const uint32_t *__restrict__ geom, const uint32_t *__restrict_
     atomicAdd(&tri_counts[goff[g] + p], 1u);
 }
 
+// ------------------------------------------------------------ closest points
+// Open3D ComputeClosestPoints / ComputeDistance (rtcPointQuery + ClosestPointFunc;
+// reference: compute_signed_distance at pyQSM/viz/ray_casting.py:250,255).
+// Bit-for-bit twin of oracle/qsmrt_oracle.c::cp_triangle / cp_one: Ericson's
+// region test on a = v0, ab = -e1, ac = e2; smallest squared distance wins,
+// exact ties go to the lowest (geometry, primitive).
+struct CpBest { float d2; f3 q; float u, v; uint32_t geom, prim, tri; };
+
+__device__ __forceinline__ f3 f3sub(f3 a, f3 b) { return f3{ __fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z) }; }
+__device__ __forceinline__ f3 f3add(f3 a, f3 b) { return f3{ __fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z) }; }
+__device__ __forceinline__ f3 f3madd(f3 a, float s, f3 b) { return f3{ __fmaf_rn(s, b.x, a.x), __fmaf_rn(s, b.y, a.y), __fmaf_rn(s, b.z, a.z) }; }
+
+__device__ __forceinline__ void cp_triangle(const float4 p0, const float4 p1, const float4 p2, f3 p, f3 &q, float &bu, float &bv)
+{
+    f3 a = { p0.x, p0.y, p0.z }, ab = { -p1.x, -p1.y, -p1.z }, ac = { p2.x, p2.y, p2.z };
+    f3 b = f3add(a, ab), c = f3add(a, ac);
+    f3 ap = f3sub(p, a);
+    float d1 = f3dot(ab, ap), d2 = f3dot(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) { q = a; bu = 0.0f; bv = 0.0f; return; }
+    f3 bp = f3sub(p, b);
+    float d3 = f3dot(ab, bp), d4 = f3dot(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) { q = b; bu = 1.0f; bv = 0.0f; return; }
+    f3 cp = f3sub(p, c);
+    float d5 = f3dot(ab, cp), d6 = f3dot(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) { q = c; bu = 0.0f; bv = 1.0f; return; }
+    float vc = __fmaf_rn(d1, d4, -__fmul_rn(d3, d2));
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { float v = __fdiv_rn(d1, __fsub_rn(d1, d3)); q = f3madd(a, v, ab); bu = v; bv = 0.0f; return; }
+    float vb = __fmaf_rn(d5, d2, -__fmul_rn(d1, d6));
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { float w = __fdiv_rn(d2, __fsub_rn(d2, d6)); q = f3madd(a, w, ac); bu = 0.0f; bv = w; return; }
+    float va = __fmaf_rn(d3, d6, -__fmul_rn(d5, d4));
+    float e43 = __fsub_rn(d4, d3), e56 = __fsub_rn(d5, d6);
+    if (va <= 0.0f && e43 >= 0.0f && e56 >= 0.0f) {
+        float w = __fdiv_rn(e43, __fadd_rn(e43, e56));
+        q = f3madd(b, w, f3sub(c, b)); bu = __fsub_rn(1.0f, w); bv = w; return;
+    }
+    float denom = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(va, vb), vc));
+    float v = __fmul_rn(vb, denom), w = __fmul_rn(vc, denom);
+    q = f3madd(f3madd(a, v, ab), w, ac); bu = v; bv = w;
+}
+
+__device__ __forceinline__ float box_dist2(float lox, float hix, float loy, float hiy, float loz, float hiz, f3 p)
+{
+    float dx = fmaxf(fmaxf(__fsub_rn(lox, p.x), __fsub_rn(p.x, hix)), 0.0f);
+    float dy = fmaxf(fmaxf(__fsub_rn(loy, p.y), __fsub_rn(p.y, hiy)), 0.0f);
+    float dz = fmaxf(fmaxf(__fsub_rn(loz, p.z), __fsub_rn(p.z, hiz)), 0.0f);
+    return __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
+}
+
+__global__ void __launch_bounds__(TR_BLOCK)
+k_closest_points(SceneView sc, const float *__restrict__ pts, uint64_t N, float *__restrict__ closest, float *__restrict__ dist,
+                 uint32_t *__restrict__ geom, uint32_t *__restrict__ prim, float2 *__restrict__ uv, float *__restrict__ nrm)
+{
+    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
+    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+    if (i >= N) return;
+    int spill[TR_LSTACK];
+    Stack st; st.s = sstack + threadIdx.x; st.loc = spill; st.sp = 0;
+    const f3 p = { pts[3 * i], pts[3 * i + 1], pts[3 * i + 2] };
+    CpBest best{ INFINITY, f3{ 0.0f, 0.0f, 0.0f }, 0.0f, 0.0f, QSMRT_INVALID, QSMRT_INVALID, 0u };
+    if (sc.ntris) {
+        int cur = 0;
+        for (;;) {
+            if (cur >= 0) {
+                float4 a, b, c; int4 d;
+                load_node(sc.nodes, cur, a, b, c, d);
+                float d0 = box_dist2(a.x, a.y, a.z, a.w, c.x, c.y, p);
+                float d1 = box_dist2(b.x, b.y, b.z, b.w, c.z, c.w, p);
+                bool h0 = d0 <= best.d2, h1 = d1 <= best.d2;
+                if (h0 & h1) {
+                    bool swap = d1 < d0;
+                    st.push(swap ? d.x : d.y);
+                    cur = swap ? d.y : d.x;
+                    continue;
+                }
+                if (h0) { cur = d.x; continue; }
+                if (h1) { cur = d.y; continue; }
+            } else {
+                uint32_t ref = (uint32_t)~cur, first = ref >> 2, count = (ref & 3u) + 1u;
+                for (uint32_t k = 0; k < count; ++k) {
+                    float4 p0, p1, p2;
+                    load_tri(sc.tris, first + k, p0, p1, p2);
+                    f3 q; float u, v;
+                    cp_triangle(p0, p1, p2, p, q, u, v);
+                    f3 df = f3sub(q, p);
+                    float d2 = f3dot(df, df);
+                    uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
+                    bool better = (d2 < best.d2) | ((d2 == best.d2) & ((pg < best.geom) | ((pg == best.geom) & (pp < best.prim))));
+                    if (better) { best.d2 = d2; best.q = q; best.u = u; best.v = v; best.geom = pg; best.prim = pp; best.tri = first + k; }
+                }
+            }
+            if (st.sp == 0) break;
+            cur = st.pop();
+        }
+    }
+    const bool ok = best.prim != QSMRT_INVALID;
+    if (closest) { closest[3 * i] = best.q.x; closest[3 * i + 1] = best.q.y; closest[3 * i + 2] = best.q.z; }
+    if (dist) dist[i] = ok ? __fsqrt_rn(best.d2) : INFINITY;
+    if (geom) geom[i] = best.geom;
+    if (prim) prim[i] = best.prim;
+    if (uv) uv[i] = make_float2(best.u, best.v);
+    if (nrm) {
+        float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (ok) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, best.tri, p0, p1, p2);
+            f3 Ng = f3cross(f3{ p2.x, p2.y, p2.z }, f3{ p1.x, p1.y, p1.z });
+            float inv = __fdiv_rn(1.0f, __fsqrt_rn(f3dot(Ng, Ng)));
+            nx = __fmul_rn(Ng.x, inv); ny = __fmul_rn(Ng.y, inv); nz = __fmul_rn(Ng.z, inv);
+        }
+        nrm[3 * i] = nx; nrm[3 * i + 1] = ny; nrm[3 * i + 2] = nz;
+    }
+}
+
+// signed distance = distance with the sign of the occupancy (count parity)
+__global__ void __launch_bounds__(256)
+k_apply_sign(float *__restrict__ dist, const int32_t *__restrict__ counts, uint64_t N)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < N && (counts[i] & 1)) dist[i] = -dist[i];
+}
+
+// rays for the occupancy test of Open3D ComputeOccupancy (nsamples == 1): origin = point, direction (1,1,1)
+__global__ void __launch_bounds__(256)
+k_points_to_rays(const float *__restrict__ pts, float *__restrict__ rays, uint64_t N)
+{
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float2 *p = reinterpret_cast<float2 *>(rays + 6 * i);
+    p[0] = make_float2(pts[3 * i], pts[3 * i + 1]); p[1] = make_float2(pts[3 * i + 2], 1.0f); p[2] = make_float2(1.0f, 1.0f);
+}
+
 inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 } // namespace
@@ -1084,6 +1215,31 @@ int trv_gen_hemisphere(float *rays, const float *points, const float *normals, u
     uint64_t n = n_points * (uint64_t)dir_count;
     if (n == 0) return 0;
     k_gen_hemisphere<<<grid_for(n, 256), 256, 0, st>>>(rays, hemisphere_source(points, normals, dir_begin, dir_count, seed, offset), n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_closest_points(const SceneView &sc, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
+                       uint32_t *prim, float *uv, float *nrm, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_closest_points<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, pts, N, closest, dist, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_points_to_rays(const float *pts, float *rays, uint64_t N, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_points_to_rays<<<grid_for(N, 256), 256, 0, st>>>(pts, rays, N);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int trv_apply_sign(float *dist, const int32_t *counts, uint64_t N, cudaStream_t st)
+{
+    if (N == 0) return 0;
+    k_apply_sign<<<grid_for(N, 256), 256, 0, st>>>(dist, counts, N);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

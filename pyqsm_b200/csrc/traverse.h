@@ -33,3 +33,7 @@ int trv_sky_visibility(const SceneView &sc, const float *points, const float *no
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st);
 int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points,
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, cudaStream_t st);
+int trv_closest_points(const SceneView &sc, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
+                       uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
+int trv_points_to_rays(const float *pts, float *rays, uint64_t N, cudaStream_t st);
+int trv_apply_sign(float *dist, const int32_t *counts, uint64_t N, cudaStream_t st);

@@ -261,6 +261,64 @@ class RaycastingScene:
                 self.output_device = saved
             return self._out((cnt % 2 == 1).to(torch.float32))
 
+    def _points(self, query_points):
+        p = _unwrap(query_points)
+        if p is None:
+            p = np.asarray(query_points, dtype=np.float32)
+        if isinstance(p, np.ndarray):
+            if p.dtype != np.float32:
+                raise RuntimeError(f"query_points has dtype {p.dtype}, but it must be Float32")
+            p = torch.from_numpy(np.ascontiguousarray(p))
+        elif p.dtype != torch.float32:
+            raise RuntimeError(f"query_points has dtype {p.dtype}, but it must be Float32")
+        if p.ndim < 1 or p.shape[-1] != 3:
+            raise RuntimeError(f"query_points has shape {tuple(p.shape)}, but the last dimension must be 3")
+        return p
+
+    def compute_closest_points(self, query_points, nthreads: int = 0) -> dict:
+        """Closest surface point per query point.  Keys as Open3D: ``points``,
+        ``geometry_ids``, ``primitive_ids``, ``primitive_uvs``, ``primitive_normals``."""
+        p = self._points(query_points)
+        shp = tuple(p.shape[:-1])
+        with torch.cuda.device(self.device):
+            p = p.to(self.device).contiguous()
+            n = p.numel() // 3
+            pts = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+            gid = torch.empty(n, dtype=torch.uint32, device=self.device)
+            pid = torch.empty(n, dtype=torch.uint32, device=self.device)
+            uv = torch.empty(n, 2, dtype=torch.float32, device=self.device)
+            nrm = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+            _lib.check(self._L.qsmrt_closest_points(self._h, _ptr(p), n, _ptr(pts), None, _ptr(gid), _ptr(pid), _ptr(uv), _ptr(nrm),
+                                                    self._stream()))
+            return {"points": self._out(pts).reshape(shp + (3,)), "geometry_ids": self._out(gid).reshape(shp),
+                    "primitive_ids": self._out(pid).reshape(shp), "primitive_uvs": self._out(uv).reshape(shp + (2,)),
+                    "primitive_normals": self._out(nrm).reshape(shp + (3,))}
+
+    def compute_distance(self, query_points, nthreads: int = 0) -> torch.Tensor:
+        """Unsigned distance to the closest surface point."""
+        p = self._points(query_points)
+        shp = tuple(p.shape[:-1])
+        with torch.cuda.device(self.device):
+            p = p.to(self.device).contiguous()
+            n = p.numel() // 3
+            d = torch.empty(n, dtype=torch.float32, device=self.device)
+            _lib.check(self._L.qsmrt_closest_points(self._h, _ptr(p), n, None, _ptr(d), None, None, None, None, self._stream()))
+            return self._out(d).reshape(shp)
+
+    def compute_signed_distance(self, query_points, nthreads: int = 0, nsamples: int = 1) -> torch.Tensor:
+        """Distance, negative inside (``ray_casting.py:250,255``): the sign is
+        ``compute_occupancy`` (odd intersection count along (1,1,1))."""
+        if nsamples != 1:
+            raise RuntimeError("compute_signed_distance: only nsamples == 1 is implemented")
+        p = self._points(query_points)
+        shp = tuple(p.shape[:-1])
+        with torch.cuda.device(self.device):
+            p = p.to(self.device).contiguous()
+            n = p.numel() // 3
+            d = torch.empty(n, dtype=torch.float32, device=self.device)
+            _lib.check(self._L.qsmrt_signed_distance(self._h, _ptr(p), n, _ptr(d), self._stream()))
+            return self._out(d).reshape(shp)
+
     def mark_hit_primitives(self, ans: dict):
         """Device-side form of ``ray_casting.py:285-289``: uint8 flags of the
         triangles (scene order) and vertices that own a closest hit."""

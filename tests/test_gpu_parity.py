@@ -350,3 +350,52 @@ def test_fetch_counters(RS):
         assert 1 < nn.value / rays.shape[0] < 200 and 0 < nt.value / rays.shape[0] < 50
     finally:
         _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 0))
+
+
+def test_closest_points_and_signed_distance(RS, oracle_mod):
+    """compute_closest_points / compute_distance / compute_signed_distance (ray_casting.py:250,255)
+    bit-identical to the oracle; the mri() call pattern of the reference runs unchanged."""
+    from pyqsm_b200.mesh import TriangleMesh
+    v, t = syn.qsm_tree_mesh(seed=3, n_cylinders=60)
+    v2, t2 = syn.box_mesh((3, 3, 0), (5, 5, 2))
+    g, o = RS(), oracle_mod.OracleScene()
+    for s in (g, o):
+        s.add_triangles(v, t)
+        s.add_triangles(v2, t2)
+    q = np.random.default_rng(2).uniform(v.min(0) - 1, v.max(0) + 1, size=(50000, 3)).astype(np.float32)
+    q[:100] = v[:100]                                   # on-surface queries: distance 0, many ties
+    a, r = g.compute_closest_points(q), o.compute_closest_points(q, 1)
+    for k in ("points", "geometry_ids", "primitive_ids", "primitive_uvs", "primitive_normals"):
+        assert np.array_equal(a[k].numpy(), r[k]), k
+    assert np.array_equal(g.compute_distance(q).numpy(), r["distance"])
+    sd = g.compute_signed_distance(q).numpy()
+    assert np.array_equal(sd, o.compute_signed_distance(q, 1))
+    assert (sd < 0).sum() > 50 and np.all(np.abs(sd) == r["distance"])
+    # vs brute force on a subsample
+    rb = o.compute_closest_points(q[:3000], 0)
+    assert np.array_equal(a["primitive_ids"].numpy()[:3000], rb["primitive_ids"])
+    # reference pattern, ray_casting.py:241-255 (mri): random points + a 64^3 grid
+    v3_, t3_ = syn.box_mesh((3.1, 3.37, 0.23), (5.02, 5.61, 2.11))     # irregular bounds: no ray through an exact edge
+    mesh = TriangleMesh(v3_, t3_)
+    scene = RS()
+    _ = scene.add_triangles(mesh)
+    o3 = oracle_mod.OracleScene()
+    o3.add_triangles(v3_, t3_)
+    min_bound = mesh.vertex.positions.min(0).numpy()
+    max_bound = mesh.vertex.positions.max(0).numpy()
+    query_points = np.random.uniform(low=min_bound, high=max_bound, size=[256, 3]).astype(np.float32)
+    signed_distance = scene.compute_signed_distance(query_points)
+    assert signed_distance.shape == (256,) and torch.all(signed_distance <= 0)
+    xyz_range = np.linspace(min_bound - 0.5, max_bound + 0.5, num=64)
+    query_points = np.stack(np.meshgrid(*xyz_range.T), axis=-1).astype(np.float32)
+    signed_distance = scene.compute_signed_distance(query_points)
+    assert signed_distance.numpy()[:, :, 10].shape == (64, 64)
+    assert np.array_equal(signed_distance.numpy(), o3.compute_signed_distance(query_points, 1))
+    inside = np.all((query_points > min_bound) & (query_points < max_bound), axis=-1)
+    # single-sample parity (Open3D's default too) is fooled only by rays grazing a box edge exactly
+    assert ((signed_distance.numpy() < 0) != inside).mean() < 1e-3
+    # empty scene: infinite distance
+    e = RS()
+    assert torch.all(torch.isinf(e.compute_distance(q[:4])))
+    with pytest.raises(RuntimeError):
+        g.compute_distance(np.zeros((4, 2), np.float32))

@@ -202,3 +202,37 @@ def test_multi_geometry_ids_and_ties(orc):
         assert a["geometry_ids"].tolist() == [0, 0] and a["primitive_ids"].tolist() == [0, 0]
         assert s.count_intersections(rays, mode).tolist() == [2, 2]
         assert s.edge_flags(rays, mode=mode).tolist() == [2, 3]
+
+
+def test_closest_points_oracle(orc):
+    """Closest-point query: analytic answers on the unit box, brute force == LBVH, and the
+    result is a true minimum (an independent float64 point/triangle distance)."""
+    v, t = syn.box_mesh()
+    s = orc.OracleScene()
+    s.add_triangles(v, t)
+    q = np.array([[0.5, 0.5, 2], [0.5, 0.5, 0.5], [2, 2, 2], [-1, 0.5, 0.5], [0.25, 0.3, 0.9]], np.float32)
+    for mode in (0, 1):
+        r = s.compute_closest_points(q, mode)
+        np.testing.assert_allclose(r["distance"], [1.0, 0.5, 3 ** 0.5, 1.0, 0.1], rtol=1e-6)
+        np.testing.assert_allclose(r["points"], [[0.5, 0.5, 1], [0.5, 0.5, 0], [1, 1, 1], [0, 0.5, 0.5], [0.25, 0.3, 1]], atol=1e-6)
+        np.testing.assert_allclose(s.compute_signed_distance(q, mode), [1.0, -0.5, 3 ** 0.5, 1.0, -0.1], rtol=1e-6)
+        assert s.compute_occupancy(q, mode).tolist() == [0, 1, 0, 0, 1]
+    v, t = syn.qsm_tree_mesh(seed=3, n_cylinders=25)
+    s = orc.OracleScene()
+    s.add_triangles(v, t)
+    q = np.random.default_rng(0).uniform(v.min(0) - 1, v.max(0) + 1, size=(3000, 3)).astype(np.float32)
+    a, b = s.compute_closest_points(q, 0), s.compute_closest_points(q, 1)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    # uv convention reconstructs the closest point; the point lies on the reported triangle
+    tri = t[a["primitive_ids"]]
+    uv = a["primitive_uvs"].astype(np.float64)
+    p = v[tri[:, 1]] * uv[:, :1] + v[tri[:, 2]] * uv[:, 1:] + v[tri[:, 0]] * (1 - uv.sum(1))[:, None]
+    np.testing.assert_allclose(p, a["points"], atol=2e-6)
+    np.testing.assert_allclose(np.linalg.norm(a["points"].astype(np.float64) - q, axis=1), a["distance"], rtol=1e-5, atol=1e-6)
+    # no sampled surface point is closer than the reported distance
+    rng = np.random.default_rng(1)
+    w = rng.dirichlet([1, 1, 1], size=t.shape[0])
+    samples = (v[t[:, 0]] * w[:, :1] + v[t[:, 1]] * w[:, 1:2] + v[t[:, 2]] * w[:, 2:]).astype(np.float64)
+    for i in range(0, 3000, 150):
+        assert np.min(np.linalg.norm(samples - q[i], axis=1)) >= a["distance"][i] * (1 - 1e-5)
