@@ -399,3 +399,34 @@ def test_closest_points_and_signed_distance(RS, oracle_mod):
     assert torch.all(torch.isinf(e.compute_distance(q[:4])))
     with pytest.raises(RuntimeError):
         g.compute_distance(np.zeros((4, 2), np.float32))
+
+
+def test_open3d_shim_import_path():
+    """SURVEY.md 8b route 2: with the shim on sys.path the reference's own import lines bind the B200 engine
+    (ray_casting.py:8,43) and its get_points_inside_mesh pattern (:55-69) runs."""
+    import importlib
+    import os
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyqsm_b200", "open3d_shim")
+    sys.path.insert(0, shim)
+    try:
+        for m in [k for k in sys.modules if k == "open3d" or k.startswith("open3d.")]:
+            del sys.modules[m]
+        from open3d.t.geometry import RaycastingScene as rcs          # ray_casting.py:8
+        import open3d as o3d
+        import open3d.core as o3c                                      # ray_casting.py:43
+        import pyqsm_b200
+        assert rcs is pyqsm_b200.RaycastingScene and rcs.INVALID_ID == 4294967295
+        cv, ct = syn.cylinder_mesh(radius=0.5, height=2.0)
+        mesh = o3d.t.geometry.TriangleMesh(cv, ct)
+        query_pts = np.array([[0, 0, 0], [0.2, 0.1, 0.8], [0.6, 0, 0], [0, 0, 1.2]])
+        tpts = o3c.Tensor(query_pts, o3c.float32)                      # ray_casting.py:62
+        scene = rcs()
+        _ = scene.add_triangles(mesh)
+        occ = scene.compute_occupancy(tpts)                            # ray_casting.py:69
+        assert occ.numpy().tolist() == [1.0, 1.0, 0.0, 0.0]
+    finally:
+        sys.path.remove(shim)
+        for m in [k for k in sys.modules if k == "open3d" or k.startswith("open3d.")]:
+            del sys.modules[m]
+        importlib.invalidate_caches()
