@@ -47,6 +47,8 @@ typedef struct qsmrt_stats {
     float    scene_lo[3], scene_hi[3];
     uint32_t leaf_max;           /* triangles per collapsed leaf */
     uint32_t bvh_height;         /* binary LBVH height (bounds the traversal stack) */
+    uint32_t quantised_nodes;    /* 1: the persistent kernel reads the 32-byte 16-bit-grid nodes */
+    uint32_t reserved;
 } qsmrt_stats;
 
 const char *qsmrt_last_error(void);
@@ -207,6 +209,9 @@ int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out);
  * are idle / hold a second leaf / finished descending, [7] triangle-phase
  * iterations, [8] lanes testing a triangle. */
 int qsmrt_debug_get_census(uint64_t out[16]);
+/* 0 forces the 64-byte fp32 nodes even where the 32-byte quantised nodes
+ * qualify (A/B measurements; results are identical either way). */
+int qsmrt_debug_set_quantised_nodes(int allow);
 /* Node fetch path of the persistent kernel: 0 = 256-bit LSU loads (default),
  * 1 = texture fetches, 2 = half and half (L1 data-pipe experiment). */
 int qsmrt_debug_set_node_path(int path);

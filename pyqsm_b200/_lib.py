@@ -23,7 +23,7 @@ class Stats(C.Structure):
         ("bvh_bytes", C.c_uint64),
         ("build_ms", C.c_float), ("sort_ms", C.c_float), ("box_pad", C.c_float),
         ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3),
-        ("leaf_max", C.c_uint32), ("bvh_height", C.c_uint32),
+        ("leaf_max", C.c_uint32), ("bvh_height", C.c_uint32), ("quantised_nodes", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -56,6 +56,7 @@ SYMBOLS = {
     "qsmrt_debug_get_build": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "qsmrt_debug_set_quantised_nodes": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_node_path": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_leaf_max": (C.c_int, [C.c_int]),
     "qsmrt_debug_get_census": (C.c_int, [C.POINTER(C.c_uint64)]),

@@ -6,6 +6,8 @@ struct BuildParams {        // device-resident; filled by the bounds kernels
     float slo[3], shi[3];   // scene bounds over referenced vertices
     float scale[3];         // 2^21 / extent per axis (0 for a flat axis)
     float pad;              // absolute AABB padding
+    float glo[3], cell[3], inv_cell[3];   // 16-bit quantisation grid of the 32-byte nodes
+    float leaf_diag_sum;    // sum of leaf box diagonals (mean leaf size decides whether the grid is fine enough)
 };
 
 struct LbvhBuildArgs {
@@ -27,6 +29,7 @@ struct LbvhBuildArgs {
     uint32_t   *flags;              // [T-1]
     TriRec     *tris;               // [T]
     TNode      *tnodes;             // [max(T-1,1)]
+    QNode      *qnodes;             // [max(T-1,1)] quantised twin of tnodes
     unsigned long long *counters;   // [3] nodes emitted, leaves emitted, binary tree height
     cudaEvent_t ev_sort0, ev_sort1; // optional
 };

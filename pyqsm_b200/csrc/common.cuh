@@ -24,6 +24,13 @@ struct __align__(16) BNode {
 //                                child <  0: leaf, ~child = first<<2 | (count-1)
 struct __align__(64) TNode { float4 a, b, c; int4 d; };
 
+// 32-byte quantised traversal node: the same two child boxes on a 16-bit grid
+// spanning the padded scene bounds (plane = glo + q * cell), one 256-bit load.
+//   w[0..2] = child 0 x,y,z (lo | hi << 16), w[3..5] = child 1, w[6], w[7] = child refs.
+// Boxes are widened by 3 cells per side at encode time, which covers the decode
+// rounding (t = fma(2^23 + q, cell/d, const), <= ~1.1 cells) -- still conservative.
+struct __align__(32) QNode { uint32_t w[8]; };
+
 // 48-byte triangle record (3 x 16-byte loads), Embree TriangleM convention.
 struct __align__(16) TriRec {
     float4 p0;   // v0.xyz, primitive id bits
@@ -37,6 +44,8 @@ struct SceneView {
     uint32_t      ntris;
     uint32_t      height;      // binary LBVH height: bound on the traversal stack depth
     cudaTextureObject_t node_tex;   // float4 view of nodes (TEX-path experiment), 0 if absent
+    const QNode  *qnodes;      // 32-byte quantised nodes, nullptr when the grid is too coarse for this scene
+    float         glo[3], cell[3];
 };
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \

@@ -77,6 +77,15 @@ __global__ void k_finalize_bounds(const uint32_t *ob, BuildParams *bp)
     }
     float pad = __fmul_rn(m, 7.62939453125e-06f);   // 2^-17, see DESIGN.md "box padding"
     bp->pad = pad > 0.0f ? pad : 1e-30f;
+    // quantisation grid: padded bounds plus a 32-cell margin so the +-3-cell widening never clamps
+    for (int a = 0; a < 3; ++a) {
+        float ext = bp->shi[a] - bp->slo[a];
+        float e = bp->pad + ext * 4.8828125e-04f;       // 2^-11
+        bp->glo[a] = bp->slo[a] - e;
+        bp->cell[a] = (ext + 2.0f * e) / 65535.0f;
+        bp->inv_cell[a] = 1.0f / bp->cell[a];
+    }
+    bp->leaf_diag_sum = 0.0f;
 }
 
 // ---------------------------------------------------------------- Morton
@@ -292,32 +301,39 @@ __device__ __forceinline__ uint32_t geom_of(const uint64_t *__restrict__ goff, u
 __global__ void __launch_bounds__(256)
 k_emit_leaves(const float *__restrict__ verts, const uint32_t *__restrict__ idx, int64_t n,
               const uint32_t *__restrict__ order, const uint64_t *__restrict__ goff, uint32_t ngeoms,
-              const BuildParams *__restrict__ bp, BNode *__restrict__ bn, TriRec *__restrict__ tris)
+              BuildParams *__restrict__ bp, BNode *__restrict__ bn, TriRec *__restrict__ tris)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t t = order[i];
-    uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
-    float p0[3], p1[3], p2[3];
+    float diag = 0.0f;
+    if (i < n) {
+        uint64_t t = order[i];
+        uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
+        float p0[3], p1[3], p2[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { p0[a] = verts[3ull * i0 + a]; p1[a] = verts[3ull * i1 + a]; p2[a] = verts[3ull * i2 + a]; }
-    const float pad = bp->pad;
-    BNode b;
-    b.lox = __fsub_rn(fminf(p0[0], fminf(p1[0], p2[0])), pad);
-    b.loy = __fsub_rn(fminf(p0[1], fminf(p1[1], p2[1])), pad);
-    b.loz = __fsub_rn(fminf(p0[2], fminf(p1[2], p2[2])), pad);
-    b.hix = __fadd_rn(fmaxf(p0[0], fmaxf(p1[0], p2[0])), pad);
-    b.hiy = __fadd_rn(fmaxf(p0[1], fmaxf(p1[1], p2[1])), pad);
-    b.hiz = __fadd_rn(fmaxf(p0[2], fmaxf(p1[2], p2[2])), pad);
-    b.left = -1; b.right = -1;
-    bn[n - 1 + i] = b;
-    uint32_t g = ngeoms > 1 ? geom_of(goff, ngeoms, t) : 0u;
-    uint32_t prim = (uint32_t)(t - goff[g]);
-    TriRec r;
-    r.p0 = make_float4(p0[0], p0[1], p0[2], __uint_as_float(prim));
-    r.p1 = make_float4(__fsub_rn(p0[0], p1[0]), __fsub_rn(p0[1], p1[1]), __fsub_rn(p0[2], p1[2]), __uint_as_float(g));
-    r.p2 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.0f);
-    tris[i] = r;
+        for (int a = 0; a < 3; ++a) { p0[a] = verts[3ull * i0 + a]; p1[a] = verts[3ull * i1 + a]; p2[a] = verts[3ull * i2 + a]; }
+        const float pad = bp->pad;
+        BNode b;
+        b.lox = __fsub_rn(fminf(p0[0], fminf(p1[0], p2[0])), pad);
+        b.loy = __fsub_rn(fminf(p0[1], fminf(p1[1], p2[1])), pad);
+        b.loz = __fsub_rn(fminf(p0[2], fminf(p1[2], p2[2])), pad);
+        b.hix = __fadd_rn(fmaxf(p0[0], fmaxf(p1[0], p2[0])), pad);
+        b.hiy = __fadd_rn(fmaxf(p0[1], fmaxf(p1[1], p2[1])), pad);
+        b.hiz = __fadd_rn(fmaxf(p0[2], fmaxf(p1[2], p2[2])), pad);
+        b.left = -1; b.right = -1;
+        bn[n - 1 + i] = b;
+        float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
+        diag = sqrtf(dx * dx + dy * dy + dz * dz);
+        uint32_t g = ngeoms > 1 ? geom_of(goff, ngeoms, t) : 0u;
+        uint32_t prim = (uint32_t)(t - goff[g]);
+        TriRec r;
+        r.p0 = make_float4(p0[0], p0[1], p0[2], __uint_as_float(prim));
+        r.p1 = make_float4(__fsub_rn(p0[0], p1[0]), __fsub_rn(p0[1], p1[1]), __fsub_rn(p0[2], p1[2]), __uint_as_float(g));
+        r.p2 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.0f);
+        tris[i] = r;
+    }
+    // mean leaf size (decides whether the 16-bit node grid is fine enough): one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) diag += __shfl_xor_sync(0xFFFFFFFFu, diag, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&bp->leaf_diag_sum, diag);
 }
 
 // Bottom-up refit: one thread per leaf climbs; the second arrival at a node
@@ -348,6 +364,27 @@ k_refit(int64_t n, BNode *bn, const int32_t *__restrict__ parent, uint32_t *flag
 // Collapse subtrees of <= QSMRT_LEAF_MAX triangles into leaves and emit the
 // 64-byte traversal nodes (indexed like the binary internal nodes; collapsed
 // interior nodes are simply never referenced).
+// conservative 16-bit encoding of one box axis: floor/ceil on the grid, widened by 3 cells
+__device__ __forceinline__ uint32_t quantise_axis(float lo, float hi, float glo, float inv_cell)
+{
+    float fl = floorf((lo - glo) * inv_cell) - 3.0f, fh = ceilf((hi - glo) * inv_cell) + 3.0f;
+    uint32_t ql = (uint32_t)fminf(fmaxf(fl, 0.0f), 65535.0f), qh = (uint32_t)fminf(fmaxf(fh, 0.0f), 65535.0f);
+    return ql | (qh << 16);
+}
+
+__device__ __forceinline__ QNode quantise_node(const TNode &o, const BuildParams *__restrict__ bp)
+{
+    QNode q;
+    q.w[0] = quantise_axis(o.a.x, o.a.y, bp->glo[0], bp->inv_cell[0]);
+    q.w[1] = quantise_axis(o.a.z, o.a.w, bp->glo[1], bp->inv_cell[1]);
+    q.w[2] = quantise_axis(o.c.x, o.c.y, bp->glo[2], bp->inv_cell[2]);
+    q.w[3] = quantise_axis(o.b.x, o.b.y, bp->glo[0], bp->inv_cell[0]);
+    q.w[4] = quantise_axis(o.b.z, o.b.w, bp->glo[1], bp->inv_cell[1]);
+    q.w[5] = quantise_axis(o.c.z, o.c.w, bp->glo[2], bp->inv_cell[2]);
+    q.w[6] = (uint32_t)o.d.x; q.w[7] = (uint32_t)o.d.y;
+    return q;
+}
+
 __device__ __forceinline__ int child_ref(int32_t c, int64_t n, const int2 *__restrict__ range, int leaf_max)
 {
     if (c >= n - 1) return ~(int)(((uint32_t)(c - (n - 1)) << 2) | 0u);
@@ -359,7 +396,8 @@ __device__ __forceinline__ int child_ref(int32_t c, int64_t n, const int2 *__res
 
 __global__ void __launch_bounds__(256)
 k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ range,
-              TNode *__restrict__ tn, unsigned long long *__restrict__ counters, int leaf_max)
+              TNode *__restrict__ tn, QNode *__restrict__ qn, const BuildParams *__restrict__ bp,
+              unsigned long long *__restrict__ counters, int leaf_max)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool live = i < n - 1;
@@ -387,10 +425,12 @@ k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ 
     int r0 = child_ref(me.left, n, range, leaf_max), r1 = child_ref(me.right, n, range, leaf_max);
     o.d = make_int4(r0, r1, 0, 0);
     tn[i] = o;
+    qn[i] = quantise_node(o, bp);
 }
 
 // single-triangle scene: one node, one real child, one empty (inverted) box
-__global__ void k_emit_single(const BNode *__restrict__ bn, TNode *__restrict__ tn, unsigned long long *counters)
+__global__ void k_emit_single(const BNode *__restrict__ bn, TNode *__restrict__ tn, QNode *__restrict__ qn,
+                              const BuildParams *__restrict__ bp, unsigned long long *counters)
 {
     BNode c0 = bn[0];
     TNode o;
@@ -400,6 +440,10 @@ __global__ void k_emit_single(const BNode *__restrict__ bn, TNode *__restrict__ 
     o.d = make_int4(~0, ~0, 0, 0);
     // second child: empty box, never entered
     tn[0] = o;
+    // the quantised twin cannot express an empty box: child 1 repeats child 0 (same leaf twice is harmless)
+    TNode dup = o;
+    dup.b = o.a; dup.c = make_float4(o.c.x, o.c.y, o.c.x, o.c.y);
+    qn[0] = quantise_node(dup, bp);
     counters[0] = 1; counters[1] = 1; counters[2] = 1;
 }
 
@@ -448,13 +492,13 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     k_emit_leaves<<<gN, B, 0, st>>>(A.verts, A.idx, (int64_t)n, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris);
     CUDA_TRY(cudaMemsetAsync(A.counters, 0, 3 * sizeof(unsigned long long), st));
     if (n == 1) {
-        k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.counters);
+        k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);
     } else {
         const unsigned gI = (unsigned)((n - 1 + B - 1) / B);
         CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(uint32_t), st));
         k_karras<<<gI, B, 0, st>>>(A.keys, (int64_t)n, A.bnodes, A.parent, A.range);
         k_refit<<<gN, B, 0, st>>>((int64_t)n, A.bnodes, A.parent, A.flags, A.counters);
-        k_emit_tnodes<<<gI, B, 0, st>>>((int64_t)n, A.bnodes, A.range, A.tnodes, A.counters, A.leaf_max);
+        k_emit_tnodes<<<gI, B, 0, st>>>((int64_t)n, A.bnodes, A.range, A.tnodes, A.qnodes, A.params, A.counters, A.leaf_max);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

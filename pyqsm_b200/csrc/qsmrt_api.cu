@@ -16,6 +16,7 @@
 #include "traverse.h"
 
 static thread_local char g_err[512] = "";
+static int g_allow_qnodes = 1;              // qsmrt_debug_set_quantised_nodes
 static int g_leaf_max = 2;                  // triangles per leaf (qsmrt_debug_set_leaf_max); 2 measured best on C2
 
 void qsmrt_set_error(const char *fmt, ...)
@@ -53,6 +54,7 @@ struct qsmrt_scene {
     // build products kept for traversal / introspection
     uint64_t *keys = nullptr; uint32_t *order = nullptr;
     BNode *bnodes = nullptr; TNode *tnodes = nullptr; TriRec *tris = nullptr;
+    QNode *qnodes = nullptr; bool use_qnodes = false; float glo[3] = {}, cell[3] = {};
     BuildParams *params = nullptr;
     qsmrt_stats stats{};
     cudaTextureObject_t node_tex = 0;
@@ -79,7 +81,8 @@ void free_build(qsmrt_scene *s)
     if (s->own_concat) { dfree(s->verts); dfree(s->idx); }
     s->verts = nullptr; s->idx = nullptr; s->own_concat = false;
     dfree(s->goff); dfree(s->voff); dfree(s->keys); dfree(s->order);
-    dfree(s->bnodes); dfree(s->tnodes); dfree(s->tris); dfree(s->params);
+    dfree(s->bnodes); dfree(s->tnodes); dfree(s->tris); dfree(s->params); dfree(s->qnodes);
+    s->use_qnodes = false;
     dfree(s->list_raw_off); dfree(s->list_raw);
     s->list_rays = nullptr; s->list_n = 0;
     if (s->node_tex) { cudaDestroyTextureObject(s->node_tex); s->node_tex = 0; }
@@ -135,6 +138,8 @@ SceneView view_of(const qsmrt_scene *s)
     SceneView v;
     v.nodes = s->tnodes; v.tris = s->tris; v.ntris = (uint32_t)s->ntris; v.height = s->stats.bvh_height;
     v.node_tex = s->node_tex;
+    v.qnodes = (s->use_qnodes && g_allow_qnodes) ? s->qnodes : nullptr;
+    for (int a = 0; a < 3; ++a) { v.glo[a] = s->glo[a]; v.cell[a] = s->cell[a]; }
     return v;
 }
 
@@ -169,7 +174,8 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         dmalloc(&sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&bounds, 8) ||
         dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&parent, 2 * T - 1) ||
         dmalloc(&range, T) || dmalloc(&flags, T) || dmalloc(&s->tris, T) ||
-        dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&counters, 3))
+        dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(T - 1, 1)) ||
+        dmalloc(&counters, 3))
         return 1;
     if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
     else {
@@ -191,6 +197,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
     A.bounds_ord = bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = keys_tmp;
     A.order = s->order; A.order_tmp = order_tmp; A.sort_scratch = sort_scratch;
     A.bnodes = s->bnodes; A.parent = parent; A.range = range; A.flags = flags;
+    A.qnodes = s->qnodes;
     A.tris = s->tris; A.tnodes = s->tnodes; A.counters = counters; A.ev_sort0 = es0; A.ev_sort1 = es1;
     int rc = lbvh_build(A, st);
     if (!rc) {
@@ -204,7 +211,13 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         for (int a = 0; a < 3; ++a) { s->stats.scene_lo[a] = bp.slo[a]; s->stats.scene_hi[a] = bp.shi[a]; }
         s->stats.box_pad = bp.pad;
         s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];
-        s->stats.bvh_bytes = cnt[0] * sizeof(TNode) + T * sizeof(TriRec);
+        // the 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf
+        float max_cell = std::max(bp.cell[0], std::max(bp.cell[1], bp.cell[2]));
+        float mean_leaf = bp.leaf_diag_sum / (float)T;
+        s->use_qnodes = 6.0f * max_cell <= 0.15f * mean_leaf;
+        for (int a = 0; a < 3; ++a) { s->glo[a] = bp.glo[a]; s->cell[a] = bp.cell[a]; }
+        s->stats.quantised_nodes = s->use_qnodes ? 1u : 0u;
+        s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + T * sizeof(TriRec);
         {   // float4 texture view of the node array (TEX-path experiment); optional
             cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = s->tnodes;
             rd.res.linear.desc = cudaCreateChannelDesc<float4>();
@@ -354,6 +367,12 @@ int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out)
     if (g_trv_stats_dev) CUDA_TRY(cudaMemcpy(h, g_trv_stats_dev, sizeof(h), cudaMemcpyDeviceToHost));
     if (nodes_out) *nodes_out = h[0];
     if (tris_out) *tris_out = h[1];
+    return 0;
+}
+
+int qsmrt_debug_set_quantised_nodes(int allow)
+{
+    g_allow_qnodes = allow != 0;
     return 0;
 }
 

@@ -110,7 +110,21 @@ struct TraceArgs {
 
 constexpr int CNT_SET = 32;     // distinct (geometry, t) pairs a lane can hold before it defers to the exact slow path
 
-template <int MODE, bool COUNTERS>
+__device__ __forceinline__ void ld256u(const void *p, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
+                                       uint32_t &w4, uint32_t &w5, uint32_t &w6, uint32_t &w7)
+{
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7)
+                 : "l"(p));
+}
+// 16-bit grid coordinate -> the float 2^23 + q, one PRMT each (no int->float conversion)
+__device__ __forceinline__ float qlo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
+__device__ __forceinline__ float qhi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
+
+// QUANT: read the 32-byte quantised nodes (one 256-bit load per node step instead of two; the L1 data pipe
+// is the binding resource, profiles/README.md).  The ray's slab constants are folded with the grid:
+// t = (2^23 + q) * (cell/d) - (2^23 * cell/d - (glo - o)/d), so the slab code is unchanged.
+template <int MODE, bool COUNTERS, bool QUANT>
 __global__ void __launch_bounds__(TR_BLOCK)
 k_trace5(const TraceArgs A)
 {
@@ -135,6 +149,7 @@ k_trace5(const TraceArgs A)
     float *const tset = reinterpret_cast<float *>(sstack + A.depth * TR_BLOCK) + threadIdx.x;      // MODE 2
     uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + CNT_SET) * TR_BLOCK) + threadIdx.x;
     int cnt = 0; bool overflow = false;
+    uint32_t snx = 0x7610u, sny = 0x7610u, snz = 0x7610u;       // QUANT: per-axis "near plane" byte selectors
 
 #define PARK_LEAF5() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; \
                           sptr -= TR_BLOCK; cur = *sptr; } while (0)
@@ -187,6 +202,17 @@ k_trace5(const TraceArgs A)
                     uint64_t i;
                     if (slot < A.nslots && ray_index_of_slot(slot, A.N, A.row_len, i)) {
                         r = source_ray(A.src, i);
+                        if (QUANT) {
+                            const float ax = A.sc.cell[0] * r.idx, ay = A.sc.cell[1] * r.idy, az = A.sc.cell[2] * r.idz;
+                            r.oodx = fmaf(8388608.0f, ax, -((A.sc.glo[0] - r.O.x) * r.idx));
+                            r.oody = fmaf(8388608.0f, ay, -((A.sc.glo[1] - r.O.y) * r.idy));
+                            r.oodz = fmaf(8388608.0f, az, -((A.sc.glo[2] - r.O.z) * r.idz));
+                            r.idx = ax; r.idy = ay; r.idz = az;
+                            // PRMT selectors that decode the near / far plane of each axis straight from the packed word
+                            // (sign of 1/d, not of d: a -0.0 component has a negative reciprocal)
+                            snx = ax < 0.0f ? 0x7632u : 0x7610u; sny = ay < 0.0f ? 0x7632u : 0x7610u;
+                            snz = az < 0.0f ? 0x7632u : 0x7610u;
+                        }
                         ray_i = i; have_ray = true;
                         best_t = ANYHIT ? A.tfar : INFINITY;
                         cnt = 0; overflow = false;
@@ -220,21 +246,44 @@ k_trace5(const TraceArgs A)
                 }
             }
             if (inner) {
-                float4 a, b, c, dd;
-                if (A.node_path == 0) {
-                    ld256f(nodes + cur, a, b);
-                    ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
-                } else if (A.node_path == 1) {         // experiment: all four 16-byte chunks through the TEX path
-                    a = tex1Dfetch<float4>(A.sc.node_tex, cur * 4);     b = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 1);
-                    c = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 2); dd = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 3);
-                } else {                               // experiment: half through TEX, half through LSU
-                    a = tex1Dfetch<float4>(A.sc.node_tex, cur * 4);     b = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 1);
-                    ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
-                }
-                const int c0 = __float_as_int(dd.x), c1 = __float_as_int(dd.y);
+                int c0, c1;
                 float t0, t1;
-                const bool h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, best_t, t0);
-                const bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, best_t, t1);
+                bool h0, h1;
+                if (QUANT) {
+                    // the ray's direction signs pick each axis' entry / exit plane while decoding (PRMT with a
+                    // per-lane selector), so the slab test needs no per-axis min/max: 8 FMNMX instead of 24
+                    uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+                    ld256u(A.sc.qnodes + cur, w0, w1, w2, w3, w4, w5, w6, w7);
+                    const uint32_t sfx = snx ^ 0x0022u, sfy = sny ^ 0x0022u, sfz = snz ^ 0x0022u;
+#define QPL(W, S) __uint_as_float(__byte_perm((W), 0x4B000000u, (S)))
+                    float nx = fmaf(QPL(w0, snx), r.idx, -r.oodx), fx = fmaf(QPL(w0, sfx), r.idx, -r.oodx);
+                    float ny = fmaf(QPL(w1, sny), r.idy, -r.oody), fy = fmaf(QPL(w1, sfy), r.idy, -r.oody);
+                    float nz = fmaf(QPL(w2, snz), r.idz, -r.oodz), fz = fmaf(QPL(w2, sfz), r.idz, -r.oodz);
+                    t0 = fmaxf(fmax3(nx, ny, nz), 0.0f);
+                    h0 = t0 <= fminf(fmin3(fx, fy, fz), best_t);
+                    nx = fmaf(QPL(w3, snx), r.idx, -r.oodx); fx = fmaf(QPL(w3, sfx), r.idx, -r.oodx);
+                    ny = fmaf(QPL(w4, sny), r.idy, -r.oody); fy = fmaf(QPL(w4, sfy), r.idy, -r.oody);
+                    nz = fmaf(QPL(w5, snz), r.idz, -r.oodz); fz = fmaf(QPL(w5, sfz), r.idz, -r.oodz);
+                    t1 = fmaxf(fmax3(nx, ny, nz), 0.0f);
+                    h1 = t1 <= fminf(fmin3(fx, fy, fz), best_t);
+#undef QPL
+                    c0 = (int)w6; c1 = (int)w7;
+                } else {
+                    float4 a, b, c, dd;
+                    if (A.node_path == 0) {
+                        ld256f(nodes + cur, a, b);
+                        ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
+                    } else if (A.node_path == 1) {         // experiment: all four 16-byte chunks through the TEX path
+                        a = tex1Dfetch<float4>(A.sc.node_tex, cur * 4);     b = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 1);
+                        c = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 2); dd = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 3);
+                    } else {                               // experiment: half through TEX, half through LSU
+                        a = tex1Dfetch<float4>(A.sc.node_tex, cur * 4);     b = tex1Dfetch<float4>(A.sc.node_tex, cur * 4 + 1);
+                        ld256f(reinterpret_cast<const char *>(nodes + cur) + 32, c, dd);
+                    }
+                    c0 = __float_as_int(dd.x); c1 = __float_as_int(dd.y);
+                    h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, best_t, t0);
+                    h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, best_t, t1);
+                }
                 if (COUNTERS) ++n_node;
                 // take child 1 first when child 0 is missed, or both are hit and 1 is nearer
                 const bool take1 = !h0 || (CLOSEST && h1 && (t1 < t0));

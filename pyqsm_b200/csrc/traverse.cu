@@ -972,6 +972,18 @@ template <int MODE> int sched_grid(int *blocks)
 }
 
 
+template <int MODE, bool COUNTERS, bool QUANT>
+int launch_trace5_q(TraceArgs &a, size_t smem, int per_sm, int sms, cudaStream_t st)
+{
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_trace5<MODE, COUNTERS, QUANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<MODE, COUNTERS, QUANT>, TR_BLOCK, smem));
+    if (per_sm < 1) { qsmrt_set_error("persistent kernel does not fit (smem %zu)", smem); return 1; }
+    unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
+    k_trace5<MODE, COUNTERS, QUANT><<<g, TR_BLOCK, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // common launch of the persistent kernel: tuning, work cursor, occupancy-sized grid
 template <int MODE, bool COUNTERS>
 int launch_trace5(TraceArgs &a, size_t smem, cudaStream_t st)
@@ -982,13 +994,8 @@ int launch_trace5(TraceArgs &a, size_t smem, cudaStream_t st)
     int dev = 0, per_sm = 0, sms = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_trace5<MODE, COUNTERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<MODE, COUNTERS>, TR_BLOCK, smem));
-    if (per_sm < 1) { qsmrt_set_error("persistent kernel does not fit (smem %zu)", smem); return 1; }
-    unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
-    k_trace5<MODE, COUNTERS><<<g, TR_BLOCK, smem, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    if (a.sc.qnodes) return launch_trace5_q<MODE, COUNTERS, true>(a, smem, per_sm, sms, st);
+    return launch_trace5_q<MODE, COUNTERS, false>(a, smem, per_sm, sms, st);
 }
 
 inline size_t stack_bytes(const SceneView &sc) { return (size_t)((int)sc.height + 2) * TR_BLOCK * sizeof(int); }

@@ -126,7 +126,7 @@ class RaycastingScene:
     def stats(self) -> dict:
         st = _lib.Stats()
         _lib.check(self._L.qsmrt_get_stats(self._h, C.byref(st)))
-        d = {k: getattr(st, k) for k, _ in st._fields_ if k not in ("scene_lo", "scene_hi")}
+        d = {k: getattr(st, k) for k, _ in st._fields_ if k not in ("scene_lo", "scene_hi", "reserved")}
         d["scene_lo"] = list(st.scene_lo)
         d["scene_hi"] = list(st.scene_hi)
         return d

@@ -310,6 +310,11 @@ def test_variants_tilings_and_leaf_sizes_agree(RS, oracle_mod):
     o.add_triangles(v, t)
     grid = syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(35, 200), 301, 203)   # not multiples of the 8x4 tile
     rays = syn.materialize_grid(*grid, 301, 203)
+    # signed zeros and axis-parallel directions: -0.0 has a negative reciprocal (near/far plane selection)
+    g2 = syn.parallel_ray_grid(v.min(0), v.max(0), np.array([-0.6, -0.0, -0.8]), 301, 203)
+    rays[: 301 * 100] = syn.materialize_grid(*g2, 301, 203)[: 301 * 100]
+    rays[301 * 100: 301 * 120, 3:] = np.array([0.0, -0.0, -1.0], np.float32)
+    rays[301 * 120: 301 * 140, 3:] = np.array([-0.0, 1.0, 0.0], np.float32)
     ref = o.cast_rays(rays, 1)
     rays_img = torch.from_numpy(rays.reshape(203, 301, 6)).cuda()
     try:
@@ -319,16 +324,19 @@ def test_variants_tilings_and_leaf_sizes_agree(RS, oracle_mod):
             g.add_triangles(v, t)
             g.commit()
             assert g.stats()["leaf_max"] == leaf_max and g.stats()["bvh_height"] >= 10
-            for variant in (1, 2, 3, 4, 5):
+            assert g.stats()["quantised_nodes"] == 1                     # this mesh qualifies for the 32-byte nodes
+            for variant, quant in ((1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (5, 0)):
                 _lib.check(L.qsmrt_debug_set_variant(variant))
+                _lib.check(L.qsmrt_debug_set_quantised_nodes(quant))     # only variant 5 reads them
                 for r in (rays_img, rays_img.reshape(-1, 6)):            # 2-D tiles / linear
                     ans = {k: a.cpu().reshape((-1,) + tuple(a.shape[r.ndim - 1:])) for k, a in g.cast_rays(r).items()}
-                    assert_cast_equal(ans, ref, None, f"leaf{leaf_max}/v{variant}")
+                    assert_cast_equal(ans, ref, None, f"leaf{leaf_max}/v{variant}/q{quant}")
             occ = g.test_occlusions(rays_img.reshape(-1, 6)).cpu().numpy()
             assert np.array_equal(occ, np.isfinite(ref["t_hit"]))
     finally:
         _lib.check(L.qsmrt_debug_set_leaf_max(2))
         _lib.check(L.qsmrt_debug_set_variant(5))
+        _lib.check(L.qsmrt_debug_set_quantised_nodes(1))
         _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 0))
 
 

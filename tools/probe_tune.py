@@ -32,6 +32,7 @@ for k in range(a.angles):
     for combo in a.combos.split(";"):
         var, rest = combo.split(":"); rf, wt, tm, lm, *npth = map(int, rest.split(","))
         _lib.check(L.qsmrt_debug_set_node_path(npth[0] if npth else 0))
+        _lib.check(L.qsmrt_debug_set_quantised_nodes(npth[1] if len(npth) > 1 else 1))
         if lm != cur_lm:
             _lib.check(L.qsmrt_debug_set_leaf_max(lm)); cur_lm = lm
             s = RaycastingScene(output_device="cuda"); s.add_triangles(v, t); s.commit()
@@ -42,4 +43,4 @@ for k in range(a.angles):
         nn, nt = C.c_uint64(), C.c_uint64(); _lib.check(L.qsmrt_debug_get_counters(C.byref(nn), C.byref(nt)))
         cs = (C.c_uint64 * 16)(); _lib.check(L.qsmrt_debug_get_census(cs)); cs = list(cs)
         if cs[2]: print(f"      node-phase iters/ray {cs[2]*32/n:.1f} lanes step {cs[3]/cs[2]:.1f} idle {cs[4]/cs[2]:.1f} leaf2 {cs[5]/cs[2]:.1f} done {cs[6]/cs[2]:.1f} | tri-phase iters/ray {cs[7]*32/n:.1f} lanes {cs[8]/max(cs[7],1):.1f}")
-        print(f"   v{var} refill {rf:2d} want {wt:2d} trimin {tm:2d} leafmax {lm} path {npth[0] if npth else 0}: {ms:.2f} ms {n/ms/1e3:.0f} Mr/s {'=' if same else 'DIFF'}  nodes/ray {nn.value/n:.1f} tris/ray {nt.value/n:.2f}", flush=True)
+        print(f"   v{var} refill {rf:2d} want {wt:2d} trimin {tm:2d} leafmax {lm} path {npth[0] if npth else 0} quant {npth[1] if len(npth) > 1 else 1}: {ms:.2f} ms {n/ms/1e3:.0f} Mr/s {'=' if same else 'DIFF'}  nodes/ray {nn.value/n:.1f} tris/ray {nt.value/n:.2f}", flush=True)
