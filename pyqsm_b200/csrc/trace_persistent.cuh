@@ -125,7 +125,7 @@ __device__ __forceinline__ float qhi(uint32_t w) { return __uint_as_float(__byte
 // is the binding resource, profiles/README.md).  The ray's slab constants are folded with the grid:
 // t = (2^23 + q) * (cell/d) - (2^23 * cell/d - (glo - o)/d), so the slab code is unchanged.
 template <int MODE, bool COUNTERS, bool QUANT>
-__global__ void __launch_bounds__(TR_BLOCK)
+__global__ void __launch_bounds__(TR_BLOCK, 10)
 k_trace5(const TraceArgs A)
 {
     constexpr bool CLOSEST = MODE == 0 || MODE == 3;
