@@ -209,6 +209,9 @@ int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out);
  * are idle / hold a second leaf / finished descending, [7] triangle-phase
  * iterations, [8] lanes testing a triangle. */
 int qsmrt_debug_get_census(uint64_t out[16]);
+/* Radix sort of the builder: 0 = histogram / scan / scatter kernels per pass,
+ * 1 = one kernel per pass with decoupled look-back (default).  Same result. */
+int qsmrt_debug_set_sort(int variant);
 /* 0 forces the 64-byte fp32 nodes even where the 32-byte quantised nodes
  * qualify (A/B measurements; results are identical either way). */
 int qsmrt_debug_set_quantised_nodes(int allow);

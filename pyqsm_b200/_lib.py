@@ -56,6 +56,7 @@ SYMBOLS = {
     "qsmrt_debug_get_build": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "qsmrt_debug_set_sort": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_quantised_nodes": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_node_path": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_leaf_max": (C.c_int, [C.c_int]),

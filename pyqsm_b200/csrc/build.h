@@ -34,6 +34,7 @@ struct LbvhBuildArgs {
     cudaEvent_t ev_sort0, ev_sort1; // optional
 };
 
+extern int g_sort_variant;
 size_t lbvh_sort_scratch_bytes(uint64_t n);
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
                     uint64_t n, uint32_t *scratch, cudaStream_t st);

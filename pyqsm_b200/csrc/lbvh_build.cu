@@ -7,6 +7,7 @@
 // pyQSM/viz/ray_casting.py:66,156,219,242,276,317 then :168,223,279,319).
 // The key/ordering/topology arithmetic mirrors oracle/qsmrt_oracle.c
 // (orc_commit) so the builder can be checked bit-for-bit on the CPU.
+#include <algorithm>
 #include "common.cuh"
 #include "build.h"
 
@@ -125,8 +126,8 @@ k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint
 // exclusive scan over tiles -> ranked scatter (warp match_any multi-split).
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ROUNDS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;     // 4096 keys per tile
+constexpr int RS_ROUNDS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;     // keys per tile
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_tile_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint32_t *__restrict__ tile_hist, uint32_t ntiles)
@@ -168,7 +169,7 @@ k_rs_scan_tiles(uint32_t *__restrict__ tile_hist, uint32_t ntiles, uint32_t *__r
     if (threadIdx.x == 255) digit_tot[blockIdx.x] = part[255];
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
              uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n, int shift,
              const uint32_t *__restrict__ tile_hist, const uint32_t *__restrict__ digit_tot, uint32_t ntiles)
@@ -242,6 +243,119 @@ k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
         if (i < n) {
             uint32_t d = (uint32_t)(kreg[r] >> shift) & 0xFFu;
             uint64_t dst = (uint64_t)dbase[d] + wcnt[w][d] + rnk[r];
+            kout[dst] = kreg[r];
+            vout[dst] = vreg[r];
+        }
+    }
+}
+
+
+// ---- single-pass-per-digit variant ("Onesweep", Adinets & Merrill 2022) -------
+// One read of the keys builds all eight digit histograms; each pass is then ONE
+// kernel: a tile ranks its keys locally, publishes its per-digit counts, finds
+// its global offsets by decoupled look-back over the tiles before it, and
+// scatters.  Per pass that is one read and one write of (key, value) instead
+// of the three kernels / extra key read of the classic variant above.
+// Tiles are handed out through an atomic counter so a tile only ever waits on
+// tiles that are already running.
+constexpr uint32_t OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(256)
+k_os_histogram(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ ghist /* [8][256] */)
+{
+    __shared__ uint32_t h[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
+        uint64_t k = keys[i];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) atomicAdd(&h[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) { uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
+}
+
+// exclusive scan of each 256-bin histogram in place (one block per pass)
+__global__ void __launch_bounds__(256)
+k_os_scan_hist(uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t wsum[8];
+    uint32_t *row = ghist + blockIdx.x * 256;
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t v = row[threadIdx.x], x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (l >= o) x += y; }
+    if (l == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    row[threadIdx.x] = off + x - v;
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 4)
+k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+          uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n, int shift,
+          const uint32_t *__restrict__ gbase /* [256] digit starts of this pass */,
+          uint32_t *status /* [ntiles][256], zeroed */, uint32_t *tile_counter)
+{
+    __shared__ uint32_t wcnt[RS_WARPS][256];
+    __shared__ uint32_t dbase[256];
+    __shared__ uint32_t s_tile;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+
+    uint64_t kreg[RS_ROUNDS];
+    uint32_t vreg[RS_ROUNDS];
+    uint16_t rnk[RS_ROUNDS];
+    const uint64_t base = (uint64_t)tile * RS_TILE + (uint64_t)w * (32 * RS_ROUNDS);
+    const uint32_t lt = (1u << l) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) { uint64_t i = base + r * 32 + l; kreg[r] = i < n ? kin[i] : ~0ull; }
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) { uint64_t i = base + r * 32 + l; vreg[r] = i < n ? vin[i] : 0u; }
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const bool valid = base + r * 32 + l < n;
+        const uint32_t d = valid ? ((uint32_t)(kreg[r] >> shift) & 0xFFu) : 256u;
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+        m = valid ? m : ~m;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
+            m &= ((d >> b) & 1u) ? bal : ~bal;
+        }
+        const uint32_t before = valid ? wcnt[w][d] : 0;
+        __syncwarp();
+        if (valid && (m & lt) == 0) wcnt[w][d] = before + __popc(m);
+        __syncwarp();
+        rnk[r] = (uint16_t)(before + __popc(m & lt));
+    }
+    __syncthreads();
+    {   // thread d owns digit d: tile count, publish, look back, global base
+        const uint32_t d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < RS_WARPS; ++k) { uint32_t v = wcnt[k][d]; wcnt[k][d] = run; run += v; }
+        volatile uint32_t *st = status;
+        st[(uint64_t)tile * 256 + d] = (tile == 0 ? OS_INC : OS_AGG) | run;
+        uint32_t excl = 0;
+        for (int64_t k = (int64_t)tile - 1; k >= 0; --k) {
+            uint32_t sv;
+            do { sv = st[(uint64_t)k * 256 + d]; } while ((sv >> 30) == 0u);
+            excl += sv & OS_MASK;
+            if ((sv >> 30) == 2u) break;
+        }
+        if (tile != 0) st[(uint64_t)tile * 256 + d] = OS_INC | (excl + run);
+        dbase[d] = gbase[d] + excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        if (base + r * 32 + l < n) {
+            const uint32_t d = (uint32_t)(kreg[r] >> shift) & 0xFFu;
+            const uint64_t dst = (uint64_t)dbase[d] + wcnt[w][d] + rnk[r];
             kout[dst] = kreg[r];
             vout[dst] = vreg[r];
         }
@@ -450,10 +564,13 @@ __global__ void k_emit_single(const BNode *__restrict__ bn, TNode *__restrict__ 
 } // namespace
 
 // -------------------------------------------------------------- host side
+int g_sort_variant = 1;      // 0 classic (3 kernels per pass), 1 onesweep (decoupled look-back)
+
 size_t lbvh_sort_scratch_bytes(uint64_t n)
 {
     uint64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
-    return (size_t)(ntiles * 256 + 256) * sizeof(uint32_t);
+    // classic: tile_hist[256][ntiles] + digit_tot[256]; onesweep: ghist[8][256] + status[ntiles][256] + counters[8]
+    return (size_t)(ntiles * 256 + 8 * 256 + 256 + 64) * sizeof(uint32_t);
 }
 
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
@@ -464,6 +581,20 @@ int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t
     uint32_t *tile_hist = scratch, *digit_tot = scratch + (uint64_t)ntiles * 256;
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
+    if (g_sort_variant == 1 && n >= (8u << 20)) {      // measured: look-back wins from ~8M keys, the 3-kernel pass below that
+        uint32_t *status = scratch, *ghist = scratch + (uint64_t)ntiles * 256, *counters = ghist + 8 * 256;
+        CUDA_TRY(cudaMemsetAsync(ghist, 0, (8 * 256 + 8) * sizeof(uint32_t), st));
+        k_os_histogram<<<(unsigned)std::min<uint64_t>((n + 4095) / 4096, 148 * 8), 256, 0, st>>>(keys, n, ghist);
+        k_os_scan_hist<<<8, 256, 0, st>>>(ghist);
+        for (int pass = 0; pass < 8; ++pass) {
+            CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)ntiles * 256 * sizeof(uint32_t), st));
+            k_os_pass<<<ntiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, pass * 8, ghist + pass * 256, status, counters + pass);
+            uint64_t *tk = kin; kin = kout; kout = tk;
+            uint32_t *tv = vin; vin = vout; vout = tv;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     for (int pass = 0; pass < 8; ++pass) {
         int shift = pass * 8;
         k_rs_tile_hist<<<ntiles, RS_THREADS, 0, st>>>(kin, n, shift, tile_hist, ntiles);

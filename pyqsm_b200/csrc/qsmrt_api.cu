@@ -370,6 +370,13 @@ int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out)
     return 0;
 }
 
+int qsmrt_debug_set_sort(int variant)
+{
+    if (variant != 0 && variant != 1) FAIL("sort variant must be 0 (classic) or 1 (onesweep)");
+    g_sort_variant = variant;
+    return 0;
+}
+
 int qsmrt_debug_set_quantised_nodes(int allow)
 {
     g_allow_qnodes = allow != 0;
