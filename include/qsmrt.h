@@ -193,12 +193,14 @@ int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
  * after). */
 int qsmrt_debug_get_build(qsmrt_scene *scene, uint64_t *keys, uint32_t *order, void *nodes);
 
-/* Tuning hook for A/B measurements: 1 = plain per-thread loop, 2 = speculative
- * while-while, 3 = persistent two-phase, 4 = persistent one-step scheduler
- * (default).  Results are identical. */
+/* Tuning hook for A/B measurements: 1 = one independent loop per thread (the
+ * first kernel, kept as the simple reference), 2 = the persistent warp-uniform
+ * kernel (default).  Results are identical. */
 int qsmrt_debug_set_variant(int variant);
 
-/* Scheduler tuning of the persistent kernel (variant 4) and its fetch
+/* Thresholds of the persistent kernel (refill_thresh idle lanes trigger a
+ * refill; the node phase ends below want_thresh searching lanes; `speculate`
+ * is the triangle-phase early-exit threshold tri_min) and its fetch
  * counters: with counters != 0 every cast_rays launch counts the node records
  * and triangles it actually fetched; qsmrt_debug_get_counters reads the last
  * launch's totals (synchronises). */

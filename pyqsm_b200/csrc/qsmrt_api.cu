@@ -349,7 +349,7 @@ int qsmrt_cast_rays_2d(qsmrt_scene *s, const float *rays, uint32_t width, uint64
 
 int qsmrt_debug_set_variant(int variant)
 {
-    if (variant < 1 || variant > 5) FAIL("unknown traversal variant %d", variant);
+    if (variant != 1 && variant != 2) FAIL("unknown traversal variant %d (1 = per-thread loop, 2 = persistent kernel)", variant);
     g_trv_variant = variant;
     return 0;
 }

@@ -97,14 +97,10 @@ __device__ __forceinline__ void traverse(const SceneView &sc, const Ray &r, Stac
     }
 }
 
-// ---- v2: speculative while-while (Aila & Laine 2009) -------------------------
-// ncu on v1 (profiles/r01_v1_*): 7-8 of 32 lanes active per instruction -- the
-// long leaf path ran with only the few lanes that happened to be at a leaf.
-// Here a lane that reaches a leaf parks it and keeps descending until every
-// lane of the warp holds a leaf; then all lanes run the triangle tests
-// together.  The slab test is the FMA form (t = lo*inv - O*inv, FMNMX3): in
-// position space its rounding moves a box face by <= ~1e-7 * max|coord|, far
-// inside the 2^-17 padding every leaf box carries, so it stays conservative.
+// ---- slab test of the persistent kernel --------------------------------------
+// FMA form (t = plane * (1/d) - o * (1/d), FMNMX3): in position space its rounding
+// moves a box face by <= ~1e-7 * max|coord|, far inside the 2^-17 padding every leaf
+// box carries, so it stays conservative (checked against brute force in tests/).
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
 }
@@ -125,43 +121,6 @@ __device__ __forceinline__ bool slab_fma(float lox, float hix, float loy, float 
 }
 
 constexpr int TR_SENTINEL = 0x7FFFFFFF;
-
-template <bool ORDERED, class V>
-__device__ __forceinline__ void traverse2(const SceneView &sc, const Ray &r, Stack &st, V &vis)
-{
-    st.sp = 0;
-    st.push(TR_SENTINEL);
-    int cur = 0;      // >= 0: inner node (or sentinel); < 0: leaf
-    int leaf = 0;     // < 0: a parked leaf waiting for the warp
-    while (cur != TR_SENTINEL) {
-        while ((unsigned)cur < (unsigned)TR_SENTINEL) {
-            float4 a, b, c; int4 d;
-            load_node(sc.nodes, cur, a, b, c, d);
-            float t0, t1;
-            const float tm = vis.tmax();
-            bool h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, tm, t0);
-            bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, tm, t1);
-            if (!(h0 | h1)) {
-                cur = st.pop();
-            } else {
-                cur = h0 ? d.x : d.y;
-                if (h0 & h1) {
-                    int far = d.y;
-                    if (ORDERED && t1 < t0) { far = cur; cur = d.y; }
-                    st.push(far);
-                }
-            }
-            if (cur < 0 && leaf >= 0) { leaf = cur; cur = st.pop(); }     // park the first leaf, keep going
-            if (!__any_sync(__activemask(), leaf >= 0)) break;            // every lane holds a leaf
-        }
-        while (leaf < 0) {
-            uint32_t ref = (uint32_t)~leaf;
-            if (vis.leaf(ref >> 2, (ref & 3u) + 1u)) return;
-            leaf = cur;                                                   // a second leaf reached meanwhile
-            if (cur < 0) cur = st.pop();
-        }
-    }
-}
 
 // 2-D tile mapping for image / grid shaped ray batches [rows][row_len]: a warp
 // takes an 8 x 4 tile instead of 32 consecutive rays of one row, which keeps
@@ -205,7 +164,6 @@ struct ClosestVis {
     }
 };
 
-template <int VARIANT>
 __global__ void __launch_bounds__(TR_BLOCK)
 k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t row_len,
             float *__restrict__ t_hit, uint32_t *__restrict__ geom, uint32_t *__restrict__ prim,
@@ -218,10 +176,7 @@ k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t r
     int spill[TR_LSTACK];
     Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
     ClosestVis vis{ sc, r, INFINITY, QSMRT_INVALID, QSMRT_INVALID, 0u };
-    if (sc.ntris) {
-        if (VARIANT == 1) traverse<true>(sc, r, st, vis);
-        else traverse2<true>(sc, r, st, vis);
-    }
+    if (sc.ntris) traverse<true>(sc, r, st, vis);
     if (t_hit) t_hit[i] = vis.t;
     if (geom) geom[i] = vis.geom;
     if (prim) prim[i] = vis.prim;
@@ -241,19 +196,10 @@ k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t r
     }
 }
 
-// ---- v3: persistent, warp-uniform traversal ---------------------------------
-// Evidence (profiles/r01_v1_*): the per-thread loops spend half their issue
-// slots in leaf code with ~2.3 of 32 lanes active, and idle lanes of finished
-// rays wait for the slowest ray of the warp.  v3 keeps the whole warp on ONE
-// control path: every lane stays in the same loops and work is predicated,
-// phase changes are decided by full-mask votes, triangles are tested one per
-// lane per iteration, and lanes whose ray is finished are refilled from a
-// global cursor (ballot/popc compaction of the idle set) once REFILL lanes
-// are idle.  Lanes then only need a similar *mix* of work, not similar nodes.
-// The stack pointer lives in a register (the struct form kept it in local
-// memory), entries in shared memory [entry][thread] with a local spill.
-constexpr int TR_REFILL = 8;
-
+// ---- persistent kernel (trace_persistent.cuh): ray slots and outputs ----------
+// Evidence for its shape (profiles/README.md): the per-thread loop below spends half
+// its issue slots in leaf code with ~2.3 of 32 lanes active, and idle lanes of
+// finished rays wait for the slowest ray of the warp.
 __device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uint32_t row_len, uint64_t &i)
 {
     if (row_len == 0) { i = slot; return slot < N; }
@@ -272,142 +218,6 @@ struct CastOut {
     float *t_hit; uint32_t *geom, *prim; float2 *uv; float *nrm;
 };
 
-// MODE 0: closest hit (cast_rays).  MODE 1: any hit in (tnear, tfar] (test_occlusions).
-template <int MODE>
-__global__ void __launch_bounds__(TR_BLOCK)
-k_trace_persistent(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t row_len, uint64_t nslots,
-                   CastOut out, uint8_t *__restrict__ occluded, float tnear, float tfar_in,
-                   unsigned long long *__restrict__ cursor)
-{
-    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
-    int *const sbase = sstack + threadIdx.x;
-    int loc[TR_LSTACK];
-    const unsigned FULL = 0xFFFFFFFFu;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt = (1u << lane) - 1u;
-
-    Ray r;
-    float best_t = 0.0f; uint32_t best_geom = QSMRT_INVALID, best_prim = QSMRT_INVALID, best_tri = 0u;
-    uint64_t ray_i = 0;
-    bool have_ray = false, exhausted = false;
-    int cur = TR_SENTINEL, sp = 0;
-    uint32_t tri_i = 0, tri_end = 0;
-
-#define PUSH(v) do { if (sp < TR_SSTACK) sbase[sp * TR_BLOCK] = (v); else loc[sp - TR_SSTACK] = (v); ++sp; } while (0)
-#define POP(dst) do { --sp; (dst) = sp < TR_SSTACK ? sbase[sp * TR_BLOCK] : loc[sp - TR_SSTACK]; } while (0)
-#define PARK_LEAF() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; POP(cur); } while (0)
-
-    for (;;) {
-        // ---- retire finished rays, refill idle lanes
-        const bool idle = (cur == TR_SENTINEL) && (tri_i >= tri_end);
-        const unsigned im = __ballot_sync(FULL, idle);
-        if (im == FULL || (!exhausted && __popc(im) >= TR_REFILL)) {
-            if (idle && have_ray) {
-                have_ray = false;
-                if (MODE == 0) {
-                    if (out.t_hit) out.t_hit[ray_i] = best_t;
-                    if (out.geom) out.geom[ray_i] = best_geom;
-                    if (out.prim) out.prim[ray_i] = best_prim;
-                    if (out.uv || out.nrm) {
-                        float u = 0.0f, v = 0.0f, nx = 0.0f, ny = 0.0f, nz = 0.0f;
-                        if (best_prim != QSMRT_INVALID) {
-                            float4 p0, p1, p2;
-                            load_tri(sc.tris, best_tri, p0, p1, p2);
-                            MtHit h;
-                            mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h);
-                            u = __fdiv_rn(h.U, h.absDen); v = __fdiv_rn(h.V, h.absDen);
-                            float inv = __fdiv_rn(1.0f, __fsqrt_rn(f3dot(h.Ng, h.Ng)));
-                            nx = __fmul_rn(h.Ng.x, inv); ny = __fmul_rn(h.Ng.y, inv); nz = __fmul_rn(h.Ng.z, inv);
-                        }
-                        if (out.uv) out.uv[ray_i] = make_float2(u, v);
-                        if (out.nrm) { out.nrm[3 * ray_i] = nx; out.nrm[3 * ray_i + 1] = ny; out.nrm[3 * ray_i + 2] = nz; }
-                    }
-                } else {
-                    occluded[ray_i] = best_prim != QSMRT_INVALID ? 1 : 0;
-                }
-            }
-            if (exhausted) {
-                if (im == FULL) break;
-            } else {
-                const int need = __popc(im);
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(cursor, (unsigned long long)need);
-                base = __shfl_sync(FULL, base, 0);
-                exhausted = base + (unsigned long long)need >= nslots;
-                if (idle) {
-                    const uint64_t slot = base + __popc(im & lt);
-                    uint64_t i;
-                    if (slot < nslots && ray_index_of_slot(slot, N, row_len, i)) {
-                        r = load_ray(rays, i);
-                        ray_i = i; have_ray = true;
-                        best_t = MODE == 0 ? INFINITY : tfar_in;
-                        best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
-                        sbase[0] = TR_SENTINEL; sp = 1;
-                        cur = sc.ntris ? 0 : TR_SENTINEL;
-                        tri_i = tri_end = 0;
-                    }
-                }
-                continue;
-            }
-        }
-        // ---- inner-node phase: until every lane holds a leaf (or has nothing left)
-        for (;;) {
-            const bool inner = (unsigned)cur < (unsigned)TR_SENTINEL;
-            const bool parked = tri_i < tri_end;
-            if (!__any_sync(FULL, inner && !parked)) break;
-            if (inner) {
-                float4 a, b, c; int4 d;
-                load_node(sc.nodes, cur, a, b, c, d);
-                float t0, t1;
-                bool h0 = slab_fma(a.x, a.y, a.z, a.w, c.x, c.y, r, best_t, t0);
-                bool h1 = slab_fma(b.x, b.y, b.z, b.w, c.z, c.w, r, best_t, t1);
-                if (!(h0 | h1)) {
-                    POP(cur);
-                } else {
-                    cur = h0 ? d.x : d.y;
-                    if (h0 & h1) {
-                        int far = d.y;
-                        if (MODE == 0 && t1 < t0) { far = cur; cur = d.y; }
-                        PUSH(far);
-                    }
-                }
-                if (cur < 0 && !parked) PARK_LEAF();
-            }
-        }
-        // ---- triangle phase: one triangle per lane per iteration, drain parked leaves
-        for (;;) {
-            const bool has = tri_i < tri_end;
-            if (!__any_sync(FULL, has)) break;
-            if (has) {
-                float4 p0, p1, p2;
-                load_tri(sc.tris, tri_i, p0, p1, p2);
-                MtHit h;
-                if (MODE == 0) {
-                    if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
-                        float tt = __fdiv_rn(h.T, h.absDen);
-                        uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
-                        bool better = (tt < best_t) | ((tt == best_t) & ((pg < best_geom) | ((pg == best_geom) & (pp < best_prim))));
-                        if (better) { best_t = tt; best_geom = pg; best_prim = pp; best_tri = tri_i; }
-                    }
-                    ++tri_i;
-                    if (tri_i == tri_end && cur < 0) PARK_LEAF();
-                } else {
-                    if (mt_test(p0, p1, p2, r.O, r.D, tnear, tfar_in, h)) {
-                        best_prim = 0u; cur = TR_SENTINEL; tri_i = tri_end;       // occluded: drop the rest
-                    } else {
-                        ++tri_i;
-                        if (tri_i == tri_end && cur < 0) PARK_LEAF();
-                    }
-                }
-            }
-        }
-    }
-#undef PUSH
-#undef POP
-#undef PARK_LEAF
-}
-
-#include "trace_sched.cuh"
 #include "trace_persistent.cuh"
 
 // ---------------------------------------------------------------- any hit
@@ -918,8 +728,8 @@ inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block -
 } // namespace
 
 // --------------------------------------------------------------- launchers
-int g_trv_variant = 5;      // 1 per-thread loop, 2 speculative while-while, 3 persistent two-phase (spill stack), 4 persistent scheduler, 5 persistent two-phase, smem stack + 256-bit loads
-int g_trv_tuning[4] = { 12, 12, 1, 0 }; // refill, want, tri_min (v4: speculate), counters -- tuned on C2 (profiles/r01_tuning.txt)
+int g_trv_variant = 2;      // 1 = one independent loop per thread, 2 = persistent warp-uniform kernel (ships)
+int g_trv_tuning[4] = { 12, 12, 1, 0 }; // refill, want, tri_min, counters -- tuned on C2 (profiles/r01_tuning.txt)
 unsigned long long *g_trv_stats_dev = nullptr;
 int g_trv_node_path = 0;                // 0 LSU 256-bit loads, 1 TEX, 2 half/half (qsmrt_debug_set_node_path)
 
@@ -928,7 +738,6 @@ namespace {
 constexpr int CURSOR_RING = 256;
 unsigned long long *g_cursor_ring[64] = {};
 unsigned g_cursor_next[64] = {};
-int g_persistent_blocks[64][2] = {};
 
 int next_cursor(unsigned long long **out, cudaStream_t st)
 {
@@ -941,36 +750,6 @@ int next_cursor(unsigned long long **out, cudaStream_t st)
     CUDA_TRY(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
     return 0;
 }
-
-template <int MODE> int persistent_grid(int *blocks)
-{
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (!g_persistent_blocks[dev][MODE]) {
-        int per_sm = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_persistent<MODE>, TR_BLOCK, 0));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        g_persistent_blocks[dev][MODE] = per_sm * sms;
-    }
-    *blocks = g_persistent_blocks[dev][MODE];
-    return 0;
-}
-
-template <int MODE> int sched_grid(int *blocks)
-{
-    static int cached[64] = {};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (!cached[dev]) {
-        int per_sm = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_sched<MODE, false>, TR_BLOCK, 0));
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        cached[dev] = per_sm * sms;
-    }
-    *blocks = cached[dev];
-    return 0;
-}
-
 
 template <int MODE, bool COUNTERS, bool QUANT>
 int launch_trace5_q(TraceArgs &a, size_t smem, int per_sm, int sms, cudaStream_t st)
@@ -999,7 +778,7 @@ int launch_trace5(TraceArgs &a, size_t smem, cudaStream_t st)
 }
 
 inline size_t stack_bytes(const SceneView &sc) { return (size_t)((int)sc.height + 2) * TR_BLOCK * sizeof(int); }
-inline bool use_v5(const SceneView &sc, size_t smem) { return g_trv_variant == 5 && sc.ntris && smem <= 96 * 1024; }
+inline bool use_v5(const SceneView &sc, size_t smem) { return g_trv_variant == 2 && sc.ntris && smem <= 96 * 1024; }
 
 uint64_t slots_for(uint64_t N, uint32_t row_len)
 {
@@ -1030,33 +809,10 @@ int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t r
             a.stats = g_trv_stats_dev;
             if (launch_trace5<0, true>(a, stack_bytes(sc), st)) return 1;
         } else if (launch_trace5<0, false>(a, stack_bytes(sc), st)) return 1;
-    } else if (g_trv_variant == 4) {
-        unsigned long long *cursor = nullptr;
-        int blocks = 0;
-        if (next_cursor(&cursor, st) || sched_grid<0>(&blocks)) return 1;
-        uint64_t nslots = slots_for(N, row_len);
-        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)blocks, (nslots + TR_BLOCK - 1) / TR_BLOCK);
-        CastOut o{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
-        Tuning tu{ g_trv_tuning[0], std::max(1, g_trv_tuning[1]), g_trv_tuning[2] };
-        if (g_trv_tuning[3]) {
-            if (!g_trv_stats_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g_trv_stats_dev), 16 * sizeof(unsigned long long)));
-            CUDA_TRY(cudaMemsetAsync(g_trv_stats_dev, 0, 16 * sizeof(unsigned long long), st));
-            k_trace_sched<0, true><<<g, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, nslots, o, nullptr, 0.0f, INFINITY, cursor, tu, g_trv_stats_dev);
-        } else {
-            k_trace_sched<0, false><<<g, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, nslots, o, nullptr, 0.0f, INFINITY, cursor, tu, nullptr);
-        }
-    } else if (g_trv_variant == 3 || g_trv_variant == 5) {
-        unsigned long long *cursor = nullptr;
-        int blocks = 0;
-        if (next_cursor(&cursor, st) || persistent_grid<0>(&blocks)) return 1;
-        uint64_t nslots = slots_for(N, row_len);
-        unsigned g = (unsigned)std::min<uint64_t>((uint64_t)blocks, (nslots + TR_BLOCK - 1) / TR_BLOCK);
-        CastOut o{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
-        k_trace_persistent<0><<<g, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, nslots, o, nullptr, 0.0f, INFINITY, cursor);
-    } else if (g_trv_variant == 1)
-        k_cast_rays<1><<<grid, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
-    else
-        k_cast_rays<2><<<grid, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
+    } else {
+        // per-thread loop: the simple kernel (A/B reference; also used when the LBVH is too deep for the shared-memory stack)
+        k_cast_rays<<<grid, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1208,7 +964,7 @@ int trv_sky_visibility(const SceneView &sc, const float *points, const float *no
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st)
 {
     if (n_points == 0 || dir_count == 0) return 0;
-    if (g_trv_variant != 5 || stack_bytes(sc) > 96 * 1024) { qsmrt_set_error("sky_visibility needs the persistent kernel"); return 1; }
+    if (g_trv_variant != 2 || stack_bytes(sc) > 96 * 1024) { qsmrt_set_error("sky_visibility needs the persistent kernel"); return 1; }
     TraceArgs a{};
     a.sc = sc; a.src = hemisphere_source(points, normals, dir_begin, dir_count, seed, offset);
     a.N = n_points * (uint64_t)dir_count; a.row_len = 0; a.nslots = a.N;

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from pyqsm_b200 import RaycastingScene, synthetic as syn, _lib
 ap = argparse.ArgumentParser(); ap.add_argument("--grid", type=int, default=4000); ap.add_argument("--angles", type=int, default=2)
-ap.add_argument("--combos", default="5:12,12,1,4;5:12,12,4,4;5:12,12,8,4;5:12,12,12,4;5:12,12,1,2;5:12,12,4,2;5:12,12,8,2;5:12,16,8,2;5:12,12,1,3;5:12,12,1,1")
+ap.add_argument("--combos", default="2:12,12,1,2,0,1;2:12,12,1,2,0,0;2:12,12,1,4,0,1;2:8,8,1,2,0,1;2:16,16,1,2,0,1")
 a = ap.parse_args()
 v, t = syn.canopy_mesh(2, 1_000_000)
 s = RaycastingScene(output_device="cuda"); s.add_triangles(v, t); s.commit(); print("stats", s.stats())
@@ -27,8 +27,8 @@ for k in range(a.angles):
     el, az = sweep[(k * 27 + 5) % 64]
     g = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), a.grid, a.grid)
     _lib.check(L.qsmrt_gen_parallel_rays(P(rays), a.grid, a.grid, F3(g[0]), F3(g[1]), F3(g[2]), F3(g[3]), st))
-    _lib.check(L.qsmrt_debug_set_variant(3)); _lib.check(L.qsmrt_debug_set_tuning(8, 1, 1, 0)); ms3 = timeit(); ref = (o[0].clone(), o[2].clone(), o[3].clone())
-    print(f"el {el:.0f} az {az:.0f}: v3 {ms3:.2f} ms {n/ms3/1e3:.0f} Mr/s")
+    _lib.check(L.qsmrt_debug_set_variant(1)); ms3 = timeit(); ref = (o[0].clone(), o[2].clone(), o[3].clone())
+    print(f"el {el:.0f} az {az:.0f}: v1 {ms3:.2f} ms {n/ms3/1e3:.0f} Mr/s")
     for combo in a.combos.split(";"):
         var, rest = combo.split(":"); rf, wt, tm, lm, *npth = map(int, rest.split(","))
         _lib.check(L.qsmrt_debug_set_node_path(npth[0] if npth else 0))
