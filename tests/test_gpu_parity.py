@@ -438,3 +438,63 @@ def test_open3d_shim_import_path():
         for m in [k for k in sys.modules if k == "open3d" or k.startswith("open3d.")]:
             del sys.modules[m]
         importlib.invalidate_caches()
+
+
+def test_c2_full_size_properties(RS, oracle_mod):
+    """BASELINE config C2 at full size (2M-triangle canopy, 16M parallel sun rays): size-independent
+    properties of the domain on every ray, and the oracle on a 1M-ray subsample (every 16th ray)."""
+    import ctypes as C
+    from pyqsm_b200 import _lib
+    L = _lib.load()
+    v, t = syn.canopy_mesh(2, 1_000_000)
+    assert t.shape[0] == 2_000_000
+    g = RS(output_device="cuda")
+    g.add_triangles(v, t)
+    build_ms = g.commit()
+    st = g.stats()
+    assert st["num_triangles"] == 2_000_000 and build_ms < 50.0
+    nu = nv = 4000
+    grid = syn.parallel_ray_grid(np.asarray(st["scene_lo"]), np.asarray(st["scene_hi"]), syn.sun_direction(40, 135), nu, nv)
+    F3 = lambda x: (C.c_float * 3)(*[float(y) for y in x])
+    rays = torch.empty(nv, nu, 6, dtype=torch.float32, device="cuda")
+    _lib.check(L.qsmrt_gen_parallel_rays(C.c_void_p(rays.data_ptr()), nu, nv, F3(grid[0]), F3(grid[1]), F3(grid[2]), F3(grid[3]), None))
+    a = g.cast_rays(rays)                                   # [4000,4000,6]: 8x4 tiles, persistent kernel, quantised nodes
+    hit = torch.isfinite(a["t_hit"])
+    assert 0.2 < hit.float().mean().item() < 0.8
+    # hit <=> valid ids; misses carry INVALID_ID and zero uv / normal; normals are unit length
+    inv = torch.tensor(0xFFFFFFFF, dtype=torch.int64, device="cuda")
+    pid = a["primitive_ids"].to(torch.int64)
+    assert torch.equal(pid != inv, hit) and torch.equal(a["geometry_ids"].to(torch.int64) != inv, hit)
+    assert int(pid[hit].max()) < 2_000_000
+    assert torch.all(a["primitive_uvs"][~hit] == 0) and torch.all(a["primitive_normals"][~hit] == 0)
+    nlen = torch.linalg.norm(a["primitive_normals"][hit], dim=-1)
+    assert torch.all((nlen - 1).abs() < 1e-5)
+    uv = a["primitive_uvs"][hit]
+    assert torch.all(uv >= 0) and torch.all(uv.sum(-1) <= 1 + 1e-6)
+    # occlusion == hit; count > 0 <=> hit (test_occlusions / count_intersections, other kernels modes)
+    flat = rays.reshape(-1, 6)
+    assert torch.equal(g.test_occlusions(flat).reshape(nv, nu), hit)
+    cnt = g.count_intersections(flat[: 4_000_000])
+    assert torch.equal(cnt > 0, hit.reshape(-1)[: 4_000_000])
+    # scaling d by 4 (exact in fp32) scales t by 1/4 and changes nothing else; linear and tiled mappings agree
+    r2 = flat.clone()
+    r2[:, 3:] *= 4.0
+    b = g.cast_rays(r2)
+    assert torch.equal(b["primitive_ids"].reshape(nv, nu), a["primitive_ids"])
+    assert torch.equal(b["t_hit"].reshape(nv, nu)[hit] * 4.0, a["t_hit"][hit])
+    assert torch.equal(b["primitive_uvs"].reshape(nv, nu, 2), a["primitive_uvs"])
+    # hit point from barycentrics == o + t d (ray_casting.py:172-180 convention), on a sample
+    idx = torch.nonzero(hit.reshape(-1))[:: 997, 0]
+    tri = torch.from_numpy(t.astype(np.int64)).cuda()[pid.reshape(-1)[idx]]
+    vv = torch.from_numpy(v).cuda().double()
+    uvs = a["primitive_uvs"].reshape(-1, 2)[idx].double()
+    p = vv[tri[:, 1]] * uvs[:, :1] + vv[tri[:, 2]] * uvs[:, 1:] + vv[tri[:, 0]] * (1 - uvs.sum(1, keepdim=True))
+    q = flat[idx, :3].double() + flat[idx, 3:].double() * a["t_hit"].reshape(-1)[idx].double()[:, None]
+    assert (p - q).abs().max().item() < 5e-5
+    # the oracle on every 16th ray: bit-identical
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v, t)
+    sub = flat[::16].cpu().numpy()
+    ref = o.cast_rays(sub, 1)
+    ans = {k: x.reshape((-1,) + tuple(x.shape[2:]))[::16].cpu() for k, x in a.items()}
+    assert assert_cast_equal(ans, ref, None, "C2 full size") == 0
