@@ -184,6 +184,18 @@ int qsmrt_gen_hemisphere_rays(float *rays_dev, const float *points_dev, const fl
                               uint64_t n_points, uint64_t seed, float offset, uint32_t dir_begin,
                               uint32_t dir_count, void *stream);
 
+/* "Raycasting projection" of data/notes/methods.md:53-55 and
+ * epiphyte_isolation_methods.md:17 (the surf_2d branch of cast_rays,
+ * ray_casting.py:285-301, iterated): cast the parallel grid, sum the area of
+ * the triangles that own a closest hit (3-D and flattened along the ray
+ * direction), remove them, repeat until the rays see nothing.
+ * layer_of[T] (device, scene order, may be NULL) = layer in which each
+ * triangle was removed, -1 if never hit; layer_stats (HOST, max_layers x 3)
+ * = triangles, 3-D area, projected area per layer.  Synchronises per layer. */
+int qsmrt_peel_projection(qsmrt_scene *scene, uint64_t nu, uint64_t nv, const float origin0[3],
+                          const float du[3], const float dv[3], const float dir[3], int max_layers,
+                          int32_t *layer_of, double *layer_stats_host, int *n_layers_out, void *stream);
+
 int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
 
 /* Builder introspection (parity tests of the LBVH builder; host outputs,

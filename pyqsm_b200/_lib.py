@@ -52,6 +52,8 @@ SYMBOLS = {
     "qsmrt_sun_exposure": (C.c_int, [_vp, _u64, _u64, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "qsmrt_sky_visibility": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp, _vp]),
     "qsmrt_gen_hemisphere_rays": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp]),
+    "qsmrt_peel_projection": (C.c_int, [_vp, _u64, _u64, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.c_int, _vp,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_int), _vp]),
     "qsmrt_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "qsmrt_debug_get_build": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),

@@ -612,6 +612,39 @@ int qsmrt_gen_hemisphere_rays(float *rays, const float *points, const float *nor
     return trv_gen_hemisphere(rays, points, normals, n_points, seed, offset, dir_begin, dir_count, static_cast<cudaStream_t>(stream));
 }
 
+int qsmrt_peel_projection(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+                          const float dv[3], const float dir[3], int max_layers, int32_t *layer_of,
+                          double *layer_stats, int *n_layers_out, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (!o0 || !du || !dv || !dir || !layer_stats || !n_layers_out || max_layers < 1) FAIL("bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    *n_layers_out = 0;
+    const uint64_t T = s->ntris;
+    if (T == 0) return 0;
+    uint8_t *alive = nullptr, *hit = nullptr; double *sums = nullptr;
+    if (dmalloc(&alive, T) || dmalloc(&hit, T) || dmalloc(&sums, 3)) { dfree(alive); dfree(hit); dfree(sums); return 1; }
+    int rc = 0;
+    if (cudaMemsetAsync(alive, 1, T, st) != cudaSuccess || cudaMemsetAsync(hit, 0, T, st) != cudaSuccess ||
+        (layer_of && cudaMemsetAsync(layer_of, 0xFF, T * sizeof(int32_t), st) != cudaSuccess)) rc = 1;
+    SceneView sv = view_of(s);
+    for (int layer = 0; !rc && layer < max_layers; ++layer) {
+        double h[3] = { 0, 0, 0 };
+        if (cudaMemsetAsync(sums, 0, 3 * sizeof(double), st) != cudaSuccess) { rc = 1; break; }
+        rc = trv_peel_cast(sv, nu, nv, o0, du, dv, dir, alive, hit, st) ||
+             trv_peel_update(sv, s->order, alive, hit, layer_of, layer, dir, sums, st);
+        if (!rc && (cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                    cudaStreamSynchronize(st) != cudaSuccess)) rc = 1;
+        if (rc || h[0] == 0.0) break;                       // nothing left that the rays can see
+        layer_stats[3 * layer] = h[0]; layer_stats[3 * layer + 1] = h[1]; layer_stats[3 * layer + 2] = h[2];
+        *n_layers_out = layer + 1;
+    }
+    if (rc && !g_err[0]) qsmrt_set_error("peel_projection: %s", cudaGetErrorString(cudaGetLastError()));
+    dfree(alive); dfree(hit); dfree(sums);
+    return rc;
+}
+
 int qsmrt_get_stats(qsmrt_scene *s, qsmrt_stats *out)
 {
     if (!s || !out) FAIL("null pointer");

@@ -24,6 +24,7 @@
 //                      finished exactly by k_count_fix
 //   3  closest hit  -> atomicAdd(accum[triangle], 1)        (sun exposure: no 32 B/ray of results)
 //   4  any hit      -> atomicAdd(accum[ray / n_dirs], !hit) (sky visibility per query point)
+//   5  closest hit among the triangles still alive -> hitflag[sorted triangle] = 1   (peel projection)
 // SRC (where rays come from; a uniform runtime switch, only touched at refill)
 //   0  rays[N][6] in memory
 //   1  parallel grid: origin0 + i*du + j*dv, direction dir  (same arithmetic as k_gen_parallel)
@@ -102,6 +103,7 @@ struct TraceArgs {
     CastOut out; uint8_t *occluded; float tnear, tfar;          // MODE 0 / 1
     int32_t *counts;                                            // MODE 2
     uint32_t *accum; const uint64_t *goff;                      // MODE 3 / 4
+    const uint8_t *alive; uint8_t *hitflag;                     // MODE 5 (both indexed by sorted triangle)
     unsigned long long *cursor, *stats;
     int refill, want, tri_min, node_path;
     int depth;          // stack entries per thread; the MODE 2 hit set starts behind the stack in shared memory
@@ -128,7 +130,7 @@ template <int MODE, bool COUNTERS, bool QUANT>
 __global__ void __launch_bounds__(TR_BLOCK, 10)
 k_trace5(const TraceArgs A)
 {
-    constexpr bool CLOSEST = MODE == 0 || MODE == 3;
+    constexpr bool CLOSEST = MODE == 0 || MODE == 3 || MODE == 5;
     constexpr bool ANYHIT = MODE == 1 || MODE == 4;
     extern __shared__ int sstack[];                 // [depth][TR_BLOCK] (+ MODE 2: [CNT_SET][TR_BLOCK] t, geometry)
     int *const sbase = sstack + threadIdx.x;
@@ -185,8 +187,10 @@ k_trace5(const TraceArgs A)
                     A.counts[ray_i] = overflow ? -1 : cnt;           // -1: k_count_fix recounts this ray exactly
                 } else if (MODE == 3) {
                     if (best_prim != QSMRT_INVALID) atomicAdd(&A.accum[(A.goff ? A.goff[best_geom] : 0ull) + best_prim], 1u);
-                } else {
+                } else if (MODE == 4) {
                     if (best_prim == QSMRT_INVALID) atomicAdd(&A.accum[ray_i / A.src.dir_count], 1u);     // unoccluded sky ray
+                } else {
+                    if (best_prim != QSMRT_INVALID) A.hitflag[best_tri] = 1;
                 }
             }
             if (exhausted) {
@@ -308,7 +312,7 @@ k_trace5(const TraceArgs A)
                 MtHit h;
                 if (COUNTERS) ++n_tri;
                 if (CLOSEST) {
-                    if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                    if ((MODE != 5 || A.alive[tri_i]) && mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
                         float tt = __fdiv_rn(h.T, h.absDen);
                         uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
                         bool better = (tt < best_t) | ((tt == best_t) & ((pg < best_geom) | ((pg == best_geom) & (pp < best_prim))));

@@ -723,6 +723,32 @@ k_points_to_rays(const float *__restrict__ pts, float *__restrict__ rays, uint64
     p[0] = make_float2(pts[3 * i], pts[3 * i + 1]); p[1] = make_float2(pts[3 * i + 2], 1.0f); p[2] = make_float2(1.0f, 1.0f);
 }
 
+// peel projection bookkeeping: triangles hit in this layer leave the scene; their 3-D and projected areas
+// are summed (ray_casting.py:285-301: hit-triangle surface area, 3-D and flattened along the view direction)
+__global__ void __launch_bounds__(256)
+k_peel_update(const TriRec *__restrict__ tris, uint32_t n, const uint32_t *__restrict__ order, uint8_t *__restrict__ alive,
+              uint8_t *__restrict__ hitflag, int32_t *__restrict__ layer_of, int layer, f3 dir, double *__restrict__ sums)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    double cnt = 0.0, a3 = 0.0, ap = 0.0;
+    if (i < n && hitflag[i]) {
+        hitflag[i] = 0;
+        if (alive[i]) {
+            alive[i] = 0;
+            if (layer_of) layer_of[order[i]] = layer;
+            const float4 p1 = tris[i].p1, p2 = tris[i].p2;
+            f3 Ng = f3cross(f3{ p2.x, p2.y, p2.z }, f3{ p1.x, p1.y, p1.z });
+            cnt = 1.0;
+            a3 = 0.5 * sqrt((double)Ng.x * Ng.x + (double)Ng.y * Ng.y + (double)Ng.z * Ng.z);
+            ap = 0.5 * fabs((double)Ng.x * dir.x + (double)Ng.y * dir.y + (double)Ng.z * dir.z);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); a3 += __shfl_xor_sync(0xFFFFFFFFu, a3, o); ap += __shfl_xor_sync(0xFFFFFFFFu, ap, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.0) { atomicAdd(&sums[0], cnt); atomicAdd(&sums[1], a3); atomicAdd(&sums[2], ap); }
+}
+
 inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 } // namespace
@@ -1003,6 +1029,32 @@ int trv_apply_sign(float *dist, const int32_t *counts, uint64_t N, cudaStream_t 
 {
     if (N == 0) return 0;
     k_apply_sign<<<grid_for(N, 256), 256, 0, st>>>(dist, counts, N);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// one layer of the peel projection: cast the grid against the triangles still alive, flag the owners of the closest hits
+int trv_peel_cast(const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3], const float dv[3],
+                  const float dir[3], const uint8_t *alive, uint8_t *hitflag, cudaStream_t st)
+{
+    if (nu * nv == 0 || sc.ntris == 0) return 0;
+    if (!use_v5(sc, stack_bytes(sc))) { qsmrt_set_error("peel projection needs the persistent kernel"); return 1; }
+    TraceArgs a{};
+    a.sc = sc; a.src.kind = 1; a.src.nu = nu;
+    a.src.o0 = f3{ o0[0], o0[1], o0[2] }; a.src.du = f3{ du[0], du[1], du[2] };
+    a.src.dv = f3{ dv[0], dv[1], dv[2] }; a.src.dir = f3{ dir[0], dir[1], dir[2] };
+    a.N = nu * nv; a.row_len = nu >= 8 && nu < (1ull << 32) ? (uint32_t)nu : 0; a.nslots = slots_for(a.N, a.row_len);
+    a.alive = alive; a.hitflag = hitflag; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
+    return launch_trace5<5, false>(a, stack_bytes(sc), st);
+}
+
+int trv_peel_update(const SceneView &sc, const uint32_t *order, uint8_t *alive, uint8_t *hitflag, int32_t *layer_of,
+                    int layer, const float dir[3], double *sums, cudaStream_t st)
+{
+    if (sc.ntris == 0) return 0;
+    float len = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    f3 d = len > 0.0f ? f3{ dir[0] / len, dir[1] / len, dir[2] / len } : f3{ 0.0f, 0.0f, 0.0f };
+    k_peel_update<<<grid_for(sc.ntris, 256), 256, 0, st>>>(sc.tris, sc.ntris, order, alive, hitflag, layer_of, layer, d, sums);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

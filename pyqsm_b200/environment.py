@@ -133,6 +133,36 @@ def sky_gap_fraction(scene, points, normals=None, n_dirs=1000, seed=5, offset=1e
         return free[: p.shape[0]].to(torch.float32) / float(n_dirs)
 
 
+def peel_projection(scene, direction=(0.0, 0.0, -1.0), grid=(2000, 2000), margin=0.05, max_layers=256):
+    """"Raycasting projection" of the reference's methods notes
+    (``data/notes/methods.md:53-55``: "progressively casting rays,
+    removing/summing the area of interception regions and repeating until all
+    mesh components have been removed"; the ``surf_2d`` branch of
+    ``ray_casting.py:285-301`` iterated).  Parallel rays along ``direction``
+    (default: from nadir); each layer sums the area of the triangles that own
+    a closest hit and removes them.  Returns ``{"layers": [(n_triangles,
+    area_3d, area_projected), ...], "area_3d", "area_projected", "layer_of":
+    int32 [T] (-1 = never seen)}`` -- overlapping surfaces are counted
+    separately, unlike a single projection."""
+    L = _lib.load()
+    scene.commit()
+    st = scene.stats()
+    ntri = int(st["num_triangles"])
+    lo, hi = np.asarray(st["scene_lo"], np.float64), np.asarray(st["scene_hi"], np.float64)
+    nu, nv = int(grid[0]), int(grid[1])
+    o0, du, dv, d = syn.parallel_ray_grid(lo, hi, np.asarray(direction, np.float64), nu, nv, margin)
+    dev = scene.device
+    with torch.cuda.device(dev):
+        layer_of = torch.full((max(ntri, 1),), -1, dtype=torch.int32, device=dev)
+        stats = (C.c_double * (3 * max_layers))()
+        nl = C.c_int(0)
+        _lib.check(L.qsmrt_peel_projection(scene._h, nu, nv, _f3(o0), _f3(du), _f3(dv), _f3(d), int(max_layers), _ptr(layer_of),
+                                           stats, C.byref(nl), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    layers = [(int(stats[3 * k]), float(stats[3 * k + 1]), float(stats[3 * k + 2])) for k in range(nl.value)]
+    return {"layers": layers, "area_3d": sum(x[1] for x in layers), "area_projected": sum(x[2] for x in layers),
+            "layer_of": layer_of[:ntri]}
+
+
 def hemisphere_rays(points, normals=None, n_dirs=16, seed=5, offset=1e-4, dir_begin=0, device=None):
     """The exact rays ``sky_gap_fraction`` traces, materialised: float32 ``[n_points * n_dirs, 6]``."""
     L = _lib.load()

@@ -108,3 +108,47 @@ def test_rain_interception_equals_count(tree):
         hist += np.bincount(np.minimum(c, 255), minlength=256)
     assert np.array_equal(res["intersections"].cpu().numpy(), hist)
     assert res["rays"] == 300 * 240 and 0.0 < res["intercepted_fraction"] < 1.0 and res["mean_layers"] > 0
+
+
+def test_peel_projection_equals_iterated_cast(oracle_mod):
+    """methods.md:53-55 "raycasting projection": every layer's triangle set equals an oracle cast against the
+    triangles still present; areas are the hit triangles' 3-D and z-flattened areas (ray_casting.py:285-301)."""
+    from pyqsm_b200 import RaycastingScene, environment as env, _lib
+    import ctypes as C
+    v, t = syn.qsm_tree_mesh(seed=6, n_cylinders=12)
+    g = RaycastingScene(output_device="cuda")
+    g.add_triangles(v, t)
+    nu, nv = 160, 140
+    res = env.peel_projection(g, direction=(0, 0, -1), grid=(nu, nv))
+    layer_of = res["layer_of"].cpu().numpy()
+    assert len(res["layers"]) >= 3 and layer_of.shape == (t.shape[0],)
+    st = g.stats()
+    lo, hi = np.asarray(st["scene_lo"], np.float64), np.asarray(st["scene_hi"], np.float64)
+    grid = syn.parallel_ray_grid(lo, hi, np.array([0, 0, -1.0]), nu, nv)
+    rays = torch.empty(nu * nv, 6, dtype=torch.float32, device="cuda")
+    F3 = lambda x: (C.c_float * 3)(*[float(y) for y in x])
+    _lib.check(_lib.load().qsmrt_gen_parallel_rays(C.c_void_p(rays.data_ptr()), nu, nv, F3(grid[0]), F3(grid[1]), F3(grid[2]), F3(grid[3]), None))
+    torch.cuda.synchronize()
+    rays = rays.cpu().numpy()
+    alive = np.ones(t.shape[0], bool)
+    p0, p1, p2 = (v[t[:, k]].astype(np.float64) for k in range(3))
+    ng = np.cross(p1 - p0, p2 - p0)
+    a3, ap = 0.5 * np.linalg.norm(ng, axis=1), 0.5 * np.abs(ng[:, 2])
+    for k, (cnt, area3, areap) in enumerate(res["layers"]):
+        ids = np.nonzero(alive)[0]
+        o = oracle_mod.OracleScene()
+        o.add_triangles(v, t[ids])
+        ref = o.cast_rays(rays, 1)
+        hit = np.unique(ids[ref["primitive_ids"][ref["primitive_ids"] != 0xFFFFFFFF]])
+        assert np.array_equal(np.nonzero(layer_of == k)[0], hit), f"layer {k}"
+        assert cnt == len(hit)
+        np.testing.assert_allclose([area3, areap], [a3[hit].sum(), ap[hit].sum()], rtol=1e-5)
+        alive[hit] = False
+    # the loop stopped because the rays see nothing any more
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v, t[np.nonzero(alive)[0]]) if alive.any() else None
+    if alive.any():
+        assert not np.isfinite(o.cast_rays(rays, 1)["t_hit"]).any()
+    assert np.array_equal(layer_of == -1, alive)
+    np.testing.assert_allclose(res["area_projected"], ap[~alive].sum(), rtol=1e-5)
+    assert res["area_projected"] > 1.5 * ap[layer_of == 0].sum()          # overlap is counted separately
