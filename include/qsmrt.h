@@ -65,6 +65,19 @@ int qsmrt_add_triangles(qsmrt_scene *scene, const float *verts, uint64_t V,
                         const uint32_t *idx, uint64_t T, int ptrs_on_device,
                         uint32_t *geom_id_out);
 
+/* Cylinder-QSM ingestion on the device: n records of 8
+ * float32 (centre xyz, axis xyz, radius, height -- the cyl_details of
+ * pyQSM/qsm_generation.py:171-178) become ONE geometry of n closed cylinders
+ * with Open3D's create_cylinder topology (resolution 20 / split 4 in the
+ * reference, point_cloud_processing.py:274-279), rotated from +z onto the
+ * axis and moved to the centre as get_shape() does (:266-304).  Primitive id
+ * = cylinder * (2*res*(1+split)) + local triangle. */
+int qsmrt_add_cylinders(qsmrt_scene *scene, const float *records, uint64_t n, uint32_t resolution,
+                        uint32_t split, int ptr_on_device, uint32_t *geom_id_out);
+/* Size of / device copy of a registered geometry (vertices V x 3 float32, indices T x 3 uint32). */
+int qsmrt_geometry_size(qsmrt_scene *scene, uint32_t geom_id, uint64_t *V_out, uint64_t *T_out);
+int qsmrt_copy_geometry(qsmrt_scene *scene, uint32_t geom_id, float *verts_dev, uint32_t *idx_dev, void *stream);
+
 /* Embree rtcCommitScene, which Open3D runs lazily on the first query.  Builds
  * the LBVH (Morton codes, radix sort, Karras hierarchy, refit, leaf collapse).
  * Queries call it implicitly; calling it directly lets the build be timed.

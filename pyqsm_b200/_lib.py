@@ -35,6 +35,9 @@ SYMBOLS = {
     "qsmrt_scene_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "qsmrt_scene_destroy": (C.c_int, [_vp]),
     "qsmrt_add_triangles": (C.c_int, [_vp, _vp, _u64, _vp, _u64, C.c_int, C.POINTER(C.c_uint32)]),
+    "qsmrt_add_cylinders": (C.c_int, [_vp, _vp, _u64, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]),
+    "qsmrt_geometry_size": (C.c_int, [_vp, C.c_uint32, C.POINTER(_u64), C.POINTER(_u64)]),
+    "qsmrt_copy_geometry": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "qsmrt_commit": (C.c_int, [_vp, _vp, C.POINTER(_f)]),
     "qsmrt_cast_rays": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qsmrt_cast_rays_2d": (C.c_int, [_vp, _vp, C.c_uint32, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -119,6 +119,63 @@ __global__ void k_max_index(const uint32_t *__restrict__ in, uint64_t n3, uint32
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
+// QSM cylinder records -> triangle mesh with Open3D's create_cylinder topology (axis z, centred, 2 cap centres +
+// (split+1) rings of `res` vertices; 2*res cap + 2*res*split side triangles), rotated from +z onto the record's
+// axis (Rodrigues) and translated to its centre: what get_shape(..., shape="cylinder") builds on the CPU
+// (pyQSM/geometry/point_cloud_processing.py:266-304) from the records of qsm_generation.py:171-178.
+__global__ void __launch_bounds__(128)
+k_cylinders(const float *__restrict__ rec, uint64_t n, uint32_t res, uint32_t split, float *__restrict__ verts, uint32_t *__restrict__ idx)
+{
+    const uint64_t c = blockIdx.x;
+    if (c >= n) return;
+    const uint32_t V = res * (split + 1) + 2, T = 2 * res + 2 * res * split;
+    const float cx = rec[8 * c], cy = rec[8 * c + 1], cz = rec[8 * c + 2];
+    float ax = rec[8 * c + 3], ay = rec[8 * c + 4], az = rec[8 * c + 5];
+    const float radius = rec[8 * c + 6], height = rec[8 * c + 7];
+    float len = sqrtf(ax * ax + ay * ay + az * az);
+    if (len > 0.0f) { ax /= len; ay /= len; az /= len; } else { ax = 0.0f; ay = 0.0f; az = 1.0f; }
+    // R = I + [v]x + [v]x^2 / (1 + c), v = z x a = (-ay, ax, 0), c = az;  a = -z: rotate pi about x
+    float R[9];
+    if (az > -0.999999f) {
+        const float k = 1.0f / (1.0f + az), vx = -ay, vy = ax;
+        R[0] = 1.0f - vy * vy * k; R[1] = vx * vy * k;        R[2] = vy;
+        R[3] = vx * vy * k;        R[4] = 1.0f - vx * vx * k; R[5] = -vx;
+        R[6] = -vy;                R[7] = vx;                 R[8] = 1.0f - (vx * vx + vy * vy) * k;
+    } else {
+        R[0] = 1.0f; R[1] = 0.0f; R[2] = 0.0f; R[3] = 0.0f; R[4] = -1.0f; R[5] = 0.0f; R[6] = 0.0f; R[7] = 0.0f; R[8] = -1.0f;
+    }
+    float *vo = verts + 3ull * V * c;
+    for (uint32_t k = threadIdx.x; k < V; k += blockDim.x) {
+        float x, y, z;
+        if (k == 0) { x = 0.0f; y = 0.0f; z = 0.5f * height; }
+        else if (k == 1) { x = 0.0f; y = 0.0f; z = -0.5f * height; }
+        else {
+            const uint32_t ring = (k - 2) / res, j = (k - 2) % res;
+            const float th = 6.2831853071795864f * (float)j / (float)res;
+            x = cosf(th) * radius; y = sinf(th) * radius; z = 0.5f * height - (height / (float)split) * (float)ring;
+        }
+        vo[3 * k]     = R[0] * x + R[1] * y + R[2] * z + cx;
+        vo[3 * k + 1] = R[3] * x + R[4] * y + R[5] * z + cy;
+        vo[3 * k + 2] = R[6] * x + R[7] * y + R[8] * z + cz;
+    }
+    uint32_t *to = idx + 3ull * T * c;
+    const uint32_t vb = (uint32_t)(V * c);
+    for (uint32_t k = threadIdx.x; k < T; k += blockDim.x) {
+        uint32_t a, b, d;
+        if (k < 2 * res) {                               // caps, interleaved top / bottom like the host generator
+            const uint32_t j = k >> 1, j1 = (j + 1) % res;
+            if ((k & 1) == 0) { a = 0; b = 2 + j; d = 2 + j1; }
+            else { const uint32_t bb = 2 + res * split; a = 1; b = bb + j1; d = bb + j; }
+        } else {
+            const uint32_t q = k - 2 * res, i = q / (2 * res), r2 = q % (2 * res), j = r2 >> 1, j1 = (j + 1) % res;
+            const uint32_t b1 = 2 + res * i, b2 = b1 + res;
+            if ((r2 & 1) == 0) { a = b2 + j; b = b1 + j1; d = b1 + j; }
+            else { a = b2 + j; b = b2 + j1; d = b1 + j1; }
+        }
+        to[3 * k] = vb + a; to[3 * k + 1] = vb + b; to[3 * k + 2] = vb + d;
+    }
+}
+
 int use_device(qsmrt_scene *s)
 {
     if (!s) FAIL("null scene");
@@ -318,6 +375,56 @@ int qsmrt_add_triangles(qsmrt_scene *s, const float *verts, uint64_t V, const ui
     if (s->committed || s->verts) free_build(s);
     s->geoms.push_back(g);
     if (geom_id_out) *geom_id_out = (uint32_t)(s->geoms.size() - 1);
+    return 0;
+}
+
+int qsmrt_add_cylinders(qsmrt_scene *s, const float *records, uint64_t n, uint32_t resolution, uint32_t split,
+                        int on_device, uint32_t *geom_id_out)
+{
+    if (use_device(s)) return 1;
+    if (n && !records) FAIL("null records pointer");
+    if (resolution < 3 || split < 1 || resolution > 4096 || split > 4096) FAIL("resolution must be >= 3 and split >= 1");
+    const uint64_t V = (uint64_t)resolution * (split + 1) + 2, T = 2ull * resolution * (1 + split);
+    if (n * V >= (1ull << 32)) FAIL("too many cylinder vertices for 32-bit indices");
+    Geometry g;
+    g.V = n * V; g.T = n * T;
+    float *rec_dev = nullptr;
+    if (dmalloc(&g.verts, 3 * g.V) || dmalloc(&g.idx, 3 * g.T)) { dfree(g.verts); dfree(g.idx); return 1; }
+    if (n) {
+        const float *rec = records;
+        if (!on_device) {
+            if (dmalloc(&rec_dev, 8 * n)) { dfree(g.verts); dfree(g.idx); return 1; }
+            CUDA_TRY(cudaMemcpy(rec_dev, records, 8 * n * sizeof(float), cudaMemcpyHostToDevice));
+            rec = rec_dev;
+        }
+        k_cylinders<<<(unsigned)n, 128>>>(rec, n, resolution, split, g.verts, g.idx);
+        cudaError_t e = cudaDeviceSynchronize();
+        dfree(rec_dev);
+        if (e != cudaSuccess) { dfree(g.verts); dfree(g.idx); FAIL("cylinder generation failed: %s", cudaGetErrorString(e)); }
+    }
+    if (s->committed || s->verts) free_build(s);
+    s->geoms.push_back(g);
+    if (geom_id_out) *geom_id_out = (uint32_t)(s->geoms.size() - 1);
+    return 0;
+}
+
+int qsmrt_geometry_size(qsmrt_scene *s, uint32_t geom_id, uint64_t *V_out, uint64_t *T_out)
+{
+    if (!s) FAIL("null scene");
+    if (geom_id >= s->geoms.size()) FAIL("geometry id %u out of range", geom_id);
+    if (V_out) *V_out = s->geoms[geom_id].V;
+    if (T_out) *T_out = s->geoms[geom_id].T;
+    return 0;
+}
+
+int qsmrt_copy_geometry(qsmrt_scene *s, uint32_t geom_id, float *verts_dev, uint32_t *idx_dev, void *stream)
+{
+    if (use_device(s)) return 1;
+    if (geom_id >= s->geoms.size()) FAIL("geometry id %u out of range", geom_id);
+    const Geometry &g = s->geoms[geom_id];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (verts_dev && g.V) CUDA_TRY(cudaMemcpyAsync(verts_dev, g.verts, 3 * g.V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (idx_dev && g.T) CUDA_TRY(cudaMemcpyAsync(idx_dev, g.idx, 3 * g.T * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

@@ -117,6 +117,31 @@ class RaycastingScene:
         _lib.check(self._L.qsmrt_add_triangles(self._h, _ptr(v), v.shape[0], _ptr(t), t.shape[0], 1, C.byref(gid)))
         return int(gid.value)
 
+    def add_cylinders(self, centers, axes, radii, heights, resolution: int = 20, split: int = 4) -> int:
+        """Register a cylinder QSM (``cyl_details`` of ``pyQSM/qsm_generation.py:171-178``: centre, axis,
+        radius, height per cylinder) as one geometry; the closed cylinder meshes (Open3D ``create_cylinder``
+        topology) are generated on the GPU.  Returns the geometry id."""
+        rec = torch.cat([torch.as_tensor(np.asarray(centers), dtype=torch.float32).reshape(-1, 3),
+                         torch.as_tensor(np.asarray(axes), dtype=torch.float32).reshape(-1, 3),
+                         torch.as_tensor(np.asarray(radii), dtype=torch.float32).reshape(-1, 1),
+                         torch.as_tensor(np.asarray(heights), dtype=torch.float32).reshape(-1, 1)], dim=1)
+        rec = rec.to(self.device).contiguous()
+        gid = C.c_uint32()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            _lib.check(self._L.qsmrt_add_cylinders(self._h, _ptr(rec), rec.shape[0], int(resolution), int(split), 1, C.byref(gid)))
+        return int(gid.value)
+
+    def geometry(self, geometry_id: int):
+        """(vertex_positions float32 [V,3], triangle_indices uint32 [T,3]) of a registered geometry."""
+        nv, nt = C.c_uint64(), C.c_uint64()
+        _lib.check(self._L.qsmrt_geometry_size(self._h, int(geometry_id), C.byref(nv), C.byref(nt)))
+        with torch.cuda.device(self.device):
+            v = torch.empty(nv.value, 3, dtype=torch.float32, device=self.device)
+            t = torch.empty(nt.value, 3, dtype=torch.uint32, device=self.device)
+            _lib.check(self._L.qsmrt_copy_geometry(self._h, int(geometry_id), _ptr(v), _ptr(t), self._stream()))
+            return self._out(v), self._out(t)
+
     def commit(self) -> float:
         """Build the LBVH now (queries do it lazily); returns the build time in ms."""
         ms = C.c_float()

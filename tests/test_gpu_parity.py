@@ -498,3 +498,40 @@ def test_c2_full_size_properties(RS, oracle_mod):
     ref = o.cast_rays(sub, 1)
     ans = {k: x.reshape((-1,) + tuple(x.shape[2:]))[::16].cpu() for k, x in a.items()}
     assert assert_cast_equal(ans, ref, None, "C2 full size") == 0
+
+
+def test_add_cylinders_on_device(RS, oracle_mod):
+    """QSM cylinder records -> mesh on the GPU: same topology and vertices as Open3D's
+    create_cylinder + get_shape() placement built on the host, and rays see the same scene."""
+    from pyqsm_b200.synthetic import _rotation_to
+    rng = np.random.default_rng(8)
+    n = 40
+    centers = rng.uniform(-3, 3, size=(n, 3))
+    axes = rng.normal(size=(n, 3))
+    axes[0] = (0, 0, 1); axes[1] = (0, 0, -1); axes[2] = (1, 0, 0)
+    radii = rng.uniform(0.05, 0.4, size=n)
+    heights = rng.uniform(0.3, 2.0, size=n)
+    g = RS()
+    gid = g.add_cylinders(centers, axes, radii, heights)
+    assert gid == 0
+    v_dev, t_dev = g.geometry(gid)
+    cv, ct = syn.cylinder_mesh(1.0, 1.0, 20, 4)
+    vs, ts = [], []
+    for k in range(n):
+        R = _rotation_to(axes[k])
+        vk = (cv.astype(np.float64) * np.array([radii[k], radii[k], heights[k]])) @ R.T + centers[k]
+        vs.append(vk)
+        ts.append(ct + np.uint32(k * cv.shape[0]))
+    v_ref, t_ref = np.concatenate(vs).astype(np.float32), np.concatenate(ts)
+    assert v_dev.shape == (n * 102, 3) and t_dev.shape == (n * 200, 3)
+    assert np.array_equal(t_dev.numpy(), t_ref)
+    np.testing.assert_allclose(v_dev.numpy(), v_ref, atol=2e-6 * 8)
+    # the device-generated geometry traces like the same mesh handed to the oracle
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v_dev.numpy(), t_dev.numpy())
+    rays = syn.random_rays(v_ref.min(0), v_ref.max(0), 20000, seed=4)
+    a, r = g.cast_rays(rays), o.cast_rays(rays, 1)
+    assert_cast_equal(a, r, None, "cylinders")
+    assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 1))
+    inside = g.compute_occupancy(centers.astype(np.float32)).numpy()
+    assert inside.mean() > 0.9                                           # cylinder centres are inside their cylinders
