@@ -755,7 +755,7 @@ inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block -
 
 // --------------------------------------------------------------- launchers
 int g_trv_variant = 2;      // 1 = one independent loop per thread, 2 = persistent warp-uniform kernel (ships)
-int g_trv_tuning[4] = { 12, 12, 1, 0 }; // refill, want, tri_min, counters -- tuned on C2 (profiles/r01_tuning.txt)
+int g_trv_tuning[4] = { 12, 16, 1, 0 }; // refill, want, tri_min, counters -- tuned on C2 (profiles/r01_tuning.txt)
 unsigned long long *g_trv_stats_dev = nullptr;
 int g_trv_node_path = 0;                // 0 LSU 256-bit loads, 1 TEX, 2 half/half (qsmrt_debug_set_node_path)
 
