@@ -121,7 +121,14 @@ __device__ __forceinline__ void ld256u(const void *p, uint32_t &w0, uint32_t &w1
                  : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7)
                  : "l"(p));
 }
-// 16-bit grid coordinate -> the float 2^23 + q, one PRMT each (no int->float conversion)
+// 16-bit grid coordinate -> the float 2^23 + q, one PRMT each (no int->float conversion).  Raw prmt.b32: the
+// __byte_perm intrinsic masks a run-time selector first (an extra LOP3 per plane pair)
+__device__ __forceinline__ float prmt_f(uint32_t w, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x4B000000u), "r"(sel));
+    return __uint_as_float(d);
+}
 __device__ __forceinline__ float qlo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
 __device__ __forceinline__ float qhi(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
@@ -267,7 +274,7 @@ k_trace5(const TraceArgs A)
                     uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
                     ld256u(A.sc.qnodes + cur, w0, w1, w2, w3, w4, w5, w6, w7);
                     const uint32_t sfx = snx ^ 0x0022u, sfy = sny ^ 0x0022u, sfz = snz ^ 0x0022u;
-#define QPL(W, S) __uint_as_float(__byte_perm((W), 0x4B000000u, (S)))
+#define QPL(W, S) prmt_f((W), (S))
                     float nx = fmaf(QPL(w0, snx), r.idx, -r.oodx), fx = fmaf(QPL(w0, sfx), r.idx, -r.oodx);
                     float ny = fmaf(QPL(w1, sny), r.idy, -r.oody), fy = fmaf(QPL(w1, sfy), r.idy, -r.oody);
                     float nz = fmaf(QPL(w2, snz), r.idz, -r.oodz), fz = fmaf(QPL(w2, sfz), r.idz, -r.oodz);
