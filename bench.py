@@ -304,8 +304,8 @@ def run_ours(args):
             pass
     roofline["note"] = ("frac > 1 is expected here: the denominator charges every node/triangle fetch of the canonical "
                         "traversal to HBM, but ncu shows DRAM traffic ~= rays + results only (traffic field) -- the BVH is "
-                        "served from L1/L2 -- and the binding resource is the L1 data pipe "
-                        "(l1tex__data_pipe_lsu_wavefronts ~90% of peak, profiles/r01_cast_rays_summary.json)")
+                        "served from L1/L2 -- and the kernel is ALU-pipe / issue bound (sm__inst_executed_pipe_alu ~67-71%, "
+                        "issue ~69-71%, L1 data pipe ~61% of peak; profiles/r01_cast_rays_summary.json)")
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same rays
     cpu = None
