@@ -535,3 +535,30 @@ def test_add_cylinders_on_device(RS, oracle_mod):
     assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 1))
     inside = g.compute_occupancy(centers.astype(np.float32)).numpy()
     assert inside.mean() > 0.9                                           # cylinder centres are inside their cylinders
+
+
+from hypothesis import given, settings  # noqa: E402
+from test_oracle import _mesh_and_rays  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(_mesh_and_rays())
+def test_property_gpu_equals_brute_force(case):
+    """Adversarial small meshes (shared edges, slivers, duplicates, degenerates, three scales; rays through
+    vertices / edge midpoints / axis-parallel): every GPU query equals the oracle's brute force, bit for bit."""
+    import oracle
+    from pyqsm_b200 import RaycastingScene
+    v, t, rays = case
+    o, g = oracle.OracleScene(), RaycastingScene()
+    o.add_triangles(v, t)
+    g.add_triangles(v, t)
+    ref = o.cast_rays(rays, 0)
+    assert assert_cast_equal(g.cast_rays(rays), ref, None, "property") == 0
+    assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 0))
+    assert np.array_equal(g.test_occlusions(rays).numpy(), np.isfinite(ref["t_hit"]))
+    gl, ol = g.list_intersections(rays), o.list_intersections(rays, 0)
+    for k in ol:
+        assert np.array_equal(gl[k].numpy(), ol[k]), k
+    gp, op_ = g.compute_closest_points(rays[:, :3].copy()), o.compute_closest_points(rays[:, :3], 0)
+    for k in gp:
+        assert np.array_equal(gp[k].numpy(), op_[k]), k

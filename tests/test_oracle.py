@@ -236,3 +236,70 @@ def test_closest_points_oracle(orc):
     samples = (v[t[:, 0]] * w[:, :1] + v[t[:, 1]] * w[:, 1:2] + v[t[:, 2]] * w[:, 2:]).astype(np.float64)
     for i in range(0, 3000, 150):
         assert np.min(np.linalg.norm(samples - q[i], axis=1)) >= a["distance"][i] * (1 - 1e-5)
+
+
+# ---- property tests (hypothesis): the canonical LBVH is not semantics -- brute force is ----------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def _mesh_and_rays(draw):
+    """Small adversarial meshes: a grid patch with shared edges, optional slivers, duplicates and
+    degenerate triangles; rays that aim at vertices / edge midpoints as well as random ones."""
+    n = draw(st.integers(2, 5))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    xs, ys = np.meshgrid(np.arange(n + 1, dtype=np.float64), np.arange(n + 1, dtype=np.float64))
+    zs = rng.integers(-1, 2, size=xs.shape) * 0.25 * draw(st.sampled_from([0.0, 1.0]))
+    v = np.stack([xs.ravel(), ys.ravel(), zs.ravel()], 1)
+    tri = []
+    for j in range(n):
+        for i in range(n):
+            a, b, c, d = j * (n + 1) + i, j * (n + 1) + i + 1, (j + 1) * (n + 1) + i + 1, (j + 1) * (n + 1) + i
+            tri += [(a, b, c), (a, c, d)]
+    tri = np.asarray(tri, np.uint32)
+    if draw(st.booleans()):
+        tri = np.concatenate([tri, tri[: draw(st.integers(1, 4))]])               # exact duplicates
+    if draw(st.booleans()):
+        tri = np.concatenate([tri, np.array([[0, 0, 1], [2, 2, 2]], np.uint32)])      # degenerate
+    if draw(st.booleans()):
+        v = np.concatenate([v, [[0.5, 0.5, 1.0], [0.5 + 1e-6, 0.5, 1.0], [2.5, 2.5, 1.0]]])
+        tri = np.concatenate([tri, np.array([[len(v) - 3, len(v) - 2, len(v) - 1]], np.uint32)])   # sliver
+    scale = draw(st.sampled_from([1.0, 1e-3, 250.0]))
+    v = (v * scale).astype(np.float32)
+    k = 40
+    targets = np.concatenate([v[rng.integers(0, len(v), k)],                                    # through vertices
+                              0.5 * (v[tri[rng.integers(0, len(tri), k), 0]] + v[tri[rng.integers(0, len(tri), k), 1]]),
+                              rng.uniform(v.min(0), v.max(0) + 1e-6, size=(k, 3))]).astype(np.float64)
+    origins = targets + rng.normal(size=targets.shape) * scale * 3 + np.array([0, 0, 4.0 * scale])
+    axis = rng.integers(0, 3, len(targets))
+    d = targets - origins
+    snap = rng.random(len(targets)) < 0.3                                         # some axis-parallel rays
+    d[snap] = 0
+    d[snap, axis[snap]] = -scale
+    rays = np.concatenate([origins, d], 1).astype(np.float32)
+    return v, tri, rays
+
+
+@settings(max_examples=40, deadline=None)
+@given(_mesh_and_rays())
+def test_property_brute_equals_bvh(case):
+    import oracle
+    v, t, rays = case
+    s = oracle.OracleScene()
+    s.add_triangles(v, t)
+    a, b = s.cast_rays(rays, 0), s.cast_rays(rays, 1)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    c0, c1 = s.count_intersections(rays, 0), s.count_intersections(rays, 1)
+    assert np.array_equal(c0, c1)
+    assert np.array_equal(c0 > 0, np.isfinite(a["t_hit"]))
+    assert np.array_equal(s.test_occlusions(rays, mode=0), s.test_occlusions(rays, mode=1))
+    l0, l1 = s.list_intersections(rays, 0), s.list_intersections(rays, 1)
+    for k in l0:
+        assert np.array_equal(l0[k], l1[k]), k
+    assert np.array_equal(np.diff(l0["ray_splits"]), c0)
+    q = rays[:, :3]
+    p0, p1 = s.compute_closest_points(q, 0), s.compute_closest_points(q, 1)
+    for k in p0:
+        assert np.array_equal(p0[k], p1[k]), k
