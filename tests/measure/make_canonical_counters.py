@@ -6,10 +6,10 @@ algorithmic bytes per ray of the roofline:
     B_ray = 24 + OUT + 32 * N_node + 48 * N_tri
 They depend only on (mesh, rays), never on the GPU kernel.
 
-    python tools/make_canonical_counters.py            # ~2 min on 8 threads
+    python tests/measure/make_canonical_counters.py            # ~2 min on 8 threads
 """
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import oracle
 from pyqsm_b200 import synthetic as syn
@@ -44,7 +44,7 @@ for k, rows in out["configs"].items():
     nn = float(np.mean([r["n_node"] for r in rows])); nt = float(np.mean([r["n_tri"] for r in rows]))
     OUT = 4 if k.endswith("count") else 32
     out.setdefault("summary", {})[k] = dict(n_node=nn, n_tri=nt, out_bytes=OUT, b_ray=24 + OUT + 32 * nn + 48 * nt)
-os.makedirs(os.path.join(os.path.dirname(__file__), "..", "baseline"), exist_ok=True)
-with open(os.path.join(os.path.dirname(__file__), "..", "baseline", "canonical_counters.json"), "w") as f:
+os.makedirs(os.path.join(os.path.dirname(__file__), "..", "..", "baseline"), exist_ok=True)
+with open(os.path.join(os.path.dirname(__file__), "..", "..", "baseline", "canonical_counters.json"), "w") as f:
     json.dump(out, f, indent=1)
 print(json.dumps(out["summary"], indent=1))

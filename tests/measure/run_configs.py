@@ -2,17 +2,17 @@
 BASELINE.md section 7 (Mrays/s, canonical bytes per ray, roofline, build ms, CPU oracle Mrays/s, parity).
 Test / measurement infrastructure: uses the oracle as checker and CPU baseline.
 
-    python tools/run_configs.py [c1 c2 c3 c4 c5] > profiles/r01_configs.json
+    python tests/measure/run_configs.py [c1 c2 c3 c4 c5] > profiles/r01_configs.json
 """
 import ctypes as C, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import oracle
 from pyqsm_b200 import RaycastingScene, synthetic as syn, environment as env, _lib
 
 L = _lib.load()
 P = lambda x: C.c_void_p(x.data_ptr()); F3 = lambda x: (C.c_float * 3)(*[float(y) for y in x])
-HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6552.0
+HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json")) else 6552.0
 want = [a.lower() for a in sys.argv[1:]] or ["c1", "c2", "c3", "c4", "c5"]
 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
 rows = []
@@ -66,7 +66,7 @@ if "c2" in want or "c5" in want:
 if "c2" in want:
     sweep = syn.hemisphere_sweep(); env.sun_exposure(s2, sweep[:2], grid=(4000, 4000)); torch.cuda.synchronize()
     t0 = time.perf_counter(); r = env.sun_exposure(s2, sweep, grid=(4000, 4000)); torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    cc = json.load(open(os.path.join(os.path.dirname(__file__), "..", "baseline", "canonical_counters.json")))["summary"]["c2_canopy_2m_cast"]
+    cc = json.load(open(os.path.join(os.path.dirname(__file__), "..", "..", "baseline", "canonical_counters.json")))["summary"]["c2_canopy_2m_cast"]
     rays = gen_grid(s2, syn.sun_direction(40, 135), 4000, 4000); n = rays.shape[0]
     out = [torch.empty(n, device="cuda"), torch.empty(n, dtype=torch.uint32, device="cuda"), torch.empty(n, dtype=torch.uint32, device="cuda"), torch.empty(n, 2, device="cuda"), torch.empty(n, 3, device="cuda")]
     ms = gpu_time(lambda: _lib.check(L.qsmrt_cast_rays_2d(s2._h, P(rays), 4000, 4000, *[P(x) for x in out], None)))
