@@ -48,11 +48,11 @@ def test_fails_loudly_without_gpu():
 
 
 def test_product_does_not_import_oracle():
-    """The oracle is test infrastructure: nothing under pyqsm_b200/ may reference it."""
-    pkg = os.path.join(ROOT, "pyqsm_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h")):
-                text = open(os.path.join(dirpath, fn)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
-                assert "libqsmrt_oracle" not in text, fn
+    """The oracle is test infrastructure: nothing under pyqsm_b200/ or tools/ may reference it."""
+    for top in ("pyqsm_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, fn)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+                    assert "libqsmrt_oracle" not in text, fn
