@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -519,7 +520,9 @@ int qsmrt_cast_rays_host(qsmrt_scene *s, const float *rays, uint64_t N, float *t
     if (N && !rays) FAIL("rays pointer is null");
     if (do_commit(s, nullptr, nullptr)) return 1;
     if (N == 0) return 0;
-    const uint64_t chunk = std::min<uint64_t>(N, 1ull << 20);
+    uint64_t chunk_rays = 1ull << 20;                       // QSMRT_HOST_CHUNK overrides (rays per pipeline stage)
+    if (const char *e = getenv("QSMRT_HOST_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk_rays = (uint64_t)v; }
+    const uint64_t chunk = std::min<uint64_t>(N, chunk_rays);
     if (ensure_pipe(s, chunk)) return 1;
     HostPipe &hp = s->pipe;
     SceneView sv = view_of(s);

@@ -780,8 +780,18 @@ int next_cursor(unsigned long long **out, cudaStream_t st)
 template <int MODE, bool COUNTERS, bool QUANT>
 int launch_trace5_q(TraceArgs &a, size_t smem, int per_sm, int sms, cudaStream_t st)
 {
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_trace5<MODE, COUNTERS, QUANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<MODE, COUNTERS, QUANT>, TR_BLOCK, smem));
+    // occupancy of this instantiation at this stack size: queried once per device (small launches are latency bound)
+    static size_t cached_smem[64] = {};
+    static int cached_per_sm[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || cached_smem[dev] != smem || cached_per_sm[dev] == 0) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_trace5<MODE, COUNTERS, QUANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<MODE, COUNTERS, QUANT>, TR_BLOCK, smem));
+        if (dev >= 0 && dev < 64) { cached_smem[dev] = smem; cached_per_sm[dev] = per_sm; }
+    } else {
+        per_sm = cached_per_sm[dev];
+    }
     if (per_sm < 1) { qsmrt_set_error("persistent kernel does not fit (smem %zu)", smem); return 1; }
     unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
     k_trace5<MODE, COUNTERS, QUANT><<<g, TR_BLOCK, smem, st>>>(a);
