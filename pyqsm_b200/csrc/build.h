@@ -8,6 +8,7 @@ struct BuildParams {        // device-resident; filled by the bounds kernels
     float pad;              // absolute AABB padding
     float glo[3], cell[3], inv_cell[3];   // 16-bit quantisation grid of the 32-byte nodes
     float leaf_diag_sum;    // sum of leaf box diagonals (mean leaf size decides whether the grid is fine enough)
+    int   use_q;            // decided on the device after the leaves are emitted: write / read the 32-byte nodes
 };
 
 struct LbvhBuildArgs {

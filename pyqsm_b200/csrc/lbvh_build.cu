@@ -450,6 +450,13 @@ k_emit_leaves(const float *__restrict__ verts, const uint32_t *__restrict__ idx,
     if ((threadIdx.x & 31) == 0) atomicAdd(&bp->leaf_diag_sum, diag);
 }
 
+// The 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf.
+__global__ void k_decide_quant(BuildParams *bp, float ntris)
+{
+    const float max_cell = fmaxf(bp->cell[0], fmaxf(bp->cell[1], bp->cell[2]));
+    bp->use_q = 6.0f * max_cell <= 0.15f * (bp->leaf_diag_sum / ntris) ? 1 : 0;
+}
+
 // Bottom-up refit: one thread per leaf climbs; the second arrival at a node
 // (atomic flag) merges the two child boxes and continues.
 __global__ void __launch_bounds__(256)
@@ -539,7 +546,7 @@ k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ 
     int r0 = child_ref(me.left, n, range, leaf_max), r1 = child_ref(me.right, n, range, leaf_max);
     o.d = make_int4(r0, r1, 0, 0);
     tn[i] = o;
-    qn[i] = quantise_node(o, bp);
+    if (bp->use_q) qn[i] = quantise_node(o, bp);
 }
 
 // single-triangle scene: one node, one real child, one empty (inverted) box
@@ -621,6 +628,7 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st)) return 1;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
     k_emit_leaves<<<gN, B, 0, st>>>(A.verts, A.idx, (int64_t)n, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris);
+    k_decide_quant<<<1, 1, 0, st>>>(A.params, (float)n);
     CUDA_TRY(cudaMemsetAsync(A.counters, 0, 3 * sizeof(unsigned long long), st));
     if (n == 1) {
         k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);

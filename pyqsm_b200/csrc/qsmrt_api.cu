@@ -269,10 +269,8 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         for (int a = 0; a < 3; ++a) { s->stats.scene_lo[a] = bp.slo[a]; s->stats.scene_hi[a] = bp.shi[a]; }
         s->stats.box_pad = bp.pad;
         s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];
-        // the 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf
-        float max_cell = std::max(bp.cell[0], std::max(bp.cell[1], bp.cell[2]));
-        float mean_leaf = bp.leaf_diag_sum / (float)T;
-        s->use_qnodes = 6.0f * max_cell <= 0.15f * mean_leaf;
+        s->use_qnodes = bp.use_q != 0;                      // decided on the device (k_decide_quant)
+        if (!s->use_qnodes) dfree(s->qnodes);
         for (int a = 0; a < 3; ++a) { s->glo[a] = bp.glo[a]; s->cell[a] = bp.cell[a]; }
         s->stats.quantised_nodes = s->use_qnodes ? 1u : 0u;
         s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + T * sizeof(TriRec);
