@@ -562,3 +562,32 @@ def test_property_gpu_equals_brute_force(case):
     gp, op_ = g.compute_closest_points(rays[:, :3].copy()), o.compute_closest_points(rays[:, :3], 0)
     for k in gp:
         assert np.array_equal(gp[k].numpy(), op_[k]), k
+
+
+def test_far_origins_and_offset_scenes(RS, oracle_mod):
+    """The conservative-box argument (leaf padding 2^-17, 3-cell widening of quantised nodes) is stated for ray
+    origins within a few tens of scene sizes and scenes near the coordinate origin; check it holds with margin:
+    origins 20 scene diagonals away, and the same tree translated 300 m from the origin (LiDAR plot offsets)."""
+    from pyqsm_b200 import _lib
+    L = _lib.load()
+    v, t = syn.qsm_tree_mesh(seed=11, n_cylinders=40)
+    diag = float(np.linalg.norm(v.max(0) - v.min(0)))
+    for shift in (np.zeros(3, np.float32), np.array([300.0, -250.0, 40.0], np.float32)):
+        vs = (v + shift).astype(np.float32)
+        o = oracle_mod.OracleScene()
+        o.add_triangles(vs, t)
+        near = syn.random_rays(vs.min(0), vs.max(0), 6000, seed=3)
+        far = near.copy()
+        far[:, :3] -= far[:, 3:] * np.float32(20.0 * diag)             # same lines, origins 20 diagonals back
+        rays = np.concatenate([near, far])
+        ref = o.cast_rays(rays, 0)                                     # brute force
+        assert np.isfinite(ref["t_hit"][6000:]).sum() > 300
+        try:
+            for quant in (1, 0):
+                _lib.check(L.qsmrt_debug_set_quantised_nodes(quant))
+                g = RS()
+                g.add_triangles(vs, t)
+                assert_cast_equal(g.cast_rays(rays), ref, None, f"far/shift{shift[0]}/q{quant}")
+                assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 0))
+        finally:
+            _lib.check(L.qsmrt_debug_set_quantised_nodes(1))
