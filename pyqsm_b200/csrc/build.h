@@ -25,9 +25,7 @@ struct LbvhBuildArgs {
     uint32_t   *order, *order_tmp;  // [T]
     uint32_t   *sort_scratch;       // lbvh_sort_scratch_bytes(T)
     BNode      *bnodes;             // [2T-1]
-    int32_t    *parent;             // [2T-1]
-    int2       *range;              // [T-1]
-    uint32_t   *flags;              // [T-1]
+    unsigned long long *flags;      // [T-1] hand-over slot of each split (k_hierarchy_refit_emit)
     TriRec     *tris;               // [T]
     TNode      *tnodes;             // [max(T-1,1)]
     QNode      *qnodes;             // [max(T-1,1)] quantised twin of tnodes

@@ -103,22 +103,46 @@ __device__ __forceinline__ uint64_t spread21(uint32_t x)
 
 __global__ void __launch_bounds__(256)
 k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n,
-         const BuildParams *__restrict__ bp, uint64_t *__restrict__ keys, uint32_t *__restrict__ order)
+         BuildParams *__restrict__ bp, uint64_t *__restrict__ keys, uint32_t *__restrict__ order)
 {
-    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    float lo[3], hi[3];
-    tri_bounds(verts, idx, t, lo, hi);
-    uint32_t q[3];
+    __shared__ float wsum[8];
+    const float pad = bp->pad;
+    float diag = 0.0f;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        float lo[3], hi[3];
+        tri_bounds(verts, idx, t, lo, hi);
+        uint32_t q[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        float c = __fmul_rn(__fadd_rn(lo[a], hi[a]), 0.5f);
-        float f = __fmul_rn(__fsub_rn(c, bp->slo[a]), bp->scale[a]);
-        f = fminf(fmaxf(f, 0.0f), 2097151.0f);
-        q[a] = (uint32_t)f;
+        for (int a = 0; a < 3; ++a) {
+            float c = __fmul_rn(__fadd_rn(lo[a], hi[a]), 0.5f);
+            float f = __fmul_rn(__fsub_rn(c, bp->slo[a]), bp->scale[a]);
+            f = fminf(fmaxf(f, 0.0f), 2097151.0f);
+            q[a] = (uint32_t)f;
+        }
+        keys[t] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+        order[t] = (uint32_t)t;
+        // diagonal of the padded leaf box, as k_leaves_refit_emit will write it
+        float dx = __fadd_rn(hi[0], pad) - __fsub_rn(lo[0], pad), dy = __fadd_rn(hi[1], pad) - __fsub_rn(lo[1], pad),
+              dz = __fadd_rn(hi[2], pad) - __fsub_rn(lo[2], pad);
+        diag += sqrtf(dx * dx + dy * dy + dz * dz);
     }
-    keys[t] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
-    order[t] = (uint32_t)t;
+    // mean leaf size (decides whether the 16-bit node grid is fine enough): one atomic per block -- one per warp
+    // of a 10M-triangle launch is 312k atomics on one address, ~0.45 ms of serialised L2 traffic
+    for (int o = 16; o > 0; o >>= 1) diag += __shfl_xor_sync(0xFFFFFFFFu, diag, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = diag;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int k = 0; k < 8; ++k) s += wsum[k];
+        atomicAdd(&bp->leaf_diag_sum, s);
+    }
+}
+
+// The 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf.
+__global__ void k_decide_quant(BuildParams *bp, float ntris)
+{
+    const float max_cell = fmaxf(bp->cell[0], fmaxf(bp->cell[1], bp->cell[2]));
+    bp->use_q = 6.0f * max_cell <= 0.15f * (bp->leaf_diag_sum / ntris) ? 1 : 0;
 }
 
 // ------------------------------------------------------------ radix sort
@@ -256,9 +280,15 @@ k_rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
 // its global offsets by decoupled look-back over the tiles before it, and
 // scatters.  Per pass that is one read and one write of (key, value) instead
 // of the three kernels / extra key read of the classic variant above.
-// Tiles are handed out through an atomic counter so a tile only ever waits on
-// tiles that are already running.
+// The tile is first sorted by digit in shared memory, so the global stores of
+// a warp are runs of consecutive addresses (one run per digit present) rather
+// than 32 unrelated 8-byte stores.  Tiles are handed out through an atomic
+// counter so a tile only ever waits on tiles that are already running.
 constexpr uint32_t OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_MASK = (1u << 30) - 1u;
+constexpr int OS_THREADS = 256;
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_ITEMS = 12;                         // keys per thread
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;       // 3072 keys: 36 KB staged + 8 KB counters -> 4 CTAs / SM
 
 __global__ void __launch_bounds__(256)
 k_os_histogram(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ ghist /* [8][256] */)
@@ -291,34 +321,38 @@ k_os_scan_hist(uint32_t *__restrict__ ghist)
     row[threadIdx.x] = off + x - v;
 }
 
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(OS_THREADS, 4)
 k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
           uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n, int shift,
           const uint32_t *__restrict__ gbase /* [256] digit starts of this pass */,
           uint32_t *status /* [ntiles][256], zeroed */, uint32_t *tile_counter)
 {
-    __shared__ uint32_t wcnt[RS_WARPS][256];
-    __shared__ uint32_t dbase[256];
+    __shared__ uint64_t skey[OS_TILE];
+    __shared__ uint32_t sval[OS_TILE];
+    __shared__ uint32_t wcnt[OS_WARPS][256];     // per-warp digit counts, then exclusive offsets inside the tile
+    __shared__ uint32_t gofs[256];               // global address of the digit's first key of this tile - its tile offset
+    __shared__ uint32_t wsum[OS_WARPS];
     __shared__ uint32_t s_tile;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < OS_WARPS * 256; i += OS_THREADS) (&wcnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    const uint64_t tbase = (uint64_t)tile * OS_TILE;
+    const uint32_t tcount = (uint32_t)min((uint64_t)OS_TILE, n - tbase);
 
-    uint64_t kreg[RS_ROUNDS];
-    uint32_t vreg[RS_ROUNDS];
-    uint16_t rnk[RS_ROUNDS];
-    const uint64_t base = (uint64_t)tile * RS_TILE + (uint64_t)w * (32 * RS_ROUNDS);
+    uint64_t kreg[OS_ITEMS];
+    uint16_t rnk[OS_ITEMS];
+    const uint32_t wbase = (uint32_t)w * (32 * OS_ITEMS);
     const uint32_t lt = (1u << l) - 1u;
 #pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) { uint64_t i = base + r * 32 + l; kreg[r] = i < n ? kin[i] : ~0ull; }
+    for (int r = 0; r < OS_ITEMS; ++r) { uint32_t j = wbase + r * 32 + l; kreg[r] = j < tcount ? kin[tbase + j] : ~0ull; }
 #pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) { uint64_t i = base + r * 32 + l; vreg[r] = i < n ? vin[i] : 0u; }
-#pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) {
-        const bool valid = base + r * 32 + l < n;
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const bool valid = wbase + r * 32 + l < tcount;
         const uint32_t d = valid ? ((uint32_t)(kreg[r] >> shift) & 0xFFu) : 256u;
+        // lanes holding the same digit: nine ballots (8 digit bits + validity) instead of MATCH.ANY,
+        // which serialises over the distinct values of the warp
         uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
         m = valid ? m : ~m;
 #pragma unroll
@@ -333,13 +367,22 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
         rnk[r] = (uint16_t)(before + __popc(m & lt));
     }
     __syncthreads();
-    {   // thread d owns digit d: tile count, publish, look back, global base
+    {   // thread d owns digit d: tile count, publish, offsets inside the tile, look back, global base
         const uint32_t d = threadIdx.x;
         uint32_t run = 0;
 #pragma unroll
-        for (int k = 0; k < RS_WARPS; ++k) { uint32_t v = wcnt[k][d]; wcnt[k][d] = run; run += v; }
+        for (int k = 0; k < OS_WARPS; ++k) { uint32_t v = wcnt[k][d]; wcnt[k][d] = run; run += v; }
         volatile uint32_t *st = status;
         st[(uint64_t)tile * 256 + d] = (tile == 0 ? OS_INC : OS_AGG) | run;
+        // exclusive scan of the tile's digit counts -> where each digit starts in the staged tile
+        uint32_t x = run;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (l >= o) x += y; }
+        if (l == 31) wsum[w] = x;
+        __syncthreads();
+        uint32_t tstart = x - run;
+        for (int k = 0; k < w; ++k) tstart += wsum[k];
+#pragma unroll
+        for (int k = 0; k < OS_WARPS; ++k) wcnt[k][d] += tstart;
         uint32_t excl = 0;
         for (int64_t k = (int64_t)tile - 1; k >= 0; --k) {
             uint32_t sv;
@@ -348,59 +391,40 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
             if ((sv >> 30) == 2u) break;
         }
         if (tile != 0) st[(uint64_t)tile * 256 + d] = OS_INC | (excl + run);
-        dbase[d] = gbase[d] + excl;
+        gofs[d] = gbase[d] + excl - tstart;
+    }
+    __syncthreads();
+    // stage: keys (and their values, read now) to their place in the digit-sorted tile
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const uint32_t j = wbase + r * 32 + l;
+        if (j < tcount) {
+            const uint32_t d = (uint32_t)(kreg[r] >> shift) & 0xFFu;
+            const uint32_t pos = wcnt[w][d] + rnk[r];
+            skey[pos] = kreg[r];
+            sval[pos] = vin[tbase + j];
+        }
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RS_ROUNDS; ++r) {
-        if (base + r * 32 + l < n) {
-            const uint32_t d = (uint32_t)(kreg[r] >> shift) & 0xFFu;
-            const uint64_t dst = (uint64_t)dbase[d] + wcnt[w][d] + rnk[r];
-            kout[dst] = kreg[r];
-            vout[dst] = vreg[r];
+    for (int r = 0; r < OS_ITEMS; ++r) {
+        const uint32_t j = r * OS_THREADS + threadIdx.x;
+        if (j < tcount) {
+            const uint64_t k = skey[j];
+            const uint32_t dst = gofs[(uint32_t)(k >> shift) & 0xFFu] + j;      // mod 2^32: gofs may have wrapped below 0
+            kout[dst] = k;
+            vout[dst] = sval[j];
         }
     }
 }
 
 // ------------------------------------------------------------- hierarchy
-__device__ __forceinline__ int delta(const uint64_t *__restrict__ k, int64_t n, int64_t i, int64_t j)
+// Common-prefix length of the augmented keys (key, index) of the adjacent sorted leaves j and j + 1
+// (Karras 2012, section 4: ties broken by the index); -1 outside the array.
+__device__ __forceinline__ int delta_adjacent(uint64_t ka, uint64_t kb, int64_t j)
 {
-    if (j < 0 || j >= n) return -1;
-    uint64_t a = k[i], b = k[j];
-    if (a != b) return __clzll((long long)(a ^ b));
-    return 64 + __clz((int)((uint32_t)i ^ (uint32_t)j));
-}
-
-// Karras 2012: one thread per internal node; writes children (unified index
-// space), parents and the covered leaf range.
-__global__ void __launch_bounds__(256)
-k_karras(const uint64_t *__restrict__ keys, int64_t n, BNode *__restrict__ bn,
-         int32_t *__restrict__ parent, int2 *__restrict__ range)
-{
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    int dmin = delta(keys, n, i, i - d);
-    int64_t lmax = 2;
-    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
-    int64_t l = 0;
-    for (int64_t t = lmax / 2; t >= 1; t /= 2)
-        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    int64_t j = i + l * d;
-    int dnode = delta(keys, n, i, j);
-    int64_t sp = 0;
-    for (int64_t t = (l + 1) / 2;; t = (t + 1) / 2) {
-        if (delta(keys, n, i, i + (sp + t) * d) > dnode) sp += t;
-        if (t <= 1) break;
-    }
-    int64_t gamma = i + sp * d + (d < 0 ? -1 : 0);
-    int64_t first = min(i, j), last = max(i, j);
-    int32_t left  = (first == gamma)    ? (int32_t)(n - 1 + gamma)     : (int32_t)gamma;
-    int32_t right = (last == gamma + 1) ? (int32_t)(n - 1 + gamma + 1) : (int32_t)(gamma + 1);
-    bn[i].left = left; bn[i].right = right;
-    parent[left] = (int32_t)i; parent[right] = (int32_t)i;
-    if (i == 0) parent[0] = -1;
-    range[i] = make_int2((int)first, (int)last);
+    if (ka != kb) return __clzll((long long)(ka ^ kb));
+    return 64 + __clz((int)((uint32_t)j ^ (uint32_t)(j + 1)));
 }
 
 __device__ __forceinline__ uint32_t geom_of(const uint64_t *__restrict__ goff, uint32_t ngeoms, uint64_t t)
@@ -410,81 +434,6 @@ __device__ __forceinline__ uint32_t geom_of(const uint64_t *__restrict__ goff, u
     return lo;
 }
 
-// Leaves in sorted order: padded boxes into the binary node array and the
-// 48-byte triangle records the traversal kernels read.
-__global__ void __launch_bounds__(256)
-k_emit_leaves(const float *__restrict__ verts, const uint32_t *__restrict__ idx, int64_t n,
-              const uint32_t *__restrict__ order, const uint64_t *__restrict__ goff, uint32_t ngeoms,
-              BuildParams *__restrict__ bp, BNode *__restrict__ bn, TriRec *__restrict__ tris)
-{
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    float diag = 0.0f;
-    if (i < n) {
-        uint64_t t = order[i];
-        uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
-        float p0[3], p1[3], p2[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { p0[a] = verts[3ull * i0 + a]; p1[a] = verts[3ull * i1 + a]; p2[a] = verts[3ull * i2 + a]; }
-        const float pad = bp->pad;
-        BNode b;
-        b.lox = __fsub_rn(fminf(p0[0], fminf(p1[0], p2[0])), pad);
-        b.loy = __fsub_rn(fminf(p0[1], fminf(p1[1], p2[1])), pad);
-        b.loz = __fsub_rn(fminf(p0[2], fminf(p1[2], p2[2])), pad);
-        b.hix = __fadd_rn(fmaxf(p0[0], fmaxf(p1[0], p2[0])), pad);
-        b.hiy = __fadd_rn(fmaxf(p0[1], fmaxf(p1[1], p2[1])), pad);
-        b.hiz = __fadd_rn(fmaxf(p0[2], fmaxf(p1[2], p2[2])), pad);
-        b.left = -1; b.right = -1;
-        bn[n - 1 + i] = b;
-        float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
-        diag = sqrtf(dx * dx + dy * dy + dz * dz);
-        uint32_t g = ngeoms > 1 ? geom_of(goff, ngeoms, t) : 0u;
-        uint32_t prim = (uint32_t)(t - goff[g]);
-        TriRec r;
-        r.p0 = make_float4(p0[0], p0[1], p0[2], __uint_as_float(prim));
-        r.p1 = make_float4(__fsub_rn(p0[0], p1[0]), __fsub_rn(p0[1], p1[1]), __fsub_rn(p0[2], p1[2]), __uint_as_float(g));
-        r.p2 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.0f);
-        tris[i] = r;
-    }
-    // mean leaf size (decides whether the 16-bit node grid is fine enough): one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) diag += __shfl_xor_sync(0xFFFFFFFFu, diag, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&bp->leaf_diag_sum, diag);
-}
-
-// The 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf.
-__global__ void k_decide_quant(BuildParams *bp, float ntris)
-{
-    const float max_cell = fmaxf(bp->cell[0], fmaxf(bp->cell[1], bp->cell[2]));
-    bp->use_q = 6.0f * max_cell <= 0.15f * (bp->leaf_diag_sum / ntris) ? 1 : 0;
-}
-
-// Bottom-up refit: one thread per leaf climbs; the second arrival at a node
-// (atomic flag) merges the two child boxes and continues.
-__global__ void __launch_bounds__(256)
-k_refit(int64_t n, BNode *bn, const int32_t *__restrict__ parent, uint32_t *flags, unsigned long long *counters)
-{
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int32_t p = parent[n - 1 + i];
-    uint32_t h = 0;                       // height of the subtree just finished (leaf = 0)
-    while (p >= 0) {
-        __threadfence();
-        // the flag carries the first child's height + 1; 0 = nobody arrived yet
-        uint32_t other = atomicExch(&flags[p], h + 1u);
-        if (other == 0u) return;
-        h = max(h, other - 1u) + 1u;
-        if (p == 0) counters[2] = h;      // tree height (edges from the root to the deepest leaf)
-        const float4 *cl = reinterpret_cast<const float4 *>(&bn[bn[p].left]);
-        const float4 *cr = reinterpret_cast<const float4 *>(&bn[bn[p].right]);
-        float4 llo = __ldcg(cl), lhi = __ldcg(cl + 1), rlo = __ldcg(cr), rhi = __ldcg(cr + 1);
-        bn[p].lox = fminf(llo.x, rlo.x); bn[p].loy = fminf(llo.y, rlo.y); bn[p].loz = fminf(llo.z, rlo.z);
-        bn[p].hix = fmaxf(lhi.x, rhi.x); bn[p].hiy = fmaxf(lhi.y, rhi.y); bn[p].hiz = fmaxf(lhi.z, rhi.z);
-        p = parent[p];
-    }
-}
-
-// Collapse subtrees of <= QSMRT_LEAF_MAX triangles into leaves and emit the
-// 64-byte traversal nodes (indexed like the binary internal nodes; collapsed
-// interior nodes are simply never referenced).
 // conservative 16-bit encoding of one box axis: floor/ceil on the grid, widened by 3 cells
 __device__ __forceinline__ uint32_t quantise_axis(float lo, float hi, float glo, float inv_cell)
 {
@@ -506,47 +455,173 @@ __device__ __forceinline__ QNode quantise_node(const TNode &o, const BuildParams
     return q;
 }
 
-__device__ __forceinline__ int child_ref(int32_t c, int64_t n, const int2 *__restrict__ range, int leaf_max)
+// The hierarchy, the refit and all node output in ONE kernel, one thread per sorted leaf.
+//
+// Topology bottom-up (Apetrei 2014, "Fast and simple agglomerative LBVH construction"): a thread holds a
+// finished subtree over the sorted leaves [l, r] together with its box and the prefix lengths dl = delta(l-1, l),
+// dr = delta(r, r+1) to its two outside neighbours.  The subtree's parent joins it with the neighbour it shares
+// the LONGER prefix with (dl == dr is impossible for sorted distinct augmented keys): dr > dl -> it is the left
+// child of the node whose split lies between r and r+1, else the right child of the split between l-1 and l.
+// That is the same binary radix tree Karras' top-down search produces, and its numbering follows too: Karras
+// gives a left child the index of its LAST leaf and a right child the index of its FIRST leaf (root 0), so a
+// node learns its own index the moment it knows which side its parent lies on -- no search, no parent / range
+// arrays, no separate hierarchy kernel.
+//   * warp phase: while the sibling subtree is held by a lane of the same warp (the lane of its first leaf), the
+//     left lane takes the sibling's box, far end and far delta with shuffles -- no loads, atomics or fences
+//     (about 5 of 6 internal nodes end here);
+//   * global phase: a 64-bit exchange on the split's flag hands the first arrival's far end, far delta and
+//     height to the second, which reads the sibling's box (one 32-byte read from L2) and goes on;
+//   * output: the merging thread holds both child boxes, so it writes the binary node, the 64-byte traversal
+//     node and (when the scene uses them) its 32-byte quantised twin.  Subtrees of <= leaf_max triangles
+//     collapse into leaves: such a node is never referenced and its traversal node is not written.
+struct RefitOut {
+    BNode *bn; TNode *tn; QNode *qn; const BuildParams *bp; unsigned long long *counters;
+    int64_t n; int leaf_max; bool use_q;
+};
+
+// Write node `id` = [l .. g | g+1 .. r] with child boxes (llo, lhi) and (rlo, rhi); returns its box in mlo / mhi.
+__device__ __forceinline__ void refit_write(const RefitOut &R, int32_t id, int l, int g, int r,
+                                            const float4 llo, const float4 lhi, const float4 rlo, const float4 rhi,
+                                            float4 &mlo, float4 &mhi, unsigned &n_nodes, unsigned &n_leafrefs)
 {
-    if (c >= n - 1) return ~(int)(((uint32_t)(c - (n - 1)) << 2) | 0u);
-    int2 r = range[c];
-    int cnt = r.y - r.x + 1;
-    if (cnt <= leaf_max) return ~(int)(((uint32_t)r.x << 2) | (uint32_t)(cnt - 1));
-    return c;
+    const int32_t left = l == g ? (int32_t)(R.n - 1) + g : g;
+    const int32_t right = g + 1 == r ? (int32_t)(R.n - 1) + g + 1 : g + 1;
+    if (id == 0 || r - l + 1 > R.leaf_max) {
+        const int cl = g - l + 1, cr = r - g;
+        const int r0 = cl <= R.leaf_max ? ~(int)(((uint32_t)l << 2) | (uint32_t)(cl - 1)) : left;
+        const int r1 = cr <= R.leaf_max ? ~(int)(((uint32_t)(g + 1) << 2) | (uint32_t)(cr - 1)) : right;
+        TNode o;
+        o.a = make_float4(llo.x, lhi.x, llo.y, lhi.y);
+        o.b = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
+        o.c = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
+        o.d = make_int4(r0, r1, 0, 0);
+        R.tn[id] = o;
+        if (R.use_q) R.qn[id] = quantise_node(o, R.bp);
+        ++n_nodes; n_leafrefs += (r0 < 0) + (r1 < 0);
+    }
+    mlo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), __int_as_float(left));
+    mhi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), __int_as_float(right));
+    reinterpret_cast<float4 *>(&R.bn[id])[0] = mlo;
+    reinterpret_cast<float4 *>(&R.bn[id])[1] = mhi;
 }
 
-__global__ void __launch_bounds__(256)
-k_emit_tnodes(int64_t n, const BNode *__restrict__ bn, const int2 *__restrict__ range,
-              TNode *__restrict__ tn, QNode *__restrict__ qn, const BuildParams *__restrict__ bp,
-              unsigned long long *__restrict__ counters, int leaf_max)
+constexpr int RF_BLOCK = 128;
+
+__global__ void __launch_bounds__(RF_BLOCK)
+k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restrict__ idx, int64_t n,
+                       const uint64_t *__restrict__ keys, const uint32_t *__restrict__ order,
+                       const uint64_t *__restrict__ goff, uint32_t ngeoms,
+                       const BuildParams *__restrict__ bp, BNode *bn, TriRec *__restrict__ tris,
+                       unsigned long long *flags, TNode *__restrict__ tn, QNode *__restrict__ qn,
+                       unsigned long long *counters, int leaf_max)
 {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool live = i < n - 1;
-    int2 r = live ? range[i] : make_int2(0, 0);
-    if (live && i != 0 && (r.y - r.x + 1) <= leaf_max) live = false;     // folded into a leaf above
-    // statistics: one atomic per warp, not per thread
-    unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-    int nleaf = 0;
-    if (live) {
-        BNode me0 = bn[i];
-        nleaf = (child_ref(me0.left, n, range, leaf_max) < 0) + (child_ref(me0.right, n, range, leaf_max) < 0);
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int w0 = (int)(i - lane);               // first leaf of this warp
+    unsigned n_nodes = 0, n_leafrefs = 0;
+    RefitOut R{ bn, tn, qn, bp, counters, n, leaf_max, bp->use_q != 0 };
+    float4 mlo = make_float4(0.f, 0.f, 0.f, 0.f), mhi = mlo;      // box of the subtree I hold, as the binary node stores it
+    int l = 0, r = 0, dl = -1, dr = -1;
+    bool holding = false;                         // I carry a finished subtree nobody has merged yet
+    if (i < n) {
+        const uint64_t t = order[i];
+        const uint64_t k = keys[i];
+        if (i > 0) dl = delta_adjacent(keys[i - 1], k, i - 1);
+        if (i + 1 < n) dr = delta_adjacent(k, keys[i + 1], i);
+        uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
+        float p0[3], p1[3], p2[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { p0[a] = verts[3ull * i0 + a]; p1[a] = verts[3ull * i1 + a]; p2[a] = verts[3ull * i2 + a]; }
+        const float pad = bp->pad;
+        mlo.x = __fsub_rn(fminf(p0[0], fminf(p1[0], p2[0])), pad);
+        mlo.y = __fsub_rn(fminf(p0[1], fminf(p1[1], p2[1])), pad);
+        mlo.z = __fsub_rn(fminf(p0[2], fminf(p1[2], p2[2])), pad);
+        mhi.x = __fadd_rn(fmaxf(p0[0], fmaxf(p1[0], p2[0])), pad);
+        mhi.y = __fadd_rn(fmaxf(p0[1], fmaxf(p1[1], p2[1])), pad);
+        mhi.z = __fadd_rn(fmaxf(p0[2], fmaxf(p1[2], p2[2])), pad);
+        mlo.w = __int_as_float(-1); mhi.w = __int_as_float(-1);
+        float4 *leaf = reinterpret_cast<float4 *>(&bn[n - 1 + i]);
+        leaf[0] = mlo; leaf[1] = mhi;
+        uint32_t g = ngeoms > 1 ? geom_of(goff, ngeoms, t) : 0u;
+        uint32_t prim = (uint32_t)(t - goff[g]);
+        TriRec rec;
+        rec.p0 = make_float4(p0[0], p0[1], p0[2], __uint_as_float(prim));
+        rec.p1 = make_float4(__fsub_rn(p0[0], p1[0]), __fsub_rn(p0[1], p1[1]), __fsub_rn(p0[2], p1[2]), __uint_as_float(g));
+        rec.p2 = make_float4(__fsub_rn(p2[0], p0[0]), __fsub_rn(p2[1], p0[1]), __fsub_rn(p2[2], p0[2]), 0.0f);
+        tris[i] = rec;
+        l = r = (int)i;
+        holding = n > 1;
     }
-    for (int o = 16; o > 0; o >>= 1) nleaf += __shfl_xor_sync(0xFFFFFFFFu, nleaf, o);
-    if ((threadIdx.x & 31) == 0 && m) {
-        atomicAdd(&counters[0], (unsigned long long)__popc(m));
-        atomicAdd(&counters[1], (unsigned long long)nleaf);
+    uint32_t h = 0;                               // height of the subtree I hold (leaf = 0)
+
+    // ---- warp phase: I am a left child (dr > dl) and the lane of leaf r+1 holds my finished right sibling
+    for (;;) {
+        const bool go_right = dr > dl;
+        const int partner = (holding && go_right && r + 1 - w0 < 32) ? r + 1 - w0 : lane;
+        const bool p_hold = __shfl_sync(FULL, (int)holding, partner) != 0;
+        const bool p_right = __shfl_sync(FULL, (int)go_right, partner) != 0;
+        const int p_r = __shfl_sync(FULL, r, partner);
+        const int p_dr = __shfl_sync(FULL, dr, partner);
+        const uint32_t p_h = __shfl_sync(FULL, h, partner);
+        float4 slo, shi;
+        slo.x = __shfl_sync(FULL, mlo.x, partner); slo.y = __shfl_sync(FULL, mlo.y, partner); slo.z = __shfl_sync(FULL, mlo.z, partner);
+        shi.x = __shfl_sync(FULL, mhi.x, partner); shi.y = __shfl_sync(FULL, mhi.y, partner); shi.z = __shfl_sync(FULL, mhi.z, partner);
+        // the partner lane's subtree starts at its own leaf (r + 1); it is my sibling iff it wants to go left
+        const bool take = partner != lane && p_hold && !p_right;
+        // a taken lane cannot see its taker (it does not know where its left sibling starts): the takers tell it
+        const unsigned consumed = __reduce_or_sync(FULL, take ? (1u << partner) : 0u);
+        if (take) {
+            const int g = r;
+            r = p_r; dr = p_dr;
+            h = max(h, p_h) + 1u;
+            const int32_t id = (l == 0 && r == (int)(n - 1)) ? 0 : (dr > dl ? r : l);
+            if (id == 0 && l == 0 && r == (int)(n - 1)) counters[2] = h;      // tree height (edges from the root to the deepest leaf)
+            refit_write(R, id, l, g, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
+            if (l == 0 && r == (int)(n - 1)) holding = false;                 // the root: done
+        }
+        if ((consumed >> lane) & 1u) holding = false;
+        if (consumed == 0u) break;
     }
-    if (!live) return;
-    BNode me = bn[i];
-    BNode c0 = bn[me.left], c1 = bn[me.right];
-    TNode o;
-    o.a = make_float4(c0.lox, c0.hix, c0.loy, c0.hiy);
-    o.b = make_float4(c1.lox, c1.hix, c1.loy, c1.hiy);
-    o.c = make_float4(c0.loz, c0.hiz, c1.loz, c1.hiz);
-    int r0 = child_ref(me.left, n, range, leaf_max), r1 = child_ref(me.right, n, range, leaf_max);
-    o.d = make_int4(r0, r1, 0, 0);
-    tn[i] = o;
-    if (bp->use_q) qn[i] = quantise_node(o, bp);
+
+    // ---- global phase: the sibling is finished by a thread of another warp
+    while (holding) {
+        const bool go_right = dr > dl;
+        const int s = go_right ? r : l - 1;       // the parent's split lies between leaves s and s + 1
+        // What the second arrival needs from the first: its far end, the delta beyond it and its height.
+        // Release exchange (MEMBAR.ALL + ATOMG): my binary node is in L2 before the flag.  __threadfence() would
+        // be MEMBAR.SC plus an L1 invalidate (CCTL.IVALL) per level, which the __ldcg sibling read does not need.
+        const unsigned long long mine = (unsigned long long)(uint32_t)((go_right ? l : r) + 1)
+                                      | ((unsigned long long)h << 32) | ((unsigned long long)(uint32_t)((go_right ? dl : dr) + 1) << 40);
+        unsigned long long other;
+        asm volatile("atom.release.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(other) : "l"(flags + s), "l"(mine) : "memory");
+        if (other == 0ull) break;                 // first to arrive: the sibling's thread takes over
+        const int o_end = (int)(uint32_t)(other & 0xFFFFFFFFull) - 1;
+        const uint32_t o_h = (uint32_t)(other >> 32) & 0xFFu;
+        const int o_d = (int)((other >> 40) & 0xFFu) - 1;
+        // sibling's index: a right sibling [s+1, o_end] is a right child (index = its first leaf), a left
+        // sibling [o_end, s] a left child (index = its last leaf); single leaves live at n-1+leaf
+        const int sib = go_right ? (o_end == s + 1 ? (int)(n - 1) + s + 1 : s + 1) : (o_end == s ? (int)(n - 1) + s : s);
+        const float4 *cs = reinterpret_cast<const float4 *>(&bn[sib]);
+        const float4 slo = __ldcg(cs), shi = __ldcg(cs + 1);
+        h = max(h, o_h) + 1u;
+        if (go_right) { r = o_end; dr = o_d; } else { l = o_end; dl = o_d; }
+        const bool root = l == 0 && r == (int)(n - 1);
+        const int32_t id = root ? 0 : (dr > dl ? r : l);
+        if (root) counters[2] = h;
+        if (go_right) refit_write(R, id, l, s, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
+        else          refit_write(R, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
+        if (root) break;
+    }
+    // statistics: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
+        n_leafrefs += __shfl_xor_sync(FULL, n_leafrefs, o);
+    }
+    if (lane == 0 && n_nodes) {
+        atomicAdd(&counters[0], (unsigned long long)n_nodes);
+        atomicAdd(&counters[1], (unsigned long long)n_leafrefs);
+    }
 }
 
 // single-triangle scene: one node, one real child, one empty (inverted) box
@@ -575,10 +650,13 @@ int g_sort_variant = 1;      // 0 classic (3 kernels per pass), 1 onesweep (deco
 
 size_t lbvh_sort_scratch_bytes(uint64_t n)
 {
-    uint64_t ntiles = (n + RS_TILE - 1) / RS_TILE;
-    // classic: tile_hist[256][ntiles] + digit_tot[256]; onesweep: ghist[8][256] + status[ntiles][256] + counters[8]
-    return (size_t)(ntiles * 256 + 8 * 256 + 256 + 64) * sizeof(uint32_t);
+    uint64_t ntiles = (n + RS_TILE - 1) / RS_TILE, os_tiles = (n + OS_TILE - 1) / OS_TILE;
+    // classic: tile_hist[256][ntiles] + digit_tot[256]; onesweep: status[8][os_tiles][256] + ghist[8][256] + counters[8]
+    uint64_t classic = ntiles * 256 + 256, onesweep = 8 * os_tiles * 256 + 8 * 256 + 8;
+    return (size_t)(std::max(classic, onesweep) + 64) * sizeof(uint32_t);
 }
+
+int g_sort_min_onesweep = 0;     // keys from which the onesweep variant is used (qsmrt_debug_set_sort)
 
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
                     uint64_t n, uint32_t *scratch, cudaStream_t st)
@@ -588,14 +666,16 @@ int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t
     uint32_t *tile_hist = scratch, *digit_tot = scratch + (uint64_t)ntiles * 256;
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
-    if (g_sort_variant == 1 && n >= (8u << 20)) {      // measured: look-back wins from ~8M keys, the 3-kernel pass below that
-        uint32_t *status = scratch, *ghist = scratch + (uint64_t)ntiles * 256, *counters = ghist + 8 * 256;
-        CUDA_TRY(cudaMemsetAsync(ghist, 0, (8 * 256 + 8) * sizeof(uint32_t), st));
+    if (g_sort_variant == 1 && n >= (uint64_t)g_sort_min_onesweep) {
+        const uint32_t os_tiles = (uint32_t)((n + OS_TILE - 1) / OS_TILE);
+        uint32_t *status = scratch, *ghist = scratch + 8ull * os_tiles * 256, *counters = ghist + 8 * 256;
+        // one clear for the look-back status of all eight passes, the histograms and the tile counters
+        CUDA_TRY(cudaMemsetAsync(scratch, 0, (8ull * os_tiles * 256 + 8 * 256 + 8) * sizeof(uint32_t), st));
         k_os_histogram<<<(unsigned)std::min<uint64_t>((n + 4095) / 4096, 148 * 8), 256, 0, st>>>(keys, n, ghist);
         k_os_scan_hist<<<8, 256, 0, st>>>(ghist);
         for (int pass = 0; pass < 8; ++pass) {
-            CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)ntiles * 256 * sizeof(uint32_t), st));
-            k_os_pass<<<ntiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, pass * 8, ghist + pass * 256, status, counters + pass);
+            k_os_pass<<<os_tiles, OS_THREADS, 0, st>>>(kin, vin, kout, vout, n, pass * 8, ghist + pass * 256,
+                                                       status + (uint64_t)pass * os_tiles * 256, counters + pass);
             uint64_t *tk = kin; kin = kout; kout = tk;
             uint32_t *tv = vin; vin = vout; vout = tv;
         }
@@ -622,23 +702,18 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     k_init_bounds<<<1, 32, 0, st>>>(A.bounds_ord);
     k_scene_bounds<<<min(gN, 148u * 8u), B, 0, st>>>(A.verts, A.idx, n, A.bounds_ord);
     k_finalize_bounds<<<1, 32, 0, st>>>(A.bounds_ord, A.params);
-    k_morton<<<gN, B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order);
+    k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order);
+    k_decide_quant<<<1, 1, 0, st>>>(A.params, (float)n);
     CUDA_TRY(cudaGetLastError());
     if (A.ev_sort0) CUDA_TRY(cudaEventRecord(A.ev_sort0, st));
     if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st)) return 1;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
-    k_emit_leaves<<<gN, B, 0, st>>>(A.verts, A.idx, (int64_t)n, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris);
-    k_decide_quant<<<1, 1, 0, st>>>(A.params, (float)n);
     CUDA_TRY(cudaMemsetAsync(A.counters, 0, 3 * sizeof(unsigned long long), st));
-    if (n == 1) {
-        k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);
-    } else {
-        const unsigned gI = (unsigned)((n - 1 + B - 1) / B);
-        CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(uint32_t), st));
-        k_karras<<<gI, B, 0, st>>>(A.keys, (int64_t)n, A.bnodes, A.parent, A.range);
-        k_refit<<<gN, B, 0, st>>>((int64_t)n, A.bnodes, A.parent, A.flags, A.counters);
-        k_emit_tnodes<<<gI, B, 0, st>>>((int64_t)n, A.bnodes, A.range, A.tnodes, A.qnodes, A.params, A.counters, A.leaf_max);
-    }
+    if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
+    k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(
+        A.verts, A.idx, (int64_t)n, A.keys, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
+        A.tnodes, A.qnodes, A.counters, A.leaf_max);
+    if (n == 1) k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
