@@ -215,8 +215,12 @@ int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
  * any may be NULL).  keys[T] uint64 sorted Morton keys; order[T] sorted
  * position -> input triangle; nodes[(2T-1) x 8] float32/int32 words of the
  * 32-byte binary nodes (lo.xyz,left,hi.xyz,right; internal 0..T-2, leaves
- * after). */
+ * after).  The builder only materialises the complete binary node array when
+ * qsmrt_debug_set_keep_binary_nodes(1) was in force at the commit (the product
+ * path writes the traversal nodes straight from registers); asking for `nodes`
+ * otherwise is an error. */
 int qsmrt_debug_get_build(qsmrt_scene *scene, uint64_t *keys, uint32_t *order, void *nodes);
+int qsmrt_debug_set_keep_binary_nodes(int keep);
 
 /* Tuning hook for A/B measurements: 1 = one independent loop per thread (the
  * first kernel, kept as the simple reference), 2 = the persistent warp-uniform

@@ -8,7 +8,7 @@ struct BuildParams {        // device-resident; filled by the bounds kernels
     float pad;              // absolute AABB padding
     float glo[3], cell[3], inv_cell[3];   // 16-bit quantisation grid of the 32-byte nodes
     float leaf_diag_sum;    // sum of leaf box diagonals (mean leaf size decides whether the grid is fine enough)
-    int   use_q;            // decided on the device after the leaves are emitted: write / read the 32-byte nodes
+    int   use_q;            // decided on the device (k_hierarchy_refit_emit): write / read the 32-byte nodes
 };
 
 struct LbvhBuildArgs {
@@ -24,7 +24,8 @@ struct LbvhBuildArgs {
     uint64_t   *keys, *keys_tmp;    // [T]
     uint32_t   *order, *order_tmp;  // [T]
     uint32_t   *sort_scratch;       // lbvh_sort_scratch_bytes(T)
-    BNode      *bnodes;             // [2T-1]
+    BNode      *bnodes;             // [2T-1] hand-over boxes of the global phase; the complete binary tree iff keep_bnodes
+    int         keep_bnodes;
     unsigned long long *flags;      // [T-1] hand-over slot of each split (k_hierarchy_refit_emit)
     TriRec     *tris;               // [T]
     TNode      *tnodes;             // [max(T-1,1)]

@@ -138,13 +138,6 @@ k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint
     }
 }
 
-// The 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf.
-__global__ void k_decide_quant(BuildParams *bp, float ntris)
-{
-    const float max_cell = fmaxf(bp->cell[0], fmaxf(bp->cell[1], bp->cell[2]));
-    bp->use_q = 6.0f * max_cell <= 0.15f * (bp->leaf_diag_sum / ntris) ? 1 : 0;
-}
-
 // ------------------------------------------------------------ radix sort
 // LSD, 8-bit digits, stable.  Per pass: per-tile digit histogram -> per-digit
 // exclusive scan over tiles -> ranked scatter (warp match_any multi-split).
@@ -305,33 +298,17 @@ k_os_histogram(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restri
     for (int i = threadIdx.x; i < 8 * 256; i += 256) { uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
 }
 
-// exclusive scan of each 256-bin histogram in place (one block per pass)
-__global__ void __launch_bounds__(256)
-k_os_scan_hist(uint32_t *__restrict__ ghist)
-{
-    __shared__ uint32_t wsum[8];
-    uint32_t *row = ghist + blockIdx.x * 256;
-    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t v = row[threadIdx.x], x = v;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (l >= o) x += y; }
-    if (l == 31) wsum[w] = x;
-    __syncthreads();
-    uint32_t off = 0;
-    for (int k = 0; k < w; ++k) off += wsum[k];
-    row[threadIdx.x] = off + x - v;
-}
-
 __global__ void __launch_bounds__(OS_THREADS, 4)
 k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
           uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n, int shift,
-          const uint32_t *__restrict__ gbase /* [256] digit starts of this pass */,
+          const uint32_t *__restrict__ ghist /* [256] digit histogram of this pass over all keys */,
           uint32_t *status /* [ntiles][256], zeroed */, uint32_t *tile_counter)
 {
     __shared__ uint64_t skey[OS_TILE];
     __shared__ uint32_t sval[OS_TILE];
     __shared__ uint32_t wcnt[OS_WARPS][256];     // per-warp digit counts, then exclusive offsets inside the tile
     __shared__ uint32_t gofs[256];               // global address of the digit's first key of this tile - its tile offset
-    __shared__ uint32_t wsum[OS_WARPS];
+    __shared__ uint32_t wsum[OS_WARPS], gsum[OS_WARPS];
     __shared__ uint32_t s_tile;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
@@ -375,14 +352,21 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
         volatile uint32_t *st = status;
         st[(uint64_t)tile * 256 + d] = (tile == 0 ? OS_INC : OS_AGG) | run;
         // exclusive scan of the tile's digit counts -> where each digit starts in the staged tile
-        uint32_t x = run;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (l >= o) x += y; }
-        if (l == 31) wsum[w] = x;
+        // ... and, with the same shuffles, of the pass' global digit histogram -> where each digit starts in the output
+        const uint32_t gcount = ghist[d];
+        uint32_t x = run, gx = gcount;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o), gy = __shfl_up_sync(0xFFFFFFFFu, gx, o);
+            if (l >= o) { x += y; gx += gy; }
+        }
+        if (l == 31) { wsum[w] = x; gsum[w] = gx; }
         __syncthreads();
-        uint32_t tstart = x - run;
-        for (int k = 0; k < w; ++k) tstart += wsum[k];
+        uint32_t tstart = x - run, gstart = gx - gcount;
+        for (int k = 0; k < w; ++k) { tstart += wsum[k]; gstart += gsum[k]; }
 #pragma unroll
         for (int k = 0; k < OS_WARPS; ++k) wcnt[k][d] += tstart;
+        // decoupled look-back.  (Reading several predecessors per round trip and fetching the values before the
+        // look-back were both measured and are slower: 0.33-0.39 ms against 0.28 ms for the sort of 2M keys.)
         uint32_t excl = 0;
         for (int64_t k = (int64_t)tile - 1; k >= 0; --k) {
             uint32_t sv;
@@ -391,7 +375,7 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
             if ((sv >> 30) == 2u) break;
         }
         if (tile != 0) st[(uint64_t)tile * 256 + d] = OS_INC | (excl + run);
-        gofs[d] = gbase[d] + excl - tstart;
+        gofs[d] = gstart + excl - tstart;
     }
     __syncthreads();
     // stage: keys (and their values, read now) to their place in the digit-sorted tile
@@ -469,61 +453,120 @@ __device__ __forceinline__ QNode quantise_node(const TNode &o, const BuildParams
 //   * warp phase: while the sibling subtree is held by a lane of the same warp (the lane of its first leaf), the
 //     left lane takes the sibling's box, far end and far delta with shuffles -- no loads, atomics or fences
 //     (about 5 of 6 internal nodes end here);
+//   * block phase: a parent whose whole leaf range lies inside this block's RF_BLOCK leaves is joined through
+//     shared memory (one 32-bit exchange on the split's slot, the first arrival's box parked beside it).  Whether
+//     the range stays inside the block is a property of the PARENT that both children evaluate alike: the parent
+//     of split s ends at the first delta below delta(s, s+1) on either side, so a prefix / suffix minimum of the
+//     block's deltas answers it in O(1).  With 512 leaves per block ~98 % of all nodes finish in the two phases;
 //   * global phase: a 64-bit exchange on the split's flag hands the first arrival's far end, far delta and
 //     height to the second, which reads the sibling's box (one 32-byte read from L2) and goes on;
-//   * output: the merging thread holds both child boxes, so it writes the binary node, the 64-byte traversal
-//     node and (when the scene uses them) its 32-byte quantised twin.  Subtrees of <= leaf_max triangles
-//     collapse into leaves: such a node is never referenced and its traversal node is not written.
+//   * output: the merging threads are few and scattered (3 of 32 lanes in the warp phase, 1-2 later; ncu: 70 % of
+//     the kernel's instructions ran at <= 4 lanes when they wrote the nodes themselves), so a merge only parks
+//     both child boxes in the shared-memory slot of the node's index; after the last phase every thread writes
+//     the node whose index is its own leaf number: the 64-byte traversal node and (when the scene uses them) its
+//     32-byte quantised twin.  Subtrees of <= leaf_max triangles collapse into leaves: such a node is never
+//     referenced and not written.  The binary nodes (BNode) are only the hand-over medium of the global phase:
+//     a thread stores its subtree's box right before the exchange, unless keep_bn asks for the complete array
+//     (qsmrt_debug_get_build, the builder-vs-oracle test).
 struct RefitOut {
-    BNode *bn; TNode *tn; QNode *qn; const BuildParams *bp; unsigned long long *counters;
-    int64_t n; int leaf_max; bool use_q;
+    BNode *bn; TNode *tn; QNode *qn; const BuildParams *bp;
+    int64_t n; int leaf_max; bool use_q, keep_bn;
 };
 
-// Write node `id` = [l .. g | g+1 .. r] with child boxes (llo, lhi) and (rlo, rhi); returns its box in mlo / mhi.
-__device__ __forceinline__ void refit_write(const RefitOut &R, int32_t id, int l, int g, int r,
-                                            const float4 llo, const float4 lhi, const float4 rlo, const float4 rhi,
-                                            float4 &mlo, float4 &mhi, unsigned &n_nodes, unsigned &n_leafrefs)
+constexpr int RF_BLOCK = 256;
+constexpr int RF_WARPS = RF_BLOCK / 32;
+constexpr int RF_BIG = 1 << 20;          // "no delta here" for the minima (deltas are -1 .. 96)
+
+// A finished merge [l .. g | g+1 .. r] -> node `id`, waiting for the dense output pass at the end of the kernel:
+// slot id - (first leaf of the block), structure of arrays so that the pass reads without bank conflicts.
+struct RefitQueue {
+    float (*f)[RF_BLOCK];       // [12] child boxes: left lo xyz, left hi xyz, right lo xyz, right hi xyz
+    int   (*i)[RF_BLOCK];       // [3]  l, g (-1: empty slot), r
+    int   first, last;          // leaves of this block
+};
+
+// 64-byte traversal node + quantised twin of node `id` = [l .. g | g+1 .. r]
+__device__ __forceinline__ void emit_node(const RefitOut &R, int32_t id, int l, int g, int r,
+                                          const float4 llo, const float4 lhi, const float4 rlo, const float4 rhi,
+                                          unsigned &n_nodes, unsigned &n_leafrefs)
 {
     const int32_t left = l == g ? (int32_t)(R.n - 1) + g : g;
     const int32_t right = g + 1 == r ? (int32_t)(R.n - 1) + g + 1 : g + 1;
-    if (id == 0 || r - l + 1 > R.leaf_max) {
-        const int cl = g - l + 1, cr = r - g;
-        const int r0 = cl <= R.leaf_max ? ~(int)(((uint32_t)l << 2) | (uint32_t)(cl - 1)) : left;
-        const int r1 = cr <= R.leaf_max ? ~(int)(((uint32_t)(g + 1) << 2) | (uint32_t)(cr - 1)) : right;
-        TNode o;
-        o.a = make_float4(llo.x, lhi.x, llo.y, lhi.y);
-        o.b = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
-        o.c = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
-        o.d = make_int4(r0, r1, 0, 0);
-        R.tn[id] = o;
-        if (R.use_q) R.qn[id] = quantise_node(o, R.bp);
-        ++n_nodes; n_leafrefs += (r0 < 0) + (r1 < 0);
-    }
-    mlo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), __int_as_float(left));
-    mhi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), __int_as_float(right));
-    reinterpret_cast<float4 *>(&R.bn[id])[0] = mlo;
-    reinterpret_cast<float4 *>(&R.bn[id])[1] = mhi;
+    const int cl = g - l + 1, cr = r - g;
+    const int r0 = cl <= R.leaf_max ? ~(int)(((uint32_t)l << 2) | (uint32_t)(cl - 1)) : left;
+    const int r1 = cr <= R.leaf_max ? ~(int)(((uint32_t)(g + 1) << 2) | (uint32_t)(cr - 1)) : right;
+    TNode o;
+    o.a = make_float4(llo.x, lhi.x, llo.y, lhi.y);
+    o.b = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
+    o.c = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
+    o.d = make_int4(r0, r1, 0, 0);
+    R.tn[id] = o;
+    if (R.use_q) R.qn[id] = quantise_node(o, R.bp);
+    ++n_nodes; n_leafrefs += (r0 < 0) + (r1 < 0);
 }
 
-constexpr int RF_BLOCK = 128;
+// Record the merge that made node `id` = [l .. g | g+1 .. r] out of the child boxes (llo, lhi) and (rlo, rhi);
+// returns the node's box in mlo / mhi.  The merging threads are few and scattered over their warps, so they only
+// park the operands; the node records are computed and stored by all threads together at the end of the kernel.
+__device__ __forceinline__ void refit_merge(const RefitOut &R, const RefitQueue &Q, int32_t id, int l, int g, int r,
+                                            const float4 llo, const float4 lhi, const float4 rlo, const float4 rhi,
+                                            float4 &mlo, float4 &mhi, unsigned &n_nodes, unsigned &n_leafrefs)
+{
+    if (id == 0 || r - l + 1 > R.leaf_max) {        // smaller subtrees collapse into a leaf: never referenced
+        if (id >= Q.first && id <= Q.last) {
+            const int k = id - Q.first;
+            Q.f[0][k] = llo.x; Q.f[1][k] = llo.y; Q.f[2][k] = llo.z; Q.f[3][k] = lhi.x; Q.f[4][k] = lhi.y; Q.f[5][k] = lhi.z;
+            Q.f[6][k] = rlo.x; Q.f[7][k] = rlo.y; Q.f[8][k] = rlo.z; Q.f[9][k] = rhi.x; Q.f[10][k] = rhi.y; Q.f[11][k] = rhi.z;
+            Q.i[0][k] = l; Q.i[1][k] = g; Q.i[2][k] = r;
+        } else {
+            emit_node(R, id, l, g, r, llo, lhi, rlo, rhi, n_nodes, n_leafrefs);     // a node numbered in another block
+        }
+    }
+    mlo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+    mhi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+    if (R.keep_bn) {
+        mlo.w = __int_as_float(l == g ? (int32_t)(R.n - 1) + g : g);
+        mhi.w = __int_as_float(g + 1 == r ? (int32_t)(R.n - 1) + g + 1 : g + 1);
+        reinterpret_cast<float4 *>(&R.bn[id])[0] = mlo;
+        reinterpret_cast<float4 *>(&R.bn[id])[1] = mhi;
+    }
+}
 
 __global__ void __launch_bounds__(RF_BLOCK)
 k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restrict__ idx, int64_t n,
                        const uint64_t *__restrict__ keys, const uint32_t *__restrict__ order,
                        const uint64_t *__restrict__ goff, uint32_t ngeoms,
-                       const BuildParams *__restrict__ bp, BNode *bn, TriRec *__restrict__ tris,
+                       BuildParams *bp, BNode *bn, TriRec *__restrict__ tris,
                        unsigned long long *flags, TNode *__restrict__ tn, QNode *__restrict__ qn,
-                       unsigned long long *counters, int leaf_max)
+                       unsigned long long *counters, int leaf_max, int keep_bn)
 {
+    // block phase state: slot k belongs to the split between leaves b0 + k and b0 + k + 1
+    __shared__ uint32_t s_flag[RF_BLOCK];
+    __shared__ float s_box[2][RF_BLOCK][6];       // [0]: box parked by the left child of the split, [1]: by the right child
+    __shared__ int s_pmin[RF_BLOCK], s_smin[RF_BLOCK];
+    __shared__ int s_wp[RF_WARPS], s_ws[RF_WARPS];
+    __shared__ float s_qf[12][RF_BLOCK];
+    __shared__ int s_qi[3][RF_BLOCK];
+
     const unsigned FULL = 0xFFFFFFFFu;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int64_t b0 = blockIdx.x * (int64_t)RF_BLOCK;
+    const int64_t i = b0 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w0 = (int)(i - lane);               // first leaf of this warp
+    const int bfirst = (int)b0, blast = (int)min(b0 + RF_BLOCK, n) - 1;      // this block's leaves
     unsigned n_nodes = 0, n_leafrefs = 0;
-    RefitOut R{ bn, tn, qn, bp, counters, n, leaf_max, bp->use_q != 0 };
-    float4 mlo = make_float4(0.f, 0.f, 0.f, 0.f), mhi = mlo;      // box of the subtree I hold, as the binary node stores it
+    // The 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf
+    // (mean leaf diagonal from k_morton).  Every thread evaluates the same expression; thread 0 records it.
+    const float max_cell = fmaxf(bp->cell[0], fmaxf(bp->cell[1], bp->cell[2]));
+    const bool use_q = 6.0f * max_cell <= 0.15f * (bp->leaf_diag_sum / (float)n);
+    if (i == 0) bp->use_q = use_q ? 1 : 0;
+    const RefitOut R{ bn, tn, qn, bp, n, leaf_max, use_q, keep_bn != 0 };
+    const RefitQueue Q{ s_qf, s_qi, bfirst, blast };
+    float4 mlo = make_float4(0.f, 0.f, 0.f, 0.f), mhi = mlo;      // box of the subtree I hold
     int l = 0, r = 0, dl = -1, dr = -1;
     bool holding = false;                         // I carry a finished subtree nobody has merged yet
+    s_qi[1][threadIdx.x] = -1;
+    s_flag[threadIdx.x] = 0u;
     if (i < n) {
         const uint64_t t = order[i];
         const uint64_t k = keys[i];
@@ -540,9 +583,11 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
         mhi.x = __fadd_rn(fmaxf(p0[0], fmaxf(p1[0], p2[0])), pad);
         mhi.y = __fadd_rn(fmaxf(p0[1], fmaxf(p1[1], p2[1])), pad);
         mhi.z = __fadd_rn(fmaxf(p0[2], fmaxf(p1[2], p2[2])), pad);
-        mlo.w = __int_as_float(-1); mhi.w = __int_as_float(-1);
-        float4 *leaf = reinterpret_cast<float4 *>(&bn[n - 1 + i]);
-        leaf[0] = mlo; leaf[1] = mhi;
+        if (keep_bn) {
+            mlo.w = __int_as_float(-1); mhi.w = __int_as_float(-1);
+            float4 *leaf = reinterpret_cast<float4 *>(&bn[n - 1 + i]);
+            leaf[0] = mlo; leaf[1] = mhi;
+        }
         uint32_t g = ngeoms > 1 ? geom_of(goff, ngeoms, t) : 0u;
         uint32_t prim = (uint32_t)(t - goff[g]);
         TriRec rec;
@@ -554,6 +599,25 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
         holding = n > 1;
     }
     uint32_t h = 0;                               // height of the subtree I hold (leaf = 0)
+
+    // ---- block-wide minima of the deltas: s_pmin[k] = min delta(j, j+1) over j = b0-1 .. b0-1+k,
+    //      s_smin[k] = min over j = b0+k .. last leaf of the block (threads past the end contribute nothing)
+    {
+        int pm = i < n ? dl : RF_BIG, sm = i < n ? dr : RF_BIG;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(FULL, pm, o), b = __shfl_down_sync(FULL, sm, o);
+            if (lane >= o) pm = min(pm, a);
+            if (lane + o < 32) sm = min(sm, b);
+        }
+        if (lane == 31) s_wp[warp] = pm;
+        if (lane == 0) s_ws[warp] = sm;
+        __syncthreads();
+        for (int k = 0; k < warp; ++k) pm = min(pm, s_wp[k]);
+        for (int k = warp + 1; k < RF_WARPS; ++k) sm = min(sm, s_ws[k]);
+        s_pmin[threadIdx.x] = pm; s_smin[threadIdx.x] = sm;
+        __syncthreads();
+    }
 
     // ---- warp phase: I am a left child (dr > dl) and the lane of leaf r+1 holds my finished right sibling
     for (;;) {
@@ -575,19 +639,55 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
             const int g = r;
             r = p_r; dr = p_dr;
             h = max(h, p_h) + 1u;
-            const int32_t id = (l == 0 && r == (int)(n - 1)) ? 0 : (dr > dl ? r : l);
-            if (id == 0 && l == 0 && r == (int)(n - 1)) counters[2] = h;      // tree height (edges from the root to the deepest leaf)
-            refit_write(R, id, l, g, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
-            if (l == 0 && r == (int)(n - 1)) holding = false;                 // the root: done
+            const bool root = l == 0 && r == (int)(n - 1);
+            const int32_t id = root ? 0 : (dr > dl ? r : l);
+            if (root) { counters[2] = h; holding = false; }      // tree height (edges from the root to the deepest leaf)
+            refit_merge(R, Q, id, l, g, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
         }
         if ((consumed >> lane) & 1u) holding = false;
         if (consumed == 0u) break;
     }
 
-    // ---- global phase: the sibling is finished by a thread of another warp
+    // ---- block phase: the parent's whole range lies inside this block -> join through shared memory
     while (holding) {
         const bool go_right = dr > dl;
         const int s = go_right ? r : l - 1;       // the parent's split lies between leaves s and s + 1
+        // parent = [l .. first delta below dr right of r] or [first delta below dl left of l .. r]
+        const bool local = l >= bfirst && r <= blast &&
+                           (go_right ? (r < blast && s_smin[r + 1 - bfirst] < dr) : (l > bfirst && s_pmin[l - 1 - bfirst] < dl));
+        if (!local) break;
+        const int k = s - bfirst;
+        float *mine_box = s_box[go_right ? 0 : 1][k];
+        mine_box[0] = mlo.x; mine_box[1] = mlo.y; mine_box[2] = mlo.z; mine_box[3] = mhi.x; mine_box[4] = mhi.y; mine_box[5] = mhi.z;
+        // far end (relative, +1 so the word is never 0), height, far delta + 1
+        const uint32_t mine = (uint32_t)((go_right ? l : r) - bfirst + 1) | (h << 11) | ((uint32_t)((go_right ? dl : dr) + 1) << 19);
+        __threadfence_block();
+        const uint32_t other = atomicExch(&s_flag[k], mine);
+        if (other == 0u) { holding = false; break; }      // first to arrive: the sibling's thread takes over
+        __threadfence_block();
+        const volatile float *ob = s_box[go_right ? 1 : 0][k];
+        float4 slo, shi;
+        slo.x = ob[0]; slo.y = ob[1]; slo.z = ob[2]; shi.x = ob[3]; shi.y = ob[4]; shi.z = ob[5];
+        const int o_end = (int)(other & 0x7FFu) - 1 + bfirst;
+        const uint32_t o_h = (other >> 11) & 0xFFu;
+        const int o_d = (int)((other >> 19) & 0xFFu) - 1;
+        h = max(h, o_h) + 1u;
+        if (go_right) { r = o_end; dr = o_d; } else { l = o_end; dl = o_d; }
+        const bool root = l == 0 && r == (int)(n - 1);
+        const int32_t id = root ? 0 : (dr > dl ? r : l);
+        if (root) { counters[2] = h; holding = false; }
+        if (go_right) refit_merge(R, Q, id, l, s, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
+        else          refit_merge(R, Q, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
+    }
+
+    // ---- global phase: the sibling is finished by a thread of another block
+    while (holding) {
+        const bool go_right = dr > dl;
+        const int s = go_right ? r : l - 1;
+        if (!keep_bn) {     // park my box where the sibling's thread will look for it
+            float4 *me = reinterpret_cast<float4 *>(&bn[l == r ? (int)(n - 1) + l : (go_right ? r : l)]);
+            me[0] = mlo; me[1] = mhi;
+        }
         // What the second arrival needs from the first: its far end, the delta beyond it and its height.
         // Release exchange (MEMBAR.ALL + ATOMG): my binary node is in L2 before the flag.  __threadfence() would
         // be MEMBAR.SC plus an L1 invalidate (CCTL.IVALL) per level, which the __ldcg sibling read does not need.
@@ -609,9 +709,20 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
         const bool root = l == 0 && r == (int)(n - 1);
         const int32_t id = root ? 0 : (dr > dl ? r : l);
         if (root) counters[2] = h;
-        if (go_right) refit_write(R, id, l, s, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
-        else          refit_write(R, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
+        if (go_right) refit_merge(R, Q, id, l, s, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
+        else          refit_merge(R, Q, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
         if (root) break;
+    }
+
+    // ---- output: every parked merge of this block, one node per thread
+    __syncthreads();
+    {
+        const int k = threadIdx.x, g = s_qi[1][k];
+        if (g >= 0) {
+            const float4 llo = make_float4(s_qf[0][k], s_qf[1][k], s_qf[2][k], 0.0f), lhi = make_float4(s_qf[3][k], s_qf[4][k], s_qf[5][k], 0.0f);
+            const float4 rlo = make_float4(s_qf[6][k], s_qf[7][k], s_qf[8][k], 0.0f), rhi = make_float4(s_qf[9][k], s_qf[10][k], s_qf[11][k], 0.0f);
+            emit_node(R, (int32_t)i, s_qi[0][k], g, s_qi[2][k], llo, lhi, rlo, rhi, n_nodes, n_leafrefs);
+        }
     }
     // statistics: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
@@ -672,7 +783,6 @@ int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t
         // one clear for the look-back status of all eight passes, the histograms and the tile counters
         CUDA_TRY(cudaMemsetAsync(scratch, 0, (8ull * os_tiles * 256 + 8 * 256 + 8) * sizeof(uint32_t), st));
         k_os_histogram<<<(unsigned)std::min<uint64_t>((n + 4095) / 4096, 148 * 8), 256, 0, st>>>(keys, n, ghist);
-        k_os_scan_hist<<<8, 256, 0, st>>>(ghist);
         for (int pass = 0; pass < 8; ++pass) {
             k_os_pass<<<os_tiles, OS_THREADS, 0, st>>>(kin, vin, kout, vout, n, pass * 8, ghist + pass * 256,
                                                        status + (uint64_t)pass * os_tiles * 256, counters + pass);
@@ -703,7 +813,6 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     k_scene_bounds<<<min(gN, 148u * 8u), B, 0, st>>>(A.verts, A.idx, n, A.bounds_ord);
     k_finalize_bounds<<<1, 32, 0, st>>>(A.bounds_ord, A.params);
     k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order);
-    k_decide_quant<<<1, 1, 0, st>>>(A.params, (float)n);
     CUDA_TRY(cudaGetLastError());
     if (A.ev_sort0) CUDA_TRY(cudaEventRecord(A.ev_sort0, st));
     if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st)) return 1;
@@ -712,7 +821,7 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
     k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(
         A.verts, A.idx, (int64_t)n, A.keys, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
-        A.tnodes, A.qnodes, A.counters, A.leaf_max);
+        A.tnodes, A.qnodes, A.counters, A.leaf_max, (A.keep_bnodes || n == 1) ? 1 : 0);
     if (n == 1) k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -18,6 +18,7 @@
 
 static thread_local char g_err[512] = "";
 static int g_allow_qnodes = 1;              // qsmrt_debug_set_quantised_nodes
+static bool g_keep_bnodes = false;          // qsmrt_debug_set_keep_binary_nodes
 static int g_leaf_max = 2;                  // triangles per leaf (qsmrt_debug_set_leaf_max); 2 measured best on C2
 
 void qsmrt_set_error(const char *fmt, ...)
@@ -253,7 +254,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
     A.verts = s->verts; A.idx = s->idx; A.ntris = T; A.geom_offsets = s->goff; A.ngeoms = G;
     A.bounds_ord = bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = keys_tmp;
     A.order = s->order; A.order_tmp = order_tmp; A.sort_scratch = sort_scratch;
-    A.bnodes = s->bnodes; A.flags = flags;
+    A.bnodes = s->bnodes; A.flags = flags; A.keep_bnodes = g_keep_bnodes ? 1 : 0;
     A.qnodes = s->qnodes;
     A.tris = s->tris; A.tnodes = s->tnodes; A.counters = counters; A.ev_sort0 = es0; A.ev_sort1 = es1;
     int rc = lbvh_build(A, st);
@@ -270,6 +271,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];
         s->use_qnodes = bp.use_q != 0;                      // decided on the device (k_decide_quant)
         if (!s->use_qnodes) dfree(s->qnodes);
+        if (!g_keep_bnodes) dfree(s->bnodes);               // only the hand-over boxes of the build were in it
         for (int a = 0; a < 3; ++a) { s->glo[a] = bp.glo[a]; s->cell[a] = bp.cell[a]; }
         s->stats.quantised_nodes = s->use_qnodes ? 1u : 0u;
         s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + T * sizeof(TriRec);
@@ -479,6 +481,12 @@ int qsmrt_debug_set_sort(int variant)
 {
     if (variant != 0 && variant != 1) FAIL("sort variant must be 0 (classic) or 1 (onesweep)");
     g_sort_variant = variant;
+    return 0;
+}
+
+int qsmrt_debug_set_keep_binary_nodes(int keep)
+{
+    g_keep_bnodes = keep != 0;
     return 0;
 }
 
@@ -771,6 +779,7 @@ int qsmrt_debug_get_build(qsmrt_scene *s, uint64_t *keys, uint32_t *order, void 
     if (T == 0) return 0;
     if (keys) CUDA_TRY(cudaMemcpy(keys, s->keys, T * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (order) CUDA_TRY(cudaMemcpy(order, s->order, T * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (nodes && !s->bnodes) FAIL("binary nodes were not kept: call qsmrt_debug_set_keep_binary_nodes(1) before the commit");
     if (nodes) CUDA_TRY(cudaMemcpy(nodes, s->bnodes, (2 * T - 1) * sizeof(BNode), cudaMemcpyDeviceToHost));
     return 0;
 }

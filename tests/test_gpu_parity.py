@@ -136,7 +136,16 @@ def test_builder_matches_oracle(c1):
     refit boxes are bit-identical to the oracle's canonical LBVH."""
     import ctypes as C
     from pyqsm_b200 import _lib
-    v, t, o, g = c1
+    from pyqsm_b200 import RaycastingScene
+    v, t, o, _ = c1
+    L = _lib.load()
+    _lib.check(L.qsmrt_debug_set_keep_binary_nodes(1))       # the product build keeps no binary node array
+    try:
+        g = RaycastingScene()
+        g.add_triangles(v, t)
+        g.commit()
+    finally:
+        _lib.check(L.qsmrt_debug_set_keep_binary_nodes(0))
     n = t.shape[0]
     keys = np.empty(n, np.uint64)
     order = np.empty(n, np.uint32)
