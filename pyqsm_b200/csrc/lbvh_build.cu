@@ -532,13 +532,60 @@ __device__ __forceinline__ void refit_merge(const RefitOut &R, const RefitQueue 
     }
 }
 
+// Global phase of the hierarchy: climb from the finished subtree [l, r] while its sibling has already arrived.
+// A 64-bit exchange on the split's flag hands the first arrival's far end, far delta and height to the second,
+// which reads the sibling's box (one 32-byte read from L2), records the parent and goes on; the first arrival
+// stops.  Nobody ever waits, so the order in which subtrees are processed does not matter.
+struct ClimbItem { int4 a; float4 b, c; };       // l, r, dl, dr | box lo, height | box hi
+
+__device__ __forceinline__ void global_climb(const RefitOut &R, const RefitQueue &Q, unsigned long long *flags,
+                                             unsigned long long *counters, int l, int r, int dl, int dr, uint32_t h,
+                                             float4 mlo, float4 mhi, unsigned &n_nodes, unsigned &n_leafrefs)
+{
+    const int64_t n = R.n;
+    BNode *bn = R.bn;
+    const bool keep_bn = R.keep_bn;
+    for (;;) {
+        const bool go_right = dr > dl;
+        const int s = go_right ? r : l - 1;
+        if (!keep_bn) {     // park my box where the sibling's thread will look for it
+            float4 *me = reinterpret_cast<float4 *>(&bn[l == r ? (int)(n - 1) + l : (go_right ? r : l)]);
+            me[0] = mlo; me[1] = mhi;
+        }
+        // Release exchange (MEMBAR.ALL + ATOMG): my binary node is in L2 before the flag.  __threadfence() would
+        // be MEMBAR.SC plus an L1 invalidate (CCTL.IVALL) per level, which the __ldcg sibling read does not need.
+        const unsigned long long mine = (unsigned long long)(uint32_t)((go_right ? l : r) + 1)
+                                      | ((unsigned long long)h << 32) | ((unsigned long long)(uint32_t)((go_right ? dl : dr) + 1) << 40);
+        unsigned long long other;
+        asm volatile("atom.release.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(other) : "l"(flags + s), "l"(mine) : "memory");
+        if (other == 0ull) break;                 // first to arrive: the sibling's thread takes over
+        const int o_end = (int)(uint32_t)(other & 0xFFFFFFFFull) - 1;
+        const uint32_t o_h = (uint32_t)(other >> 32) & 0xFFu;
+        const int o_d = (int)((other >> 40) & 0xFFu) - 1;
+        // sibling's index: a right sibling [s+1, o_end] is a right child (index = its first leaf), a left
+        // sibling [o_end, s] a left child (index = its last leaf); single leaves live at n-1+leaf
+        const int sib = go_right ? (o_end == s + 1 ? (int)(n - 1) + s + 1 : s + 1) : (o_end == s ? (int)(n - 1) + s : s);
+        const float4 *cs = reinterpret_cast<const float4 *>(&bn[sib]);
+        const float4 slo = __ldcg(cs), shi = __ldcg(cs + 1);
+        h = max(h, o_h) + 1u;
+        if (go_right) { r = o_end; dr = o_d; } else { l = o_end; dl = o_d; }
+        const bool root = l == 0 && r == (int)(n - 1);
+        const int32_t id = root ? 0 : (dr > dl ? r : l);
+        if (root) counters[2] = h;
+        if (go_right) refit_merge(R, Q, id, l, s, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
+        else          refit_merge(R, Q, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
+        if (root) break;
+    }
+}
+
 __global__ void __launch_bounds__(RF_BLOCK)
 k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restrict__ idx, int64_t n,
                        const uint64_t *__restrict__ keys, const uint32_t *__restrict__ order,
                        const uint64_t *__restrict__ goff, uint32_t ngeoms,
                        BuildParams *bp, BNode *bn, TriRec *__restrict__ tris,
                        unsigned long long *flags, TNode *__restrict__ tn, QNode *__restrict__ qn,
-                       unsigned long long *counters, int leaf_max, int keep_bn)
+                       unsigned long long *counters, int leaf_max, int keep_bn,
+                       ClimbItem *__restrict__ work, unsigned *work_count, unsigned work_cap)
 {
     // block phase state: slot k belongs to the split between leaves b0 + k and b0 + k + 1
     __shared__ uint32_t s_flag[RF_BLOCK];
@@ -680,38 +727,24 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
         else          refit_merge(R, Q, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
     }
 
-    // ---- global phase: the sibling is finished by a thread of another block
-    while (holding) {
-        const bool go_right = dr > dl;
-        const int s = go_right ? r : l - 1;
-        if (!keep_bn) {     // park my box where the sibling's thread will look for it
-            float4 *me = reinterpret_cast<float4 *>(&bn[l == r ? (int)(n - 1) + l : (go_right ? r : l)]);
-            me[0] = mlo; me[1] = mhi;
+    // ---- hand the subtrees that are still open to the climb kernel (their parents span several blocks)
+    {
+        const unsigned hm = __ballot_sync(FULL, holding);
+        unsigned base = 0;
+        if (lane == 0 && hm) base = atomicAdd(work_count, (unsigned)__popc(hm));
+        base = __shfl_sync(FULL, base, 0);
+        if (holding) {
+            const unsigned slot = base + __popc(hm & ((1u << lane) - 1u));
+            if (slot < work_cap) {
+                ClimbItem it;
+                it.a = make_int4(l, r, dl, dr);
+                it.b = make_float4(mlo.x, mlo.y, mlo.z, __uint_as_float(h));
+                it.c = make_float4(mhi.x, mhi.y, mhi.z, 0.0f);
+                work[slot] = it;
+            } else {
+                global_climb(R, Q, flags, counters, l, r, dl, dr, h, mlo, mhi, n_nodes, n_leafrefs);    // list full: climb here
+            }
         }
-        // What the second arrival needs from the first: its far end, the delta beyond it and its height.
-        // Release exchange (MEMBAR.ALL + ATOMG): my binary node is in L2 before the flag.  __threadfence() would
-        // be MEMBAR.SC plus an L1 invalidate (CCTL.IVALL) per level, which the __ldcg sibling read does not need.
-        const unsigned long long mine = (unsigned long long)(uint32_t)((go_right ? l : r) + 1)
-                                      | ((unsigned long long)h << 32) | ((unsigned long long)(uint32_t)((go_right ? dl : dr) + 1) << 40);
-        unsigned long long other;
-        asm volatile("atom.release.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(other) : "l"(flags + s), "l"(mine) : "memory");
-        if (other == 0ull) break;                 // first to arrive: the sibling's thread takes over
-        const int o_end = (int)(uint32_t)(other & 0xFFFFFFFFull) - 1;
-        const uint32_t o_h = (uint32_t)(other >> 32) & 0xFFu;
-        const int o_d = (int)((other >> 40) & 0xFFu) - 1;
-        // sibling's index: a right sibling [s+1, o_end] is a right child (index = its first leaf), a left
-        // sibling [o_end, s] a left child (index = its last leaf); single leaves live at n-1+leaf
-        const int sib = go_right ? (o_end == s + 1 ? (int)(n - 1) + s + 1 : s + 1) : (o_end == s ? (int)(n - 1) + s : s);
-        const float4 *cs = reinterpret_cast<const float4 *>(&bn[sib]);
-        const float4 slo = __ldcg(cs), shi = __ldcg(cs + 1);
-        h = max(h, o_h) + 1u;
-        if (go_right) { r = o_end; dr = o_d; } else { l = o_end; dl = o_d; }
-        const bool root = l == 0 && r == (int)(n - 1);
-        const int32_t id = root ? 0 : (dr > dl ? r : l);
-        if (root) counters[2] = h;
-        if (go_right) refit_merge(R, Q, id, l, s, r, mlo, mhi, slo, shi, mlo, mhi, n_nodes, n_leafrefs);
-        else          refit_merge(R, Q, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
-        if (root) break;
     }
 
     // ---- output: every parked merge of this block, one node per thread
@@ -730,6 +763,34 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
         n_leafrefs += __shfl_xor_sync(FULL, n_leafrefs, o);
     }
     if (lane == 0 && n_nodes) {
+        atomicAdd(&counters[0], (unsigned long long)n_nodes);
+        atomicAdd(&counters[1], (unsigned long long)n_leafrefs);
+    }
+}
+
+// The climb kernel: one open subtree per thread (grid-stride), small blocks -- a long chain towards the root holds
+// one warp, not the 256 leaves' worth of registers and shared memory it would hold inside the kernel above.
+constexpr int CL_BLOCK = 64;
+
+__global__ void __launch_bounds__(CL_BLOCK)
+k_hierarchy_climb(int64_t n, BuildParams *bp, BNode *bn, unsigned long long *flags, TNode *__restrict__ tn,
+                  QNode *__restrict__ qn, unsigned long long *counters, int leaf_max, int keep_bn,
+                  const ClimbItem *__restrict__ work, const unsigned *__restrict__ work_count, unsigned work_cap)
+{
+    const RefitOut R{ bn, tn, qn, bp, n, leaf_max, bp->use_q != 0, keep_bn != 0 };
+    const RefitQueue Q{ nullptr, nullptr, 0, -1 };          // no parking here: nodes are written as they are made
+    const unsigned count = min(*work_count, work_cap);
+    unsigned n_nodes = 0, n_leafrefs = 0;
+    for (unsigned w = blockIdx.x * CL_BLOCK + threadIdx.x; w < count; w += gridDim.x * CL_BLOCK) {
+        const ClimbItem it = work[w];
+        global_climb(R, Q, flags, counters, it.a.x, it.a.y, it.a.z, it.a.w, __float_as_uint(it.b.w),
+                     it.b, it.c, n_nodes, n_leafrefs);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, o);
+        n_leafrefs += __shfl_xor_sync(0xFFFFFFFFu, n_leafrefs, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n_nodes) {
         atomicAdd(&counters[0], (unsigned long long)n_nodes);
         atomicAdd(&counters[1], (unsigned long long)n_leafrefs);
     }
@@ -766,6 +827,11 @@ size_t lbvh_sort_scratch_bytes(uint64_t n)
     uint64_t classic = ntiles * 256 + 256, onesweep = 8 * os_tiles * 256 + 8 * 256 + 8;
     return (size_t)(std::max(classic, onesweep) + 64) * sizeof(uint32_t);
 }
+
+// capacity of the list of subtrees handed from k_hierarchy_refit_emit to k_hierarchy_climb (48-byte items); typically
+// ~n/40 are needed, a full list only means the rest climbs inside the first kernel
+size_t lbvh_climb_items(uint64_t n) { return (size_t)(n / 4 + 1024); }
+size_t lbvh_climb_bytes(uint64_t n) { return lbvh_climb_items(n) * sizeof(ClimbItem); }
 
 int g_sort_min_onesweep = 0;     // keys from which the onesweep variant is used (qsmrt_debug_set_sort)
 
@@ -817,11 +883,17 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     if (A.ev_sort0) CUDA_TRY(cudaEventRecord(A.ev_sort0, st));
     if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st)) return 1;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
-    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 3 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 4 * sizeof(unsigned long long), st));
     if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
+    const int keep = (A.keep_bnodes || n == 1) ? 1 : 0;
+    const unsigned work_cap = (unsigned)lbvh_climb_items(n);
+    unsigned *work_count = reinterpret_cast<unsigned *>(A.counters + 3);
+    ClimbItem *work = reinterpret_cast<ClimbItem *>(A.climb_work);
     k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(
         A.verts, A.idx, (int64_t)n, A.keys, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
-        A.tnodes, A.qnodes, A.counters, A.leaf_max, (A.keep_bnodes || n == 1) ? 1 : 0);
+        A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap);
+    k_hierarchy_climb<<<std::min((work_cap + CL_BLOCK - 1) / CL_BLOCK, 148u * 32u), CL_BLOCK, 0, st>>>(
+        (int64_t)n, A.params, A.bnodes, A.flags, A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap);
     if (n == 1) k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -228,12 +228,12 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
     CUDA_TRY(cudaMemcpyAsync(s->voff, voff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     // allocate everything before the timed region
     uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr, *bounds = nullptr;
-    unsigned long long *flags = nullptr, *counters = nullptr;
+    unsigned long long *flags = nullptr, *counters = nullptr; uint32_t *climb = nullptr;
     if (dmalloc(&s->keys, T) || dmalloc(&keys_tmp, T) || dmalloc(&s->order, T) || dmalloc(&order_tmp, T) ||
         dmalloc(&sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&bounds, 8) ||
         dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&flags, T) || dmalloc(&s->tris, T) ||
         dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(T - 1, 1)) ||
-        dmalloc(&counters, 3))
+        dmalloc(&counters, 4) || dmalloc(&climb, lbvh_climb_bytes(T) / sizeof(uint32_t)))
         return 1;
     if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
     else {
@@ -254,7 +254,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
     A.verts = s->verts; A.idx = s->idx; A.ntris = T; A.geom_offsets = s->goff; A.ngeoms = G;
     A.bounds_ord = bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = keys_tmp;
     A.order = s->order; A.order_tmp = order_tmp; A.sort_scratch = sort_scratch;
-    A.bnodes = s->bnodes; A.flags = flags; A.keep_bnodes = g_keep_bnodes ? 1 : 0;
+    A.bnodes = s->bnodes; A.flags = flags; A.keep_bnodes = g_keep_bnodes ? 1 : 0; A.climb_work = climb;
     A.qnodes = s->qnodes;
     A.tris = s->tris; A.tnodes = s->tnodes; A.counters = counters; A.ev_sort0 = es0; A.ev_sort1 = es1;
     int rc = lbvh_build(A, st);
@@ -284,7 +284,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         }
     }
     dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags);
-    dfree(counters);
+    dfree(counters); dfree(climb);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(es0); cudaEventDestroy(es1);
     if (rc) { s->committed = false; return 1; }
     if (build_ms_out) *build_ms_out = s->stats.build_ms;
