@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -56,47 +55,57 @@ def b_ray_for(angles):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML thread polling every ~2 ms (the region
+    is tens of milliseconds, too short for `nvidia-smi -lms`, whose start-up alone takes longer); nvidia-smi one-shot
+    as the fallback when NVML cannot be loaded."""
+    NAMES = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+             ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.sm, self.reasons, self.mx, self.h, self.nv = index, [], set(), None, None, None
+        self._stop, self._thr = threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, attr in self.NAMES:
+                    if r & getattr(nv, attr):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self.nv:
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self._thr:
+            self._stop.set()
+            self._thr.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "NVML polled every ~2 ms inside the timed region"}
         try:
-            self.proc.wait(timeout=5)
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": [], "how": "nvidia-smi one-shot after the region (NVML unavailable)"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 7:
-                continue
-            try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, p[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.path)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
 
 
 def angles_for(rank, world, nsteps):

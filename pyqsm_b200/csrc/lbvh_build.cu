@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(256)
 k_scene_bounds(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n, uint32_t *ob)
 {
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    // unrolled: the index -> vertex gathers of four triangles are in flight together (the loop is latency bound)
+#pragma unroll 4
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
         float l[3], h[3];
         tri_bounds(verts, idx, t, l, h);
@@ -108,6 +110,7 @@ k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint
     __shared__ float wsum[8];
     const float pad = bp->pad;
     float diag = 0.0f;
+#pragma unroll 2
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
         float lo[3], hi[3];
         tri_bounds(verts, idx, t, lo, hi);
@@ -281,6 +284,7 @@ constexpr uint32_t OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_MASK = (1u << 30) - 
 constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_ITEMS = 12;                         // keys per thread
+constexpr int OS_CTAS = 5;                           // resident CTAs per SM the kernel is shaped for (registers <= 51, shared <= 45.6 KB)
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;       // 3072 keys: 36 KB staged + 8 KB counters -> 4 CTAs / SM
 
 __global__ void __launch_bounds__(256)
@@ -298,7 +302,7 @@ k_os_histogram(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restri
     for (int i = threadIdx.x; i < 8 * 256; i += 256) { uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
 }
 
-__global__ void __launch_bounds__(OS_THREADS, 4)
+__global__ void __launch_bounds__(OS_THREADS, OS_CTAS)
 k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
           uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint64_t n, int shift,
           const uint32_t *__restrict__ ghist /* [256] digit histogram of this pass over all keys */,
@@ -307,7 +311,6 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
     __shared__ uint64_t skey[OS_TILE];
     __shared__ uint32_t sval[OS_TILE];
     __shared__ uint32_t wcnt[OS_WARPS][256];     // per-warp digit counts, then exclusive offsets inside the tile
-    __shared__ uint32_t gofs[256];               // global address of the digit's first key of this tile - its tile offset
     __shared__ uint32_t wsum[OS_WARPS], gsum[OS_WARPS];
     __shared__ uint32_t s_tile;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -344,6 +347,7 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
         rnk[r] = (uint16_t)(before + __popc(m & lt));
     }
     __syncthreads();
+    uint32_t gofs_d;        // global address of digit d's first key of this tile, minus its offset in the staged tile
     {   // thread d owns digit d: tile count, publish, offsets inside the tile, look back, global base
         const uint32_t d = threadIdx.x;
         uint32_t run = 0;
@@ -365,8 +369,10 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
         for (int k = 0; k < w; ++k) { tstart += wsum[k]; gstart += gsum[k]; }
 #pragma unroll
         for (int k = 0; k < OS_WARPS; ++k) wcnt[k][d] += tstart;
-        // decoupled look-back.  (Reading several predecessors per round trip and fetching the values before the
-        // look-back were both measured and are slower: 0.33-0.39 ms against 0.28 ms for the sort of 2M keys.)
+        // Decoupled look-back, one predecessor per read.  %globaltimer stamps (2M keys, one wave of 652 tiles): a tile
+        // lives ~23 us = 7 us load + ranking, 10 us here, 2.3 us staging, 2.3 us scatter.  Measured and NOT faster:
+        // 4/8/16 predecessors per round trip (volatile or relaxed.gpu reads), values fetched before the look-back,
+        // a ninth warp that publishes a shared-memory histogram early and walks back while the others rank.
         uint32_t excl = 0;
         for (int64_t k = (int64_t)tile - 1; k >= 0; --k) {
             uint32_t sv;
@@ -375,7 +381,7 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
             if ((sv >> 30) == 2u) break;
         }
         if (tile != 0) st[(uint64_t)tile * 256 + d] = OS_INC | (excl + run);
-        gofs[d] = gstart + excl - tstart;
+        gofs_d = gstart + excl - tstart;
     }
     __syncthreads();
     // stage: keys (and their values, read now) to their place in the digit-sorted tile
@@ -389,6 +395,9 @@ k_os_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
             sval[pos] = vin[tbase + j];
         }
     }
+    __syncthreads();
+    uint32_t *const gofs = &wcnt[0][0];             // the per-warp offsets are dead: their space takes the digit bases
+    gofs[threadIdx.x] = gofs_d;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < OS_ITEMS; ++r) {
@@ -845,6 +854,8 @@ int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t
     uint32_t *vin = vals, *vout = vals_tmp;
     if (g_sort_variant == 1 && n >= (uint64_t)g_sort_min_onesweep) {
         const uint32_t os_tiles = (uint32_t)((n + OS_TILE - 1) / OS_TILE);
+        static const cudaError_t carve = cudaFuncSetAttribute(k_os_pass, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        (void)carve;            // OS_CTAS x 45 KB only fit with the largest shared-memory split
         uint32_t *status = scratch, *ghist = scratch + 8ull * os_tiles * 256, *counters = ghist + 8 * 256;
         // one clear for the look-back status of all eight passes, the histograms and the tile counters
         CUDA_TRY(cudaMemsetAsync(scratch, 0, (8ull * os_tiles * 256 + 8 * 256 + 8) * sizeof(uint32_t), st));
