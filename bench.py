@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+_JSON_OUT = sys.stdout
 GRID = 4000                       # 4000 x 4000 = 16M rays per angle
 N_LEAVES = 1_000_000              # 2M triangles
 WORKLOAD = "C2: canopy leaf-soup mesh 2M triangles (seed 2), 16M parallel sun rays per angle, 64-angle hemisphere sweep"
@@ -109,10 +110,17 @@ class ClockSampler:
 
 
 def angles_for(rank, world, nsteps):
+    """Solar angles of one rank.  The 8 x 8 sweep is sharded by AZIMUTH: at step s every rank casts elevation s % 8
+    at its own azimuth ((s // 8) * world + rank + s) % 8, so the ranks of a job do equal work per step (cost follows
+    the elevation: a low sun crosses more canopy) and N in {1, 2, 4, 8} ranks partition the 64 angles exactly."""
     from pyqsm_b200 import synthetic as syn
-    sweep = syn.hemisphere_sweep()
-    # stride 9 walks all 64 angles (gcd(9,64)=1) so short runs still mix elevations
-    return [sweep[((s * world + rank) * 9) % 64] for s in range(nsteps)]
+    sweep = syn.hemisphere_sweep()                      # index = elevation * 8 + azimuth
+    per = max(1, 8 // world)
+    out = []
+    for s in range(nsteps):
+        e, j = s % 8, (s // 8) % per
+        out.append(sweep[e * 8 + (j * world + rank + e) % 8])
+    return out
 
 
 # --------------------------------------------------------------- reference arm
@@ -155,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _JSON_OUT.write(json.dumps(line) + "\n"); _JSON_OUT.flush()
 
 
 # --------------------------------------------------------------------- our arm
@@ -357,12 +365,18 @@ def run_ours(args):
         "gpu_launches": 2 * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
     }
-    print(json.dumps(line), flush=True)
+    _JSON_OUT.write(json.dumps(line) + "\n"); _JSON_OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner does) are
+    # sent to stderr, the line itself is written to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -375,7 +389,7 @@ def main():
         # launched bare: re-exec under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=_JSON_OUT))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -482,7 +482,13 @@ struct RefitOut {
     int64_t n; int leaf_max; bool use_q, keep_bn;
 };
 
-constexpr int RF_BLOCK = 256;
+#ifndef QSMRT_RF_BLOCK
+#define QSMRT_RF_BLOCK 256
+#endif
+#ifndef QSMRT_RF_MINB
+#define QSMRT_RF_MINB 1
+#endif
+constexpr int RF_BLOCK = QSMRT_RF_BLOCK;      // leaves per block (A/B: make EXTRA=-DQSMRT_RF_BLOCK=128)
 constexpr int RF_WARPS = RF_BLOCK / 32;
 constexpr int RF_BIG = 1 << 20;          // "no delta here" for the minima (deltas are -1 .. 96)
 
@@ -587,7 +593,7 @@ __device__ __forceinline__ void global_climb(const RefitOut &R, const RefitQueue
     }
 }
 
-__global__ void __launch_bounds__(RF_BLOCK)
+__global__ void __launch_bounds__(RF_BLOCK, QSMRT_RF_MINB)
 k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restrict__ idx, int64_t n,
                        const uint64_t *__restrict__ keys, const uint32_t *__restrict__ order,
                        const uint64_t *__restrict__ goff, uint32_t ngeoms,
