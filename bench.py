@@ -391,6 +391,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd, stdout=_JSON_OUT))
     if args.impl == "reference":
+        # the CPU arm uses every host thread (torchrun exports OMP_NUM_THREADS=1 to its workers); set before libgomp loads
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         run_reference(args)
     else:
         run_ours(args)
