@@ -168,6 +168,64 @@ def test_builder_matches_oracle(c1):
     assert np.array_equal(np.asarray(st["scene_lo"], np.float32), lo) and np.array_equal(np.asarray(st["scene_hi"], np.float32), hi)
 
 
+def _builder_topology(RS, oracle_mod, v, t, keep):
+    """(left, right, lo, hi) of the GPU's binary tree next to the oracle's, plus a cast through the product nodes."""
+    import ctypes as C
+    from pyqsm_b200 import _lib
+    L = _lib.load()
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v, t)
+    o.commit()
+    _lib.check(L.qsmrt_debug_set_keep_binary_nodes(1 if keep else 0))
+    try:
+        g = RS()
+        g.add_triangles(v, t)
+        g.commit()
+    finally:
+        _lib.check(L.qsmrt_debug_set_keep_binary_nodes(0))
+    n = t.shape[0]
+    if keep:
+        keys, order = np.empty(n, np.uint64), np.empty(n, np.uint32)
+        nodes = np.empty((2 * n - 1, 8), np.float32)
+        _lib.check(L.qsmrt_debug_get_build(g._h, keys.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p),
+                                           nodes.ctypes.data_as(C.c_void_p)))
+        assert np.array_equal(keys, o.sorted_keys()) and np.array_equal(order, o.sorted_order())
+        if n > 1:
+            olo, ohi, oleft, oright = o.nodes()
+            ni = nodes.view(np.int32)
+            conv = lambda c: np.where(c >= n - 1, ~(c - (n - 1)), c)
+            assert np.array_equal(conv(ni[: n - 1, 3]), oleft) and np.array_equal(conv(ni[: n - 1, 7]), oright)
+            assert np.array_equal(nodes[: n - 1, 0:3], olo) and np.array_equal(nodes[: n - 1, 4:7], ohi)
+    return o, g
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 256, 257, 511, 513, 1000, 4097, 70001])
+@pytest.mark.parametrize("kind", ["random", "duplicates", "clusters"])
+def test_builder_block_boundaries_and_equal_keys(RS, oracle_mod, n, kind):
+    """The fused bottom-up builder joins subtrees through shuffles (32 leaves), shared memory (256 leaves) and
+    global flags: sizes around those boundaries, and runs of identical Morton keys (index tie-break, the deepest
+    trees), must give the oracle's top-down Karras tree bit for bit -- and the product nodes the same hits."""
+    rng = np.random.default_rng(n * 7 + len(kind))
+    if kind == "random":
+        c = rng.uniform(-3, 3, size=(n, 3))
+    elif kind == "duplicates":                       # every triangle 1..40 times: long runs of equal keys
+        c = np.repeat(rng.uniform(-3, 3, size=(n // 20 + 1, 3)), 40, axis=0)[rng.permutation((n // 20 + 1) * 40)[:n]]
+    else:                                            # a few tight clusters: deep prefixes, unbalanced tree
+        c = rng.uniform(-3, 3, size=(5, 3))[rng.integers(0, 5, n)] + rng.normal(0, 1e-4, size=(n, 3))
+    d = np.tile(np.array([[0.05, 0, 0], [0, 0.05, 0], [0, 0, 0.0]]), (n, 1, 1)) if kind == "duplicates" else rng.normal(0, 0.05, size=(n, 3, 3))
+    v = (c[:, None, :] + d).reshape(-1, 3).astype(np.float32)
+    t = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    rays = np.concatenate([syn.random_rays((-3, -3, -3), (3, 3, 3), 1500, seed=n),
+                           np.concatenate([v.reshape(n, 3, 3).mean(1)[: min(n, 500)] + np.float32([0, 0, 8.0]), np.tile([0, 0, -1.0], (min(n, 500), 1))], axis=1).astype(np.float32)])
+    for keep in (True, False):
+        o, g = _builder_topology(RS, oracle_mod, v, t, keep)
+        mode = 0 if n <= 4097 else 1
+        ref = o.cast_rays(rays, mode)
+        assert_cast_equal(g.cast_rays(rays), ref, o.edge_flags(rays, mode=mode), f"{kind}{n}")
+        assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, mode))
+        assert np.isfinite(ref["t_hit"][1500:]).sum() >= min(n, 500) // 2      # rays over the centroids
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_random_soup_vs_brute(RS, oracle_mod, seed):
     """Random triangle soups with slivers, duplicates, degenerates, shared edges, two geometries."""
