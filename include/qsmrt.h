@@ -57,6 +57,10 @@ int qsmrt_abi_version(void);
 /* rcs()  -- ray_casting.py:65,155,218,241,275,316 */
 int qsmrt_scene_create(int cuda_device, qsmrt_scene **out);
 int qsmrt_scene_destroy(qsmrt_scene *scene);
+/* Device blocks freed by commits, queries and destroyed scenes are kept (up to QSMRT_CACHE_MB megabytes per
+ * process, default 1024) and reused, because the reference builds a new scene per call and cudaMalloc / cudaFree
+ * dominated small scenes.  This hands them back to the driver (like torch.cuda.empty_cache()).  Synchronises. */
+int qsmrt_release_cached_memory(void);
 
 /* scene.add_triangles(mesh)  -- ray_casting.py:66,156,219,242,276,317.
  * Copies V x 3 float32 positions and T x 3 uint32 indices (Open3D copies

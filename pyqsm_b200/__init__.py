@@ -8,4 +8,13 @@ drivers built on top.  There is no CPU compute path.
 """
 from .raycasting_scene import RaycastingScene, INVALID_ID  # noqa: F401
 
-__all__ = ["RaycastingScene", "INVALID_ID"]
+
+
+def empty_cache() -> None:
+    """Return the device blocks libqsmrt keeps for reuse (freed scenes, commit scratch) to the CUDA driver --
+    the counterpart of ``torch.cuda.empty_cache()``.  The cache is bounded by ``QSMRT_CACHE_MB`` (default 1024)."""
+    from . import _lib
+    _lib.check(_lib.load().qsmrt_release_cached_memory())
+
+
+__all__ = ["RaycastingScene", "INVALID_ID", "empty_cache"]

@@ -59,6 +59,7 @@ SYMBOLS = {
                                         C.POINTER(C.c_double), C.POINTER(C.c_int), _vp]),
     "qsmrt_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "qsmrt_debug_get_build": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "qsmrt_release_cached_memory": (C.c_int, []),
     "qsmrt_debug_set_keep_binary_nodes": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -10,6 +10,9 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <map>
+#include <unordered_map>
+#include <mutex>
 
 #include "../../include/qsmrt.h"
 #include "common.cuh"
@@ -19,6 +22,7 @@
 static thread_local char g_err[512] = "";
 static int g_allow_qnodes = 1;              // qsmrt_debug_set_quantised_nodes
 static bool g_keep_bnodes = false;          // qsmrt_debug_set_keep_binary_nodes
+constexpr int QSMRT_MAX_DEVICES = 64;
 static int g_leaf_max = 2;                  // triangles per leaf (qsmrt_debug_set_leaf_max); 2 measured best on C2
 
 void qsmrt_set_error(const char *fmt, ...)
@@ -68,15 +72,86 @@ struct qsmrt_scene {
 
 namespace {
 
-template <class T> int dmalloc(T **p, uint64_t count)
+// ---- device memory: a small per-device block cache in front of cudaMalloc / cudaFree.
+// The reference builds a fresh RaycastingScene in every function (ray_casting.py:65,155,218,241,275,316); a commit
+// makes ~25 allocations and as many frees, and on a 50k-triangle tree those driver calls took 6-18 ms around a
+// 0.23 ms build.  Freed blocks are kept (up to QSMRT_CACHE_MB, default 1024) and handed out again for requests of
+// nearly the same size.  A block is only recycled after cudaDeviceSynchronize(), which is what cudaFree implied:
+// no kernel that still reads it can be in flight.
+struct BlockCache {
+    std::mutex m;
+    std::multimap<size_t, void *> idle[QSMRT_MAX_DEVICES];
+    std::unordered_map<void *, size_t> size_of;          // every block we handed out or hold
+    size_t idle_bytes = 0, cap = 0;
+    bool cap_read = false;
+    size_t limit()
+    {
+        if (!cap_read) { const char *e = getenv("QSMRT_CACHE_MB"); cap = (size_t)(e ? atoll(e) : 1024) << 20; cap_read = true; }
+        return cap;
+    }
+    void release_all()
+    {
+        for (auto &mm : idle) { for (auto &kv : mm) { size_of.erase(kv.second); cudaFree(kv.second); } mm.clear(); }
+        idle_bytes = 0;
+    }
+} g_blocks;
+
+int dmalloc_bytes(void **p, size_t bytes)
 {
     *p = nullptr;
-    if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T));
-    if (e != cudaSuccess) { qsmrt_set_error("cudaMalloc(%llu bytes): %s", (unsigned long long)(count * sizeof(T)), cudaGetErrorString(e)); return 1; }
+    bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_blocks.m);
+    if (dev >= 0 && dev < QSMRT_MAX_DEVICES) {
+        auto &mm = g_blocks.idle[dev];
+        auto it = mm.lower_bound(bytes);
+        if (it != mm.end() && it->first <= bytes + bytes / 4 + (64u << 10)) {
+            *p = it->second; g_blocks.idle_bytes -= it->first; mm.erase(it);
+            return 0;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {                      // out of memory: give the cached blocks back and try once more
+        cudaGetLastError();
+        g_blocks.release_all();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) { *p = nullptr; qsmrt_set_error("cudaMalloc(%llu bytes): %s", (unsigned long long)bytes, cudaGetErrorString(e)); return 1; }
+    g_blocks.size_of[*p] = bytes;
     return 0;
 }
-template <class T> void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+thread_local int tl_frees_synced = 0;
+// one device synchronisation for a run of frees (scene teardown, end of a commit) instead of one per block
+struct SyncedFrees {
+    SyncedFrees() { cudaDeviceSynchronize(); ++tl_frees_synced; }
+    ~SyncedFrees() { --tl_frees_synced; }
+};
+
+void dfree_bytes(void *p)
+{
+    if (!p) return;
+    if (!tl_frees_synced) cudaDeviceSynchronize();      // cudaFree's implicit guarantee, kept for recycled blocks
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_blocks.m);
+    auto it = g_blocks.size_of.find(p);
+    if (it != g_blocks.size_of.end() && dev >= 0 && dev < QSMRT_MAX_DEVICES &&
+        g_blocks.idle_bytes + it->second <= g_blocks.limit()) {
+        g_blocks.idle[dev].emplace(it->second, p);
+        g_blocks.idle_bytes += it->second;
+        return;
+    }
+    if (it != g_blocks.size_of.end()) g_blocks.size_of.erase(it);
+    cudaFree(p);
+}
+
+template <class T> int dmalloc(T **p, uint64_t count)
+{
+    return dmalloc_bytes(reinterpret_cast<void **>(p), (size_t)count * sizeof(T));
+}
+template <class T> void dfree(T *&p) { dfree_bytes(p); p = nullptr; }
 
 void free_build(qsmrt_scene *s)
 {
@@ -192,8 +267,17 @@ int check_rays(const float *rays, uint64_t N)
     return 0;
 }
 
-SceneView view_of(const qsmrt_scene *s)
+SceneView view_of(qsmrt_scene *s)
 {
+    if (g_trv_node_path != 0 && !s->node_tex && s->tnodes) {
+        // float4 texture view of the node array, made on first use: only the TEX-path experiment
+        // (qsmrt_debug_set_node_path) reads it, and creating it cost every commit a driver call
+        cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = s->tnodes;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = std::max<uint64_t>(s->ntris - 1, 1) * sizeof(TNode);
+        cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+        if (cudaCreateTextureObject(&s->node_tex, &rd, &td, nullptr) != cudaSuccess) { s->node_tex = 0; cudaGetLastError(); }
+    }
     SceneView v;
     v.nodes = s->tnodes; v.tris = s->tris; v.ntris = (uint32_t)s->ntris; v.height = s->stats.bvh_height;
     v.node_tex = s->node_tex;
@@ -205,6 +289,7 @@ SceneView view_of(const qsmrt_scene *s)
 int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
 {
     if (s->committed) { if (build_ms_out) *build_ms_out = s->stats.build_ms; return 0; }
+    SyncedFrees batch;          // covers the re-commit teardown here and, after the build's own event wait, the scratch frees
     free_build(s);
     const uint32_t G = (uint32_t)s->geoms.size();
     uint64_t T = 0, V = 0;
@@ -275,14 +360,8 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         for (int a = 0; a < 3; ++a) { s->glo[a] = bp.glo[a]; s->cell[a] = bp.cell[a]; }
         s->stats.quantised_nodes = s->use_qnodes ? 1u : 0u;
         s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + T * sizeof(TriRec);
-        {   // float4 texture view of the node array (TEX-path experiment); optional
-            cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = s->tnodes;
-            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-            rd.res.linear.sizeInBytes = std::max<uint64_t>(T - 1, 1) * sizeof(TNode);
-            cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
-            if (cudaCreateTextureObject(&s->node_tex, &rd, &td, nullptr) != cudaSuccess) { s->node_tex = 0; cudaGetLastError(); }
-        }
     }
+    if (rc) cudaDeviceSynchronize();        // a failed build may still have kernels in flight
     dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags);
     dfree(counters); dfree(climb);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(es0); cudaEventDestroy(es1);
@@ -328,9 +407,10 @@ int qsmrt_scene_create(int cuda_device, qsmrt_scene **out)
         FAIL("no CUDA device (%s); libqsmrt has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     if (cuda_device < 0 || cuda_device >= ndev) FAIL("cuda_device %d out of range (0..%d)", cuda_device, ndev - 1);
     CUDA_TRY(cudaSetDevice(cuda_device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, cuda_device));
-    if (prop.major != 10) FAIL("device %d is sm_%d%d; libqsmrt is built for sm_100a only", cuda_device, prop.major, prop.minor);
+    int major = 0, minor = 0;       // two attribute reads, not cudaGetDeviceProperties (2.4 ms per new scene)
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cuda_device));
+    CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, cuda_device));
+    if (major != 10) FAIL("device %d is sm_%d%d; libqsmrt is built for sm_100a only", cuda_device, major, minor);
     qsmrt_scene *s = new qsmrt_scene();
     s->device = cuda_device;
     *out = s;
@@ -341,6 +421,7 @@ int qsmrt_scene_destroy(qsmrt_scene *s)
 {
     if (!s) return 0;
     cudaSetDevice(s->device);
+    SyncedFrees batch;
     free_build(s);
     free_pipe(s->pipe);
     for (Geometry &g : s->geoms) { dfree(g.verts); dfree(g.idx); }
@@ -481,6 +562,14 @@ int qsmrt_debug_set_sort(int variant)
 {
     if (variant != 0 && variant != 1) FAIL("sort variant must be 0 (classic) or 1 (onesweep)");
     g_sort_variant = variant;
+    return 0;
+}
+
+int qsmrt_release_cached_memory(void)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_blocks.m);
+    g_blocks.release_all();
     return 0;
 }
 

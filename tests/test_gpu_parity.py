@@ -658,3 +658,24 @@ def test_far_origins_and_offset_scenes(RS, oracle_mod):
                 assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 0))
         finally:
             _lib.check(L.qsmrt_debug_set_quantised_nodes(1))
+
+
+def test_scene_churn_reuses_device_blocks(RS, oracle_mod):
+    """The reference makes a new scene in every function; libqsmrt recycles the device blocks of dead scenes.
+    Scenes of equal size built one after the other must not see each other's data, and the cache can be dropped."""
+    import pyqsm_b200
+    rays = syn.random_rays((-3, -3, -3), (3, 3, 3), 4000, seed=3)
+    for rep in range(6):
+        rng = np.random.default_rng(100 + rep)
+        n = 3000 if rep % 2 == 0 else 2999
+        v = rng.uniform(-3, 3, size=(3 * n, 3)).astype(np.float32)
+        v[1::3] = v[0::3] + rng.normal(0, 0.3, size=(n, 3)).astype(np.float32)
+        v[2::3] = v[0::3] + rng.normal(0, 0.3, size=(n, 3)).astype(np.float32)
+        t = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+        o = oracle_mod.OracleScene(); o.add_triangles(v, t)
+        g = RS(); g.add_triangles(v, t)
+        assert_cast_equal(g.cast_rays(rays), o.cast_rays(rays, 0), o.edge_flags(rays, mode=0), f"churn{rep}")
+        assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 0))
+        del g
+        if rep == 3:
+            pyqsm_b200.empty_cache()
