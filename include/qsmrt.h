@@ -48,7 +48,7 @@ typedef struct qsmrt_stats {
     uint32_t leaf_max;           /* triangles per collapsed leaf */
     uint32_t bvh_height;         /* binary LBVH height (bounds the traversal stack) */
     uint32_t quantised_nodes;    /* 1: the persistent kernel reads the 32-byte 16-bit-grid nodes */
-    uint32_t reserved;
+    uint32_t full_sort;          /* 1: the last commit fell back to all eight radix passes (a run of > 64 keys equal in their top 40 bits) */
 } qsmrt_stats;
 
 const char *qsmrt_last_error(void);

@@ -23,7 +23,7 @@ class Stats(C.Structure):
         ("bvh_bytes", C.c_uint64),
         ("build_ms", C.c_float), ("sort_ms", C.c_float), ("box_pad", C.c_float),
         ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3),
-        ("leaf_max", C.c_uint32), ("bvh_height", C.c_uint32), ("quantised_nodes", C.c_uint32), ("reserved", C.c_uint32),
+        ("leaf_max", C.c_uint32), ("bvh_height", C.c_uint32), ("quantised_nodes", C.c_uint32), ("full_sort", C.c_uint32),
     ]
 
 

@@ -31,7 +31,8 @@ struct LbvhBuildArgs {
     TNode      *tnodes;             // [max(T-1,1)]
     QNode      *qnodes;             // [max(T-1,1)] quantised twin of tnodes
     void       *climb_work;         // lbvh_climb_bytes(T): subtrees handed to the climb kernel
-    unsigned long long *counters;   // [4] nodes emitted, leaves emitted, binary tree height, climb list length
+    unsigned long long *counters;   // [5] nodes emitted, leaves emitted, binary tree height, climb list length, sort overflow
+    int         full_sort;          // all eight radix passes (after a sort overflow: a run of > 64 keys equal in their top 40 bits)
     cudaEvent_t ev_sort0, ev_sort1; // optional
 };
 
@@ -39,5 +40,5 @@ extern int g_sort_variant;
 size_t lbvh_sort_scratch_bytes(uint64_t n);
 size_t lbvh_climb_bytes(uint64_t n);
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
-                    uint64_t n, uint32_t *scratch, cudaStream_t st);
+                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow = nullptr);
 int lbvh_build(const LbvhBuildArgs &args, cudaStream_t st);

@@ -288,18 +288,52 @@ constexpr int OS_CTAS = 5;                           // resident CTAs per SM the
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;       // 3072 keys: 36 KB staged + 8 KB counters -> 4 CTAs / SM
 
 __global__ void __launch_bounds__(256)
-k_os_histogram(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ ghist /* [8][256] */)
+k_os_histogram(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ ghist /* [8][256] */, int shift0, int npass)
 {
     __shared__ uint32_t h[8][256];
     for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
     __syncthreads();
     for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
-        uint64_t k = keys[i];
+        uint64_t k = keys[i] >> shift0;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) atomicAdd(&h[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+        for (int p = 0; p < 8; ++p) if (p < npass) atomicAdd(&h[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) { uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
+    for (int i = threadIdx.x; i < npass * 256; i += 256) { uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
+}
+
+// After the passes over the top 40 bits: order every run of keys that agree in those bits by (whole key, index) --
+// exactly what the three skipped low passes of the stable sort would have produced -- while copying to the
+// final buffers.  Runs are short (two triangles of one leaf, duplicates); a run longer than SORT_MAX_RUN raises
+// *overflow and the host repeats the build with all eight passes.
+constexpr int SORT_TOP_SHIFT = 23;          // 63-bit keys: passes at bits 23, 31, 39, 47, 55
+constexpr int SORT_MAX_RUN = 64;
+
+__global__ void __launch_bounds__(256)
+k_sort_fixup(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+             uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, int64_t n, unsigned long long *overflow)
+{
+    const int64_t i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = kin[i];
+    const uint32_t v = vin[i];
+    const uint64_t top = k >> SORT_TOP_SHIFT;
+    int64_t a = i, b = i;
+    while (a > 0 && i - a <= SORT_MAX_RUN && (kin[a - 1] >> SORT_TOP_SHIFT) == top) --a;
+    while (b + 1 < n && b - i <= SORT_MAX_RUN && (kin[b + 1] >> SORT_TOP_SHIFT) == top) ++b;
+    int64_t dst = i;
+    if (i - a > SORT_MAX_RUN || b - i > SORT_MAX_RUN) {
+        *overflow = 1ull;
+    } else if (a != b) {
+        int rank = 0;
+        for (int64_t m = a; m <= b; ++m) {
+            const uint64_t km = kin[m];
+            rank += (km < k) || (km == k && vin[m] < v);
+        }
+        dst = a + rank;
+    }
+    kout[dst] = k;
+    vout[dst] = v;
 }
 
 __global__ void __launch_bounds__(OS_THREADS, OS_CTAS)
@@ -851,7 +885,7 @@ size_t lbvh_climb_bytes(uint64_t n) { return lbvh_climb_items(n) * sizeof(ClimbI
 int g_sort_min_onesweep = 0;     // keys from which the onesweep variant is used (qsmrt_debug_set_sort)
 
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
-                    uint64_t n, uint32_t *scratch, cudaStream_t st)
+                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow)
 {
     if (n == 0) return 0;
     uint32_t ntiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
@@ -863,15 +897,20 @@ int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t
         static const cudaError_t carve = cudaFuncSetAttribute(k_os_pass, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         (void)carve;            // OS_CTAS x 45 KB only fit with the largest shared-memory split
         uint32_t *status = scratch, *ghist = scratch + 8ull * os_tiles * 256, *counters = ghist + 8 * 256;
-        // one clear for the look-back status of all eight passes, the histograms and the tile counters
+        // With `overflow`: five passes over the top 40 bits, then k_sort_fixup orders the (short) runs of keys
+        // that agree in them -- three fewer trips of 12 B per key through HBM for the same final order.
+        const int shift0 = overflow ? SORT_TOP_SHIFT : 0, npass = overflow ? 5 : 8;
+        // one clear for the look-back status of all passes, the histograms and the tile counters
         CUDA_TRY(cudaMemsetAsync(scratch, 0, (8ull * os_tiles * 256 + 8 * 256 + 8) * sizeof(uint32_t), st));
-        k_os_histogram<<<(unsigned)std::min<uint64_t>((n + 4095) / 4096, 148 * 8), 256, 0, st>>>(keys, n, ghist);
-        for (int pass = 0; pass < 8; ++pass) {
-            k_os_pass<<<os_tiles, OS_THREADS, 0, st>>>(kin, vin, kout, vout, n, pass * 8, ghist + pass * 256,
+        k_os_histogram<<<(unsigned)std::min<uint64_t>((n + 4095) / 4096, 148 * 8), 256, 0, st>>>(keys, n, ghist, shift0, npass);
+        for (int pass = 0; pass < npass; ++pass) {
+            k_os_pass<<<os_tiles, OS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift0 + pass * 8, ghist + pass * 256,
                                                        status + (uint64_t)pass * os_tiles * 256, counters + pass);
             uint64_t *tk = kin; kin = kout; kout = tk;
             uint32_t *tv = vin; vin = vout; vout = tv;
         }
+        if (overflow)       // five passes: the data sits in the tmp buffers, the fix-up brings it home
+            k_sort_fixup<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, vin, kout, vout, (int64_t)n, overflow);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -892,15 +931,15 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     const uint64_t n = A.ntris;
     const int B = 256;
     const unsigned gN = (unsigned)((n + B - 1) / B);
+    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 5 * sizeof(unsigned long long), st));
     k_init_bounds<<<1, 32, 0, st>>>(A.bounds_ord);
     k_scene_bounds<<<min(gN, 148u * 8u), B, 0, st>>>(A.verts, A.idx, n, A.bounds_ord);
     k_finalize_bounds<<<1, 32, 0, st>>>(A.bounds_ord, A.params);
     k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order);
     CUDA_TRY(cudaGetLastError());
     if (A.ev_sort0) CUDA_TRY(cudaEventRecord(A.ev_sort0, st));
-    if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st)) return 1;
+    if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st, A.full_sort ? nullptr : A.counters + 4)) return 1;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
-    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 4 * sizeof(unsigned long long), st));
     if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
     const int keep = (A.keep_bnodes || n == 1) ? 1 : 0;
     const unsigned work_cap = (unsigned)lbvh_climb_items(n);

@@ -318,7 +318,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         dmalloc(&sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&bounds, 8) ||
         dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&flags, T) || dmalloc(&s->tris, T) ||
         dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(T - 1, 1)) ||
-        dmalloc(&counters, 4) || dmalloc(&climb, lbvh_climb_bytes(T) / sizeof(uint32_t)))
+        dmalloc(&counters, 5) || dmalloc(&climb, lbvh_climb_bytes(T) / sizeof(uint32_t)))
         return 1;
     if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
     else {
@@ -342,15 +342,26 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
     A.bnodes = s->bnodes; A.flags = flags; A.keep_bnodes = g_keep_bnodes ? 1 : 0; A.climb_work = climb;
     A.qnodes = s->qnodes;
     A.tris = s->tris; A.tnodes = s->tnodes; A.counters = counters; A.ev_sort0 = es0; A.ev_sort1 = es1;
-    int rc = lbvh_build(A, st);
-    if (!rc) {
+    int rc = 0;
+    unsigned long long cnt[5] = {};
+    // The sort normally runs over the top 40 key bits plus an exact fix-up of short runs; a scene with a run of more
+    // than 64 triangles in one 2^-13 cell (thousands of coincident triangles) reports an overflow and is built again
+    // with all eight passes.  Both attempts are inside the timed region.
+    for (int attempt = 0; attempt < 2 && !rc; ++attempt) {
+        A.full_sort = attempt;
+        rc = lbvh_build(A, st);
+        if (rc) break;
         CUDA_TRY(cudaEventRecord(e1, st));
         CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaMemcpy(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+        if (!cnt[4]) break;
+    }
+    s->stats.full_sort = (uint32_t)A.full_sort;
+    if (!rc) {
         CUDA_TRY(cudaEventElapsedTime(&s->stats.build_ms, e0, e1));
         CUDA_TRY(cudaEventElapsedTime(&s->stats.sort_ms, es0, es1));
-        BuildParams bp; unsigned long long cnt[3];
+        BuildParams bp;
         CUDA_TRY(cudaMemcpy(&bp, s->params, sizeof(bp), cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost));
         for (int a = 0; a < 3; ++a) { s->stats.scene_lo[a] = bp.slo[a]; s->stats.scene_hi[a] = bp.shi[a]; }
         s->stats.box_pad = bp.pad;
         s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];

@@ -200,7 +200,7 @@ def _builder_topology(RS, oracle_mod, v, t, keep):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 256, 257, 511, 513, 1000, 4097, 70001])
-@pytest.mark.parametrize("kind", ["random", "duplicates", "clusters"])
+@pytest.mark.parametrize("kind", ["random", "duplicates", "clusters", "coincident"])
 def test_builder_block_boundaries_and_equal_keys(RS, oracle_mod, n, kind):
     """The fused bottom-up builder joins subtrees through shuffles (32 leaves), shared memory (256 leaves) and
     global flags: sizes around those boundaries, and runs of identical Morton keys (index tie-break, the deepest
@@ -210,9 +210,13 @@ def test_builder_block_boundaries_and_equal_keys(RS, oracle_mod, n, kind):
         c = rng.uniform(-3, 3, size=(n, 3))
     elif kind == "duplicates":                       # every triangle 1..40 times: long runs of equal keys
         c = np.repeat(rng.uniform(-3, 3, size=(n // 20 + 1, 3)), 40, axis=0)[rng.permutation((n // 20 + 1) * 40)[:n]]
+    elif kind == "coincident":                       # one triangle n times (plus two far corners that span the scene):
+        c = np.tile(rng.uniform(-1, 1, size=(1, 3)), (n, 1))      # a run the 40-bit sort cannot order -> full-sort fallback
+        if n > 2:
+            c[:2] = [[-3, -3, -3], [3, 3, 3]]
     else:                                            # a few tight clusters: deep prefixes, unbalanced tree
         c = rng.uniform(-3, 3, size=(5, 3))[rng.integers(0, 5, n)] + rng.normal(0, 1e-4, size=(n, 3))
-    d = np.tile(np.array([[0.05, 0, 0], [0, 0.05, 0], [0, 0, 0.0]]), (n, 1, 1)) if kind == "duplicates" else rng.normal(0, 0.05, size=(n, 3, 3))
+    d = np.tile(np.array([[0.05, 0, 0], [0, 0.05, 0], [0, 0, 0.0]]), (n, 1, 1)) if kind in ("duplicates", "coincident") else rng.normal(0, 0.05, size=(n, 3, 3))
     v = (c[:, None, :] + d).reshape(-1, 3).astype(np.float32)
     t = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
     rays = np.concatenate([syn.random_rays((-3, -3, -3), (3, 3, 3), 1500, seed=n),
@@ -224,6 +228,10 @@ def test_builder_block_boundaries_and_equal_keys(RS, oracle_mod, n, kind):
         assert_cast_equal(g.cast_rays(rays), ref, o.edge_flags(rays, mode=mode), f"{kind}{n}")
         assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, mode))
         assert np.isfinite(ref["t_hit"][1500:]).sum() >= min(n, 500) // 2      # rays over the centroids
+        if kind == "coincident":                     # > 64 keys equal in their top 40 bits: eight passes instead of 5 + fix-up
+            assert g.stats()["full_sort"] == (1 if n >= 255 else 0) or 33 < n < 255
+        else:
+            assert g.stats()["full_sort"] == 0
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])

@@ -35,3 +35,22 @@ bench("cast_rays C1 1M rays device->device (+sync)", dev, 10)
 def build():
     x = RaycastingScene(); x.add_triangles(v, t); x.commit()
 bench("scene create + add_triangles(host) + commit 50k tris", build, 10)
+# ray_casting.py:241-255: signed distance on 256 random points and on a 64^3 grid
+lo, hi = v.min(0), v.max(0)
+q256 = np.random.default_rng(0).uniform(lo, hi, size=(256, 3)).astype(np.float32)
+xs = [np.linspace(lo[a], hi[a], 64, dtype=np.float32) for a in range(3)]
+g64 = np.stack(np.meshgrid(*xs, indexing="ij"), -1)
+bench("compute_signed_distance 256 points", lambda: s.compute_signed_distance(q256))
+bench("compute_signed_distance 64^3 grid", lambda: s.compute_signed_distance(g64), 10)
+bench("compute_distance 64^3 grid", lambda: s.compute_distance(g64), 10)
+bench("compute_occupancy 64^3 grid", lambda: s.compute_occupancy(g64), 10)
+bench("compute_closest_points 64^3 grid", lambda: s.compute_closest_points(g64), 10)
+vc, tc = syn.canopy_mesh(2, 1_000_000)
+s2 = RaycastingScene(); s2.add_triangles(vc, tc); s2.commit()
+lo, hi = vc.min(0), vc.max(0)
+xs = [np.linspace(lo[a], hi[a], 64, dtype=np.float32) for a in range(3)]
+g64 = np.stack(np.meshgrid(*xs, indexing="ij"), -1)
+bench("canopy 2M tris: compute_signed_distance 64^3 grid", lambda: s2.compute_signed_distance(g64), 5)
+r1M = torch.from_numpy(syn.materialize_grid(*syn.parallel_ray_grid(lo, hi, syn.sun_direction(45, 135), 1000, 1000), 1000, 1000))
+bench("canopy 2M tris: list_intersections 1M rays", lambda: s2.list_intersections(r1M), 5)
+bench("canopy 2M tris: count_intersections 1M rays", lambda: s2.count_intersections(r1M), 5)
