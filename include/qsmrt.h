@@ -225,6 +225,9 @@ int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
  * otherwise is an error. */
 int qsmrt_debug_get_build(qsmrt_scene *scene, uint64_t *keys, uint32_t *order, void *nodes);
 int qsmrt_debug_set_keep_binary_nodes(int keep);
+/* Caps the list of open subtrees the hierarchy kernel hands to the climb kernel (0 = default, triangles / 4 + 1024);
+ * subtrees that do not fit climb inside the first kernel.  Test hook for that overflow path. */
+int qsmrt_debug_set_climb_capacity(int items);
 
 /* Tuning hook for A/B measurements: 1 = one independent loop per thread (the
  * first kernel, kept as the simple reference), 2 = the persistent warp-uniform

@@ -61,6 +61,7 @@ SYMBOLS = {
     "qsmrt_debug_get_build": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qsmrt_release_cached_memory": (C.c_int, []),
     "qsmrt_debug_set_keep_binary_nodes": (C.c_int, [C.c_int]),
+    "qsmrt_debug_set_climb_capacity": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "qsmrt_debug_set_sort": (C.c_int, [C.c_int]),

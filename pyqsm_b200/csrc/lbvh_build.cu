@@ -58,13 +58,20 @@ k_scene_bounds(const float *__restrict__ verts, const uint32_t *__restrict__ idx
             lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
         }
+    // one set of global atomics per block, not per warp (9472 warps x 6 atomics on six addresses at 2M triangles)
+    __shared__ uint32_t sb[6];
+    if (threadIdx.x < 3) sb[threadIdx.x] = 0xFFFFFFFFu; else if (threadIdx.x < 6) sb[threadIdx.x] = 0u;
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            atomicMin(&ob[a], f2ord(lo[a]));
-            atomicMax(&ob[3 + a], f2ord(hi[a]));
+            atomicMin(&sb[a], f2ord(lo[a]));
+            atomicMax(&sb[3 + a], f2ord(hi[a]));
         }
     }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicMin(&ob[threadIdx.x], sb[threadIdx.x]);
+    else if (threadIdx.x < 6) atomicMax(&ob[threadIdx.x], sb[threadIdx.x]);
 }
 
 __global__ void k_finalize_bounds(const uint32_t *ob, BuildParams *bp)
@@ -882,6 +889,7 @@ size_t lbvh_sort_scratch_bytes(uint64_t n)
 size_t lbvh_climb_items(uint64_t n) { return (size_t)(n / 4 + 1024); }
 size_t lbvh_climb_bytes(uint64_t n) { return lbvh_climb_items(n) * sizeof(ClimbItem); }
 
+int g_climb_cap_override = 0;    // qsmrt_debug_set_climb_capacity: shrink the climb list to exercise its overflow path
 int g_sort_min_onesweep = 0;     // keys from which the onesweep variant is used (qsmrt_debug_set_sort)
 
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
@@ -942,7 +950,8 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
     if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
     const int keep = (A.keep_bnodes || n == 1) ? 1 : 0;
-    const unsigned work_cap = (unsigned)lbvh_climb_items(n);
+    const unsigned work_cap = g_climb_cap_override > 0 ? std::min<unsigned>((unsigned)g_climb_cap_override, (unsigned)lbvh_climb_items(n))
+                                                       : (unsigned)lbvh_climb_items(n);
     unsigned *work_count = reinterpret_cast<unsigned *>(A.counters + 3);
     ClimbItem *work = reinterpret_cast<ClimbItem *>(A.climb_work);
     k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(

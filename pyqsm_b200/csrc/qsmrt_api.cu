@@ -584,6 +584,12 @@ int qsmrt_release_cached_memory(void)
     return 0;
 }
 
+int qsmrt_debug_set_climb_capacity(int items)
+{
+    g_climb_cap_override = items > 0 ? items : 0;
+    return 0;
+}
+
 int qsmrt_debug_set_keep_binary_nodes(int keep)
 {
     g_keep_bnodes = keep != 0;

@@ -668,6 +668,26 @@ def test_far_origins_and_offset_scenes(RS, oracle_mod):
             _lib.check(L.qsmrt_debug_set_quantised_nodes(1))
 
 
+@pytest.mark.parametrize("cap", [1, 7, 100])
+def test_builder_climb_list_overflow(RS, oracle_mod, cap):
+    """Open subtrees that do not fit the climb list finish their climb inside the hierarchy kernel: same tree."""
+    from pyqsm_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(cap)
+    n = 20011
+    c = rng.uniform(-3, 3, size=(n, 3))
+    v = (c[:, None, :] + rng.normal(0, 0.05, size=(n, 3, 3))).reshape(-1, 3).astype(np.float32)
+    t = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    rays = syn.random_rays((-3, -3, -3), (3, 3, 3), 3000, seed=cap)
+    _lib.check(L.qsmrt_debug_set_climb_capacity(cap))
+    try:
+        for keep in (True, False):
+            o, g = _builder_topology(RS, oracle_mod, v, t, keep)
+            assert_cast_equal(g.cast_rays(rays), o.cast_rays(rays, 1), o.edge_flags(rays, mode=1), f"climbcap{cap}")
+    finally:
+        _lib.check(L.qsmrt_debug_set_climb_capacity(0))
+
+
 def test_scene_churn_reuses_device_blocks(RS, oracle_mod):
     """The reference makes a new scene in every function; libqsmrt recycles the device blocks of dead scenes.
     Scenes of equal size built one after the other must not see each other's data, and the cache can be dropped."""
