@@ -783,14 +783,21 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
         else          refit_merge(R, Q, id, l, s, r, slo, shi, mlo, mhi, mlo, mhi, n_nodes, n_leafrefs);
     }
 
-    // ---- hand the subtrees that are still open to the climb kernel (their parents span several blocks)
+    // ---- hand the subtrees that are still open to the climb kernel (their parents span several blocks);
+    //      one atomic per block on the list length (per warp: 62k atomics on one address at 2M triangles)
     {
+        __shared__ unsigned s_hold[RF_WARPS], s_base;
         const unsigned hm = __ballot_sync(FULL, holding);
-        unsigned base = 0;
-        if (lane == 0 && hm) base = atomicAdd(work_count, (unsigned)__popc(hm));
-        base = __shfl_sync(FULL, base, 0);
+        if (lane == 0) s_hold[warp] = (unsigned)__popc(hm);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int k = 0; k < RF_WARPS; ++k) { const unsigned c = s_hold[k]; s_hold[k] = tot; tot += c; }
+            s_base = tot ? atomicAdd(work_count, tot) : 0u;
+        }
+        __syncthreads();
         if (holding) {
-            const unsigned slot = base + __popc(hm & ((1u << lane) - 1u));
+            const unsigned slot = s_base + s_hold[warp] + __popc(hm & ((1u << lane) - 1u));
             if (slot < work_cap) {
                 ClimbItem it;
                 it.a = make_int4(l, r, dl, dr);
@@ -813,14 +820,21 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
             emit_node(R, (int32_t)i, s_qi[0][k], g, s_qi[2][k], llo, lhi, rlo, rhi, n_nodes, n_leafrefs);
         }
     }
-    // statistics: one atomic per warp
+    // statistics: one pair of atomics per block (per warp they were 125k atomics on two addresses at 2M triangles)
     for (int o = 16; o > 0; o >>= 1) {
         n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
         n_leafrefs += __shfl_xor_sync(FULL, n_leafrefs, o);
     }
-    if (lane == 0 && n_nodes) {
-        atomicAdd(&counters[0], (unsigned long long)n_nodes);
-        atomicAdd(&counters[1], (unsigned long long)n_leafrefs);
+    __syncthreads();                        // s_wp / s_ws are free again
+    if (lane == 0) { s_wp[warp] = (int)n_nodes; s_ws[warp] = (int)n_leafrefs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tn_ = 0, tl_ = 0;
+        for (int k = 0; k < RF_WARPS; ++k) { tn_ += (unsigned)s_wp[k]; tl_ += (unsigned)s_ws[k]; }
+        if (tn_) {
+            atomicAdd(&counters[0], (unsigned long long)tn_);
+            atomicAdd(&counters[1], (unsigned long long)tl_);
+        }
     }
 }
 
