@@ -228,6 +228,9 @@ int qsmrt_debug_set_keep_binary_nodes(int keep);
 /* Caps the list of open subtrees the hierarchy kernel hands to the climb kernel (0 = default, triangles / 4 + 1024);
  * subtrees that do not fit climb inside the first kernel.  Test hook for that overflow path. */
 int qsmrt_debug_set_climb_capacity(int items);
+/* The next commits use the 32-byte quantised nodes when 6 grid cells <= frac x the mean leaf-box diagonal
+ * (default 0.15; <= 0 restores it).  A/B hook: results are identical either way. */
+int qsmrt_debug_set_quant_threshold(float frac);
 
 /* Tuning hook for A/B measurements: 1 = one independent loop per thread (the
  * first kernel, kept as the simple reference), 2 = the persistent warp-uniform

@@ -38,6 +38,7 @@ struct LbvhBuildArgs {
 
 extern int g_sort_variant;
 extern int g_climb_cap_override;
+extern float g_quant_frac;
 size_t lbvh_sort_scratch_bytes(uint64_t n);
 size_t lbvh_climb_bytes(uint64_t n);
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,

@@ -641,7 +641,7 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
                        BuildParams *bp, BNode *bn, TriRec *__restrict__ tris,
                        unsigned long long *flags, TNode *__restrict__ tn, QNode *__restrict__ qn,
                        unsigned long long *counters, int leaf_max, int keep_bn,
-                       ClimbItem *__restrict__ work, unsigned *work_count, unsigned work_cap)
+                       ClimbItem *__restrict__ work, unsigned *work_count, unsigned work_cap, float quant_frac)
 {
     // block phase state: slot k belongs to the split between leaves b0 + k and b0 + k + 1
     __shared__ uint32_t s_flag[RF_BLOCK];
@@ -661,7 +661,7 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
     // The 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf
     // (mean leaf diagonal from k_morton).  Every thread evaluates the same expression; thread 0 records it.
     const float max_cell = fmaxf(bp->cell[0], fmaxf(bp->cell[1], bp->cell[2]));
-    const bool use_q = 6.0f * max_cell <= 0.15f * (bp->leaf_diag_sum / (float)n);
+    const bool use_q = 6.0f * max_cell <= quant_frac * (bp->leaf_diag_sum / (float)n);
     if (i == 0) bp->use_q = use_q ? 1 : 0;
     const RefitOut R{ bn, tn, qn, bp, n, leaf_max, use_q, keep_bn != 0 };
     const RefitQueue Q{ s_qf, s_qi, bfirst, blast };
@@ -903,6 +903,7 @@ size_t lbvh_sort_scratch_bytes(uint64_t n)
 size_t lbvh_climb_items(uint64_t n) { return (size_t)(n / 4 + 1024); }
 size_t lbvh_climb_bytes(uint64_t n) { return lbvh_climb_items(n) * sizeof(ClimbItem); }
 
+float g_quant_frac = 0.15f;      // qsmrt_debug_set_quant_threshold: 6 grid cells <= this share of the mean leaf diagonal -> 32-byte nodes
 int g_climb_cap_override = 0;    // qsmrt_debug_set_climb_capacity: shrink the climb list to exercise its overflow path
 int g_sort_min_onesweep = 0;     // keys from which the onesweep variant is used (qsmrt_debug_set_sort)
 
@@ -970,7 +971,7 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     ClimbItem *work = reinterpret_cast<ClimbItem *>(A.climb_work);
     k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(
         A.verts, A.idx, (int64_t)n, A.keys, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
-        A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap);
+        A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap, g_quant_frac);
     k_hierarchy_climb<<<std::min((work_cap + CL_BLOCK - 1) / CL_BLOCK, 148u * 32u), CL_BLOCK, 0, st>>>(
         (int64_t)n, A.params, A.bnodes, A.flags, A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap);
     if (n == 1) k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);

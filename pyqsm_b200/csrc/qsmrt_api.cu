@@ -584,6 +584,12 @@ int qsmrt_release_cached_memory(void)
     return 0;
 }
 
+int qsmrt_debug_set_quant_threshold(float frac)
+{
+    g_quant_frac = frac > 0.0f ? frac : 0.15f;
+    return 0;
+}
+
 int qsmrt_debug_set_climb_capacity(int items)
 {
     g_climb_cap_override = items > 0 ? items : 0;
