@@ -63,6 +63,17 @@ def _mesh_arrays(mesh):
     return get(mesh.vertex, "positions"), get(mesh.triangle, "indices")
 
 
+def _occupancy_directions(nsamples: int):
+    """(1,1,1) first (the single-sample direction), then a fixed seeded set of unit vectors."""
+    dirs = [(1.0, 1.0, 1.0)]
+    if nsamples > 1:
+        rng = np.random.default_rng(42)
+        v = rng.uniform(-1.0, 1.0, size=(nsamples - 1, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        dirs += [tuple(float(x) for x in r) for r in v]
+    return dirs
+
+
 class RaycastingScene:
     """Open3D-compatible ray casting scene running on one B200.
 
@@ -263,10 +274,13 @@ class RaycastingScene:
 
     def compute_occupancy(self, query_points, nthreads: int = 0, nsamples: int = 1) -> torch.Tensor:
         """1.0 inside / 0.0 outside (``ray_casting.py:69``): parity of the
-        intersection count of a ray from each point along (1,1,1), as Open3D's
-        ``ComputeOccupancy`` does for ``nsamples == 1``."""
-        if nsamples != 1:
-            raise RuntimeError("compute_occupancy: only nsamples == 1 is implemented")
+        intersection count of a ray from each point.  ``nsamples == 1``: along
+        (1,1,1), as Open3D's ``ComputeOccupancy``; odd ``nsamples > 1``: majority
+        vote over that many fixed directions (Open3D draws its directions from
+        ``std::mt19937(42)``; which directions are used only matters for meshes that
+        are not watertight)."""
+        if nsamples < 1 or nsamples % 2 != 1:
+            raise RuntimeError("compute_occupancy: nsamples must be odd and >= 1")
         p = _unwrap(query_points)
         if p is None:
             p = np.asarray(query_points, dtype=np.float32)
@@ -278,13 +292,16 @@ class RaycastingScene:
             raise RuntimeError(f"query_points has shape {tuple(p.shape)}, but the last dimension must be 3")
         with torch.cuda.device(self.device):
             p = p.to(self.device, torch.float32)
-            rays = torch.cat([p, torch.ones_like(p)], dim=-1)
             saved, self.output_device = self.output_device, self.device
             try:
-                cnt = self.count_intersections(rays)
+                votes = torch.zeros(p.shape[:-1], dtype=torch.int32, device=self.device)
+                for d in _occupancy_directions(nsamples):
+                    dirs = torch.tensor(d, dtype=torch.float32, device=self.device).expand_as(p)
+                    cnt = self.count_intersections(torch.cat([p, dirs], dim=-1))
+                    votes += (cnt % 2 == 1).to(torch.int32)
             finally:
                 self.output_device = saved
-            return self._out((cnt % 2 == 1).to(torch.float32))
+            return self._out((2 * votes > nsamples).to(torch.float32))
 
     def _points(self, query_points):
         p = _unwrap(query_points)
@@ -332,16 +349,26 @@ class RaycastingScene:
 
     def compute_signed_distance(self, query_points, nthreads: int = 0, nsamples: int = 1) -> torch.Tensor:
         """Distance, negative inside (``ray_casting.py:250,255``): the sign is
-        ``compute_occupancy`` (odd intersection count along (1,1,1))."""
-        if nsamples != 1:
-            raise RuntimeError("compute_signed_distance: only nsamples == 1 is implemented")
+        ``compute_occupancy`` (odd intersection count along (1,1,1); majority of
+        ``nsamples`` directions when ``nsamples > 1``)."""
+        if nsamples < 1 or nsamples % 2 != 1:
+            raise RuntimeError("compute_signed_distance: nsamples must be odd and >= 1")
         p = self._points(query_points)
         shp = tuple(p.shape[:-1])
         with torch.cuda.device(self.device):
             p = p.to(self.device).contiguous()
             n = p.numel() // 3
             d = torch.empty(n, dtype=torch.float32, device=self.device)
-            _lib.check(self._L.qsmrt_signed_distance(self._h, _ptr(p), n, _ptr(d), self._stream()))
+            if nsamples == 1:
+                _lib.check(self._L.qsmrt_signed_distance(self._h, _ptr(p), n, _ptr(d), self._stream()))
+            else:
+                saved, self.output_device = self.output_device, self.device
+                try:
+                    d = self.compute_distance(p.reshape(-1, 3)).reshape(-1)
+                    inside = self.compute_occupancy(p.reshape(-1, 3), nsamples=nsamples).reshape(-1) > 0
+                finally:
+                    self.output_device = saved
+                d = torch.where(inside, -d, d)
             return self._out(d).reshape(shp)
 
     def mark_hit_primitives(self, ans: dict):

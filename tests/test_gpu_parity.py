@@ -707,3 +707,30 @@ def test_scene_churn_reuses_device_blocks(RS, oracle_mod):
         del g
         if rep == 3:
             pyqsm_b200.empty_cache()
+
+
+def test_occupancy_majority_vote(RS):
+    """compute_occupancy / compute_signed_distance with nsamples > 1 (Open3D: odd, majority of nsamples rays): on a
+    closed box every direction agrees with the analytic inside test; on a box with one face removed the single
+    (1,1,1) ray leaks through the hole for some points while the majority of 5 directions does not."""
+    v, t = syn.box_mesh((0, 0, 0), (1, 1, 1))
+    g = RS()
+    g.add_triangles(v, t)
+    rng = np.random.default_rng(7)
+    q = rng.uniform(-0.5, 1.5, size=(4000, 3)).astype(np.float32)
+    inside = np.all((q > 0) & (q < 1), axis=1)
+    for ns in (1, 3, 5):
+        assert np.array_equal(g.compute_occupancy(q, nsamples=ns).numpy() > 0, inside)
+        sd = g.compute_signed_distance(q, nsamples=ns).numpy()
+        assert np.array_equal(sd < 0, inside)
+        np.testing.assert_array_equal(np.abs(sd), g.compute_distance(q).numpy())
+    with pytest.raises(RuntimeError):
+        g.compute_occupancy(q, nsamples=2)
+    # open box: drop the two triangles of the +x face (x == 1)
+    keep = ~np.all(v[t.astype(np.int64)][:, :, 0] == 1.0, axis=1)
+    h = RS()
+    h.add_triangles(v, t[keep])
+    qi = rng.uniform(0.05, 0.95, size=(2000, 3)).astype(np.float32)
+    one = h.compute_occupancy(qi, nsamples=1).numpy() > 0
+    five = h.compute_occupancy(qi, nsamples=5).numpy() > 0
+    assert one.mean() < 0.9 and five.mean() > one.mean()
