@@ -110,8 +110,17 @@ struct TraceArgs {
     int multi_geom;     // > 1 geometry: the set also keeps geometry ids
 };
 
-constexpr int TR_NODE_STEPS = 4;     // node steps per phase vote (measured: 1 -> 2 +8 %, 2 -> 4 +2 %)
-constexpr int TR_TRI_STEPS = 2;      // triangle tests per phase vote
+#ifndef QSMRT_NODE_STEPS
+#define QSMRT_NODE_STEPS 8
+#endif
+#ifndef QSMRT_TRI_STEPS
+#define QSMRT_TRI_STEPS 2
+#endif
+#ifndef QSMRT_TRACE_MINB
+#define QSMRT_TRACE_MINB 10
+#endif
+constexpr int TR_NODE_STEPS = QSMRT_NODE_STEPS;     // node steps per phase vote (measured: 1 -> 2 +8 %, 2 -> 4 +2 %, 4 -> 8 +2-3 %, 12 / 16 lose again)
+constexpr int TR_TRI_STEPS = QSMRT_TRI_STEPS;      // triangle tests per phase vote
 constexpr int CNT_SET = 32;     // distinct (geometry, t) pairs a lane can hold before it defers to the exact slow path
 
 __device__ __forceinline__ void ld256u(const void *p, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
@@ -136,7 +145,7 @@ __device__ __forceinline__ float qhi(uint32_t w) { return __uint_as_float(__byte
 // is the binding resource, profiles/README.md).  The ray's slab constants are folded with the grid:
 // t = (2^23 + q) * (cell/d) - (2^23 * cell/d - (glo - o)/d), so the slab code is unchanged.
 template <int MODE, bool COUNTERS, bool QUANT>
-__global__ void __launch_bounds__(TR_BLOCK, 10)
+__global__ void __launch_bounds__(TR_BLOCK, QSMRT_TRACE_MINB)
 k_trace5(const TraceArgs A)
 {
     constexpr bool CLOSEST = MODE == 0 || MODE == 3 || MODE == 5;
