@@ -64,6 +64,20 @@ kats.append(dict(name="kat7_cylinder", mesh=dict(v=cv.tolist(), t=ct.tolist()),
                  list=dict(ray_splits=[0, 2, 4, 5, 5], t_hit=[5 - x, 5 + x, 4.0, 6.0, 1.0]),
                  cast=dict(t_hit=[5 - x, 4.0, 1.0, INF])))
 
+# KAT-9: Open3D test_raycasting_scene.py::test_compute_closest_points (as recalled): the triangle of KAT-1, one query
+# above its interior and one beyond the vertex (1,1,0); uv convention p = (1-u-v) v0 + u v1 + v v2
+kats.append(dict(name="kat9_closest_points", mesh=dict(v=tri_v, t=tri_t),
+                 points=[[0.2, 0.1, 1], [10, 10, 10], [0.5, -2.0, 0.0]],
+                 closest=dict(points=[[0.2, 0.1, 0], [1, 1, 0], [0.5, 0, 0]], geometry_ids=[0, 0, 0], primitive_ids=[0, 0, 0],
+                              primitive_uvs=[[0.1, 0.1], [0, 1], [0.5, 0]], primitive_normals=[[0, 0, 1]] * 3),
+                 distance=[1.0, math.sqrt(81 + 81 + 100), 2.0]))
+# KAT-10: Open3D test_compute_distance / test_compute_occupancy / test_compute_signed_distance (as recalled): unit box,
+# its centre and a point outside one corner; plus a point 0.25 under a face and one over an edge
+kats.append(dict(name="kat10_box_distance_occupancy", mesh=dict(v=bv.tolist(), t=bt.tolist()),
+                 points=[[0.5, 0.5, 0.5], [-0.5, -0.5, -0.5], [0.5, 0.5, 0.75], [0.5, 1.5, 1.5]],
+                 distance=[0.5, math.sqrt(0.75), 0.25, math.sqrt(0.5)], occupancy=[1.0, 0.0, 1.0, 0.0],
+                 signed_distance=[-0.5, math.sqrt(0.75), -0.25, math.sqrt(0.5)]))
+
 # KAT-8: pinhole camera (Open3D CreateRaysPinhole): fov 90, eye (0,0,-1) looking at the origin
 kats.append(dict(name="kat8_pinhole", pinhole=dict(fov_deg=90, center=[0, 0, 0], eye=[0, 0, -1], up=[0, 1, 0],
                                                      width_px=4, height_px=2),

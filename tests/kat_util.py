@@ -31,6 +31,22 @@ def check_kat(kat, scene_factory):
     s = scene_factory()
     gid = s.add_triangles(np.asarray(kat["mesh"]["v"], np.float32), np.asarray(kat["mesh"]["t"], np.uint32))
     assert gid == 0
+    if "points" in kat:
+        q = np.asarray(kat["points"], np.float32)
+        if "closest" in kat:
+            c, exp = s.compute_closest_points(q), kat["closest"]
+            np.testing.assert_allclose(_np(c["points"]), np.asarray(exp["points"]), rtol=RTOL, atol=1e-7, err_msg=kat["name"])
+            for key in ("geometry_ids", "primitive_ids"):
+                assert np.array_equal(_np(c[key]).astype(np.int64), np.asarray(exp[key], np.int64)), (kat["name"], key)
+            np.testing.assert_allclose(_np(c["primitive_uvs"]), np.asarray(exp["primitive_uvs"]), rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(_np(c["primitive_normals"]), np.asarray(exp["primitive_normals"]), rtol=RTOL, atol=1e-7)
+        if "distance" in kat:
+            np.testing.assert_allclose(_np(s.compute_distance(q)), np.asarray(kat["distance"]), rtol=RTOL, err_msg=kat["name"])
+        if "occupancy" in kat:
+            assert _np(s.compute_occupancy(q)).tolist() == kat["occupancy"], kat["name"]
+        if "signed_distance" in kat:
+            np.testing.assert_allclose(_np(s.compute_signed_distance(q)), np.asarray(kat["signed_distance"]), rtol=RTOL, err_msg=kat["name"])
+        return
     rays = np.asarray(kat["rays"], np.float32)
     if "cast" in kat:
         ans = s.cast_rays(rays)

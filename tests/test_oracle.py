@@ -36,6 +36,18 @@ class _ModeScene:
     def list_intersections(self, r):
         return self.s.list_intersections(r, self.mode)
 
+    def compute_closest_points(self, q):
+        return self.s.compute_closest_points(q, self.mode)
+
+    def compute_distance(self, q):
+        return self.s.compute_distance(q, self.mode)
+
+    def compute_occupancy(self, q):
+        return self.s.compute_occupancy(q, self.mode)
+
+    def compute_signed_distance(self, q):
+        return self.s.compute_signed_distance(q, self.mode)
+
 
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("kat", [k for k in KATS if "mesh" in k], ids=lambda k: k["name"])
