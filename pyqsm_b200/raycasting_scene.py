@@ -63,6 +63,17 @@ def _mesh_arrays(mesh):
     return get(mesh.vertex, "positions"), get(mesh.triangle, "indices")
 
 
+def _to_host(t: torch.Tensor) -> torch.Tensor:
+    """Device tensor -> CPU tensor.  Larger results land in page-locked memory (torch's caching host allocator keeps
+    the blocks), which roughly doubles the PCIe rate of this copy and of a later copy back to the device --
+    ``create_rays_pinhole`` -> ``cast_rays`` is the reference's own sequence (``ray_casting.py:222-223``)."""
+    if t.device.type != "cuda" or t.numel() * t.element_size() < (1 << 18):
+        return t.cpu()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t)
+    return host
+
+
 def _occupancy_directions(nsamples: int):
     """(1,1,1) first (the single-sample direction), then a fixed seeded set of unit vectors."""
     dirs = [(1.0, 1.0, 1.0)]
@@ -188,7 +199,7 @@ class RaycastingScene:
     def _out(self, t: torch.Tensor) -> torch.Tensor:
         if self.output_device.type == "cuda":
             return t
-        return t.cpu()
+        return _to_host(t)
 
     # -------------------------------------------------------------- queries
     def cast_rays(self, rays, nthreads: int = 0, grid_width: int = 0) -> dict:
@@ -420,7 +431,7 @@ class RaycastingScene:
             _lib.check(L.qsmrt_gen_pinhole_rays(_ptr(rays), w, h, Kc, Ec, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         if device is not None and torch.device(device).type == "cuda":
             return rays
-        return rays.cpu()
+        return _to_host(rays)
 
 
 def _np64(x):
