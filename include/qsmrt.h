@@ -231,6 +231,9 @@ int qsmrt_debug_set_climb_capacity(int items);
 /* The next commits use the 32-byte quantised nodes when 6 grid cells <= frac x the mean leaf-box diagonal
  * (default 0.15; <= 0 restores it).  A/B hook: results are identical either way. */
 int qsmrt_debug_set_quant_threshold(float frac);
+/* Closest-point batches of up to max_points queries use one warp per query (default 16384; 0 = always the
+ * one-thread-per-query kernel).  Results are identical. */
+int qsmrt_debug_set_cp_warp_max(int max_points);
 
 /* Tuning hook for A/B measurements: 1 = one independent loop per thread (the
  * first kernel, kept as the simple reference), 2 = the persistent warp-uniform

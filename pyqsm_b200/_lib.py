@@ -63,6 +63,7 @@ SYMBOLS = {
     "qsmrt_debug_set_keep_binary_nodes": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_climb_capacity": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_quant_threshold": (C.c_int, [C.c_float]),
+    "qsmrt_debug_set_cp_warp_max": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),
     "qsmrt_debug_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "qsmrt_debug_set_sort": (C.c_int, [C.c_int]),

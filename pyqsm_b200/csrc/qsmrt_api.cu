@@ -584,6 +584,12 @@ int qsmrt_release_cached_memory(void)
     return 0;
 }
 
+int qsmrt_debug_set_cp_warp_max(int max_points)
+{
+    g_trv_cp_warp_max = max_points < 0 ? 0 : max_points;
+    return 0;
+}
+
 int qsmrt_debug_set_quant_threshold(float frac)
 {
     g_quant_frac = frac > 0.0f ? frac : 0.15f;

@@ -753,10 +753,110 @@ inline unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block -
 
 } // namespace
 
+// Closest point, one WARP per query: for the small batches the reference makes (256 random points,
+// ray_casting.py:248-250) the per-thread kernel above is one long dependent chain -- 0.6 ms for 256 points, set by the
+// slowest query.  Here a warp shares one stack and takes up to 32 entries per round: every lane expands its node
+// (two child boxes against the warp's best distance so far) or tests its leaf, the hit children are pushed with
+// ballot-compacted offsets, the best distance is min-reduced across the lanes.  The winner is chosen by the same
+// rule (distance, then lowest geometry / primitive), so the answer is the one the per-thread kernel gives.
+constexpr int CPW_STACK = 2048;          // entries per warp; above CPW_STACK - 256 the warp goes depth-first, which needs <= height (<= 160 here) more
+constexpr int CPW_WARPS = TR_BLOCK / 32;
+
+__global__ void __launch_bounds__(TR_BLOCK)
+k_closest_points_warp(SceneView sc, const float *__restrict__ pts, uint64_t N, float *__restrict__ closest, float *__restrict__ dist,
+                      uint32_t *__restrict__ geom, uint32_t *__restrict__ prim, float2 *__restrict__ uv, float *__restrict__ nrm)
+{
+    __shared__ int wstack[CPW_WARPS][CPW_STACK];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t i = blockIdx.x * (uint64_t)CPW_WARPS + w;
+    if (i >= N) return;                                  // warp-uniform
+    int *stk = wstack[w];
+    const f3 p = { pts[3 * i], pts[3 * i + 1], pts[3 * i + 2] };
+    CpBest best{ INFINITY, f3{ 0.0f, 0.0f, 0.0f }, 0.0f, 0.0f, QSMRT_INVALID, QSMRT_INVALID, 0u };
+    float wbest = INFINITY;                              // min over the lanes' best.d2 (pruning bound)
+    int sp = 0;
+    if (sc.ntris) { if (lane == 0) stk[0] = 0; sp = 1; }
+    __syncwarp();
+    while (sp > 0) {
+        const int take = sp > CPW_STACK - 256 ? 1 : min(sp, 32);
+        const bool have = lane < take;
+        const int cur = have ? stk[sp - 1 - lane] : 0;
+        sp -= take;
+        __syncwarp();
+        int c0 = 0, c1 = 0;
+        bool h0 = false, h1 = false;
+        if (have) {
+            if (cur >= 0) {
+                float4 a, b, c; int4 d;
+                load_node(sc.nodes, cur, a, b, c, d);
+                const float d0 = box_dist2(a.x, a.y, a.z, a.w, c.x, c.y, p);
+                const float d1 = box_dist2(b.x, b.y, b.z, b.w, c.z, c.w, p);
+                h0 = d0 <= wbest; h1 = d1 <= wbest;
+                // the nearer child is pushed last, so the next round's lane 0 (top of the stack) descends towards the point
+                const bool swap = h0 && h1 && d0 < d1;
+                c0 = swap ? d.y : d.x; c1 = swap ? d.x : d.y;
+                if (swap) { const bool t_ = h0; h0 = h1; h1 = t_; }
+            } else {
+                const uint32_t ref = (uint32_t)~cur, first = ref >> 2, count = (ref & 3u) + 1u;
+                for (uint32_t k = 0; k < count; ++k) {
+                    float4 p0, p1, p2;
+                    load_tri(sc.tris, first + k, p0, p1, p2);
+                    f3 q; float u, v;
+                    cp_triangle(p0, p1, p2, p, q, u, v);
+                    const f3 df = f3sub(q, p);
+                    const float d2 = f3dot(df, df);
+                    const uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
+                    const bool better = (d2 < best.d2) | ((d2 == best.d2) & ((pg < best.geom) | ((pg == best.geom) & (pp < best.prim))));
+                    if (better) { best.d2 = d2; best.q = q; best.u = u; best.v = v; best.geom = pg; best.prim = pp; best.tri = first + k; }
+                }
+            }
+        }
+        // tighten the bound, then push the hit children compacted: first every lane's c0, then every lane's c1
+        float m = best.d2;
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
+        wbest = m;
+        const unsigned m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
+        const unsigned lt = (1u << lane) - 1u;
+        if (h0) stk[sp + __popc(m0 & lt)] = c0;
+        if (h1) stk[sp + __popc(m0) + __popc(m1 & lt)] = c1;
+        sp += __popc(m0) + __popc(m1);
+        __syncwarp();
+    }
+    // winner: smallest (d2, geometry, primitive) over the lanes
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(FULL, best.d2, o);
+        const uint32_t og = __shfl_xor_sync(FULL, best.geom, o), op = __shfl_xor_sync(FULL, best.prim, o), ot = __shfl_xor_sync(FULL, best.tri, o);
+        const float oqx = __shfl_xor_sync(FULL, best.q.x, o), oqy = __shfl_xor_sync(FULL, best.q.y, o), oqz = __shfl_xor_sync(FULL, best.q.z, o);
+        const float ou = __shfl_xor_sync(FULL, best.u, o), ov = __shfl_xor_sync(FULL, best.v, o);
+        const bool better = (od < best.d2) | ((od == best.d2) & ((og < best.geom) | ((og == best.geom) & (op < best.prim))));
+        if (better) { best.d2 = od; best.geom = og; best.prim = op; best.tri = ot; best.q = f3{ oqx, oqy, oqz }; best.u = ou; best.v = ov; }
+    }
+    if (lane != 0) return;
+    const bool ok = best.prim != QSMRT_INVALID;
+    if (closest) { closest[3 * i] = best.q.x; closest[3 * i + 1] = best.q.y; closest[3 * i + 2] = best.q.z; }
+    if (dist) dist[i] = ok ? __fsqrt_rn(best.d2) : INFINITY;
+    if (geom) geom[i] = best.geom;
+    if (prim) prim[i] = best.prim;
+    if (uv) uv[i] = make_float2(best.u, best.v);
+    if (nrm) {
+        float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (ok) {
+            float4 p0, p1, p2;
+            load_tri(sc.tris, best.tri, p0, p1, p2);
+            f3 Ng = f3cross(f3{ p2.x, p2.y, p2.z }, f3{ p1.x, p1.y, p1.z });
+            float inv = __fdiv_rn(1.0f, __fsqrt_rn(f3dot(Ng, Ng)));
+            nx = __fmul_rn(Ng.x, inv); ny = __fmul_rn(Ng.y, inv); nz = __fmul_rn(Ng.z, inv);
+        }
+        nrm[3 * i] = nx; nrm[3 * i + 1] = ny; nrm[3 * i + 2] = nz;
+    }
+}
+
 // --------------------------------------------------------------- launchers
 int g_trv_variant = 2;      // 1 = one independent loop per thread, 2 = persistent warp-uniform kernel (ships)
 int g_trv_tuning[4] = { 12, 16, 1, 0 }; // refill, want, tri_min, counters -- tuned on C2 (profiles/r01_tuning.txt)
 unsigned long long *g_trv_stats_dev = nullptr;
+int g_trv_cp_warp_max = 16384;          // closest-point queries up to this many points run one warp per query (qsmrt_debug_set_cp_warp_max)
 int g_trv_node_path = 0;                // 0 LSU 256-bit loads, 1 TEX, 2 half/half (qsmrt_debug_set_node_path)
 
 // work cursors of the persistent kernels: a per-device ring so launches in flight never share one
@@ -1022,6 +1122,9 @@ int trv_closest_points(const SceneView &sc, const float *pts, uint64_t N, float 
                        uint32_t *prim, float *uv, float *nrm, cudaStream_t st)
 {
     if (N == 0) return 0;
+    if (N <= (uint64_t)g_trv_cp_warp_max && sc.height + 2u <= 160u)       // small batch: one warp per query (latency), else one thread (throughput)
+        k_closest_points_warp<<<(unsigned)((N + CPW_WARPS - 1) / CPW_WARPS), TR_BLOCK, 0, st>>>(sc, pts, N, closest, dist, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
+    else
     k_closest_points<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, pts, N, closest, dist, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
     CUDA_TRY(cudaGetLastError());
     return 0;

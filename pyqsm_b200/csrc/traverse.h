@@ -6,6 +6,7 @@ struct HitRec { float t, u, v; uint32_t geom, prim; };   // 20-byte raw hit (lis
 
 extern int g_trv_variant;
 extern int g_trv_node_path;
+extern int g_trv_cp_warp_max;
 extern int g_trv_tuning[4];
 extern unsigned long long *g_trv_stats_dev;
 int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,

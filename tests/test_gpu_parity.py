@@ -734,3 +734,31 @@ def test_occupancy_majority_vote(RS):
     one = h.compute_occupancy(qi, nsamples=1).numpy() > 0
     five = h.compute_occupancy(qi, nsamples=5).numpy() > 0
     assert one.mean() < 0.9 and five.mean() > one.mean()
+
+
+def test_closest_points_warp_and_thread_kernels_agree(RS, oracle_mod):
+    """Small closest-point batches run one warp per query, large ones one thread per query: same answers, and the
+    oracle's, on the C1 tree (points inside, near and far outside the mesh)."""
+    from pyqsm_b200 import _lib
+    L = _lib.load()
+    v, t = syn.qsm_tree_mesh(seed=1, n_cylinders=60)
+    g = RS()
+    g.add_triangles(v, t)
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v, t)
+    rng = np.random.default_rng(11)
+    lo, hi = v.min(0), v.max(0)
+    q = np.concatenate([rng.uniform(lo, hi, size=(3000, 3)), rng.uniform(lo - 30, hi + 30, size=(1500, 3)),
+                        v[rng.integers(0, len(v), 500)] + rng.normal(0, 1e-3, size=(500, 3))]).astype(np.float32)
+    a = {k: x.numpy() for k, x in g.compute_closest_points(q).items()}
+    _lib.check(L.qsmrt_debug_set_cp_warp_max(0))
+    try:
+        b = {k: x.numpy() for k, x in g.compute_closest_points(q).items()}
+    finally:
+        _lib.check(L.qsmrt_debug_set_cp_warp_max(16384))
+    ref = o.compute_closest_points(q, 1)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+        if k in ref:
+            assert np.array_equal(a[k], ref[k]), k
+    assert np.array_equal(g.compute_distance(q).numpy(), ref["distance"]) if "distance" in ref else True
