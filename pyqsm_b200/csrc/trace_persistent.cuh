@@ -110,17 +110,15 @@ struct TraceArgs {
     int multi_geom;     // > 1 geometry: the set also keeps geometry ids
 };
 
-#ifndef QSMRT_NODE_STEPS
-#define QSMRT_NODE_STEPS 8
-#endif
-#ifndef QSMRT_TRI_STEPS
-#define QSMRT_TRI_STEPS 2
-#endif
 #ifndef QSMRT_TRACE_MINB
 #define QSMRT_TRACE_MINB 10
 #endif
-constexpr int TR_NODE_STEPS = QSMRT_NODE_STEPS;     // node steps per phase vote (measured: 1 -> 2 +8 %, 2 -> 4 +2 %, 4 -> 8 +2-3 %, 12 / 16 lose again)
-constexpr int TR_TRI_STEPS = QSMRT_TRI_STEPS;      // triangle tests per phase vote
+// Node steps per phase vote (the vote only decides the phase, so voting less often saves the loop control all 32
+// lanes execute).  Measured on one box: 1 -> 2 +8 %, 2 -> 4 +2 %; 4 -> 8 another +2-3 % for cast_rays (whose retire
+// path -- 32 B of results, uv and normal recomputed -- profits from larger refill batches) but -5 ... -8 % for the
+// fused sun / sky kernels and the small-scene count, whose lanes retire cheaply and want prompt refills; 12 / 16 lose.
+template <int MODE> struct NodeSteps { static constexpr int value = MODE == 0 ? 8 : 4; };
+constexpr int TR_TRI_STEPS = 2;      // triangle tests per phase vote (1: -1.5 %, 3: same)
 constexpr int CNT_SET = 32;     // distinct (geometry, t) pairs a lane can hold before it defers to the exact slow path
 
 __device__ __forceinline__ void ld256u(const void *p, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
@@ -267,10 +265,10 @@ k_trace5(const TraceArgs A)
                     atomicAdd(&A.stats[6], (unsigned long long)__popc(m_done));
                 }
             }
-            // TR_NODE_STEPS node steps per vote: the vote only decides the phase, so skipping every other one
+            // NodeSteps<MODE> node steps per vote: the vote only decides the phase, so skipping every other one
             // just delays a phase change by one step and saves the loop-control instructions all 32 lanes execute
 #pragma unroll
-            for (int rep = 0; rep < TR_NODE_STEPS; ++rep) {
+            for (int rep = 0; rep < NodeSteps<MODE>::value; ++rep) {
             const bool in_ = (unsigned)cur < (unsigned)TR_SENTINEL;
             const bool pk_ = tri_i < tri_end;
             if (in_) {
