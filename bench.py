@@ -110,16 +110,18 @@ class ClockSampler:
 
 
 def angles_for(rank, world, nsteps):
-    """Solar angles of one rank.  The 8 x 8 sweep is sharded by AZIMUTH: at step s every rank casts elevation s % 8
-    at its own azimuth ((s // 8) * world + rank + s) % 8, so the ranks of a job do equal work per step (cost follows
-    the elevation: a low sun crosses more canopy) and N in {1, 2, 4, 8} ranks partition the 64 angles exactly."""
+    """Solar angles of one rank.  The 8 x 8 sweep is sharded by AZIMUTH: step s = 8 j + e casts elevation e at azimuth
+    index (rank * (8 / world) + j + e) mod 8.  The ranks of a step are 360 / world degrees apart -- for 2 and 4 ranks
+    the same view of the (x/y symmetric) canopy and its ray grid, i.e. equal work per step -- and every rank walks
+    through all azimuths as the elevation changes, so axis-aligned and diagonal views (a few per cent apart in cost)
+    are mixed evenly in any run of steps.  N in {1, 2, 4, 8} ranks partition the 64 angles exactly."""
     from pyqsm_b200 import synthetic as syn
     sweep = syn.hemisphere_sweep()                      # index = elevation * 8 + azimuth
-    per = max(1, 8 // world)
+    stride = max(1, 8 // world)
     out = []
     for s in range(nsteps):
-        e, j = s % 8, (s // 8) % per
-        out.append(sweep[e * 8 + (j * world + rank + e) % 8])
+        e, j = s % 8, s // 8
+        out.append(sweep[e * 8 + (rank * stride + j + e) % 8])
     return out
 
 
@@ -239,6 +241,9 @@ def run_ours(args):
 
     for s in range(args.warmup):
         step(s)
+    if world > 1:
+        # warm the collective the timed region ends with: NCCL sets up an all-reduce's channels on its first call
+        dist.all_reduce(torch.zeros_like(exposure))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
