@@ -113,6 +113,51 @@ def test_oracle_vs_exact_float64(orc):
     np.testing.assert_allclose(a["t_hit"][m], et[m], rtol=1e-5)
 
 
+def _exact_point_triangle(p, a, b, c):
+    """float64 closest point of triangle abc to p by a formulation unlike Ericson's region walk: the plane
+    projection if it falls inside, else the nearest of the three edge segments."""
+    n = np.cross(b - a, c - a)
+    nn = n @ n
+    cands = []
+    if nn > 0:
+        q = p - n * ((p - a) @ n) / nn
+        w = [np.cross(b - a, q - a) @ n, np.cross(c - b, q - b) @ n, np.cross(a - c, q - c) @ n]
+        if min(w) >= 0:
+            cands.append(q)
+    for u, v_ in ((a, b), (b, c), (c, a)):
+        d = v_ - u
+        dd = d @ d
+        s_ = 0.0 if dd == 0 else min(1.0, max(0.0, ((p - u) @ d) / dd))
+        cands.append(u + s_ * d)
+    return min(cands, key=lambda x: (x - p) @ (x - p))
+
+
+def test_oracle_closest_point_vs_exact_float64(orc):
+    """The oracle's fp32 closest-point query (Ericson regions, as in the Embree tutorial Open3D uses) against an
+    independent float64 formulation, brute force over all triangles: distance to 1e-5, the same triangle unless a
+    second one is as close, and closest point = (1-u-v) v0 + u v1 + v v2 with the returned uv."""
+    v, t = syn.qsm_tree_mesh(seed=5, n_cylinders=2)
+    rng = np.random.default_rng(2)
+    lo, hi = v.min(0), v.max(0)
+    q = np.concatenate([rng.uniform(lo - 1, hi + 1, size=(40, 3)), v[rng.integers(0, len(v), 15)] + rng.normal(0, 0.02, size=(15, 3))]).astype(np.float32)
+    s = orc.OracleScene()
+    s.add_triangles(v, t)
+    for mode in (0, 1):
+        a = s.compute_closest_points(q, mode)
+        V = v.astype(np.float64)
+        for i, p in enumerate(q.astype(np.float64)):
+            d2 = np.array([((_exact_point_triangle(p, V[k[0]], V[k[1]], V[k[2]]) - p) ** 2).sum() for k in t])
+            best = np.sqrt(d2.min())
+            np.testing.assert_allclose(np.linalg.norm(a["points"][i].astype(np.float64) - p), best, rtol=1e-5, atol=1e-6)
+            pid = int(a["primitive_ids"][i])
+            assert np.sqrt(d2[pid]) <= best * (1 + 1e-5) + 1e-6
+            k = t[pid]
+            u, w = a["primitive_uvs"][i].astype(np.float64)
+            rec = (1 - u - w) * V[k[0]] + u * V[k[1]] + w * V[k[2]]
+            np.testing.assert_allclose(rec, a["points"][i], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(a["geometry_ids"], np.zeros(len(q), np.uint32))
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_brute_equals_bvh(orc, seed):
     rng = np.random.default_rng(seed)
