@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define QSMRT_INVALID_ID 0xFFFFFFFFu /* RaycastingScene.INVALID_ID */
-#define QSMRT_ABI_VERSION 1
+#define QSMRT_ABI_VERSION 2
 
 typedef struct qsmrt_scene qsmrt_scene;
 
@@ -61,6 +61,46 @@ int qsmrt_scene_destroy(qsmrt_scene *scene);
  * process, default 1024) and reused, because the reference builds a new scene per call and cudaMalloc / cudaFree
  * dominated small scenes.  This hands them back to the driver (like torch.cuda.empty_cache()).  Synchronises. */
 int qsmrt_release_cached_memory(void);
+
+/* Per-scene options.  Open3D's constructor takes nthreads / device
+ * (ray_casting.py:65,...: rcs()); everything else here is tuning and test
+ * hooks, stored IN THE SCENE: builder options are read at the next commit (a
+ * changed one marks the scene for rebuilding), traversal options at every
+ * launch.  No process-global state; scenes with different options can be used
+ * from different threads. */
+enum qsmrt_option {
+    /* builder */
+    QSMRT_OPT_LEAF_MAX = 1,            /* triangles per collapsed leaf, 1..4 (default 2) */
+    QSMRT_OPT_KEEP_BINARY_NODES = 2,   /* 1: keep the complete 32-byte binary node array for qsmrt_debug_get_build */
+    QSMRT_OPT_QUANT_THRESHOLD = 3,     /* 32-byte quantised nodes when 6 grid cells <= value x mean leaf-box diagonal (default 0.15; <= 0 restores it) */
+    QSMRT_OPT_CLIMB_CAPACITY = 4,      /* cap of the hierarchy kernel's hand-over list (0 = default); test hook for its overflow path */
+    QSMRT_OPT_SORT_VARIANT = 5,        /* 0 = histogram / scan / scatter per radix pass, 1 = one kernel per pass with decoupled look-back (default) */
+    /* traversal (results are identical for every setting) */
+    QSMRT_OPT_QUANTISED_NODES = 16,    /* 0 forces the 64-byte fp32 nodes even where the 32-byte nodes qualify */
+    QSMRT_OPT_TRAVERSAL_VARIANT = 17,  /* 1 = one independent loop per thread (simple reference), 2 = persistent warp-uniform kernel (default) */
+    QSMRT_OPT_REFILL = 18,             /* persistent kernel: idle lanes that trigger a refill (default 12) */
+    QSMRT_OPT_WANT = 19,               /* ... node phase ends below this many searching lanes (default 16) */
+    QSMRT_OPT_TRI_MIN = 20,            /* ... triangle-phase early-exit threshold (default 1) */
+    QSMRT_OPT_COUNTERS = 21,           /* 1: cast_rays launches count what they fetch (qsmrt_scene_get_counters) */
+    QSMRT_OPT_NODE_PATH = 22,          /* node fetch path: 0 = 256-bit LSU loads (default), 1 = texture, 2 = half and half */
+    QSMRT_OPT_CP_WARP_MAX = 23         /* closest-point batches up to this many queries use one warp per query (default 16384) */
+};
+int qsmrt_scene_set_option(qsmrt_scene *scene, int key, double value);
+int qsmrt_scene_get_option(qsmrt_scene *scene, int key, double *value);
+/* The 16 counters of the scene's last counted cast_rays launch (QSMRT_OPT_COUNTERS): [0] node records fetched,
+ * [1] triangle tests, [2] node-phase iterations, [3..6] lanes per iteration that step / are idle / hold a second
+ * leaf / finished descending, [7] triangle-phase iterations, [8] lanes testing a triangle.  Synchronises. */
+int qsmrt_scene_get_counters(qsmrt_scene *scene, uint64_t out[16]);
+
+/* Scene files (the reference pickles its built search structures next to the
+ * data: pyQSM/utils/io.py:44-60, tree_isolation.py:114,136).  save writes the
+ * geometries as added and, with QSMRT_SAVE_BVH, the committed LBVH (traversal
+ * nodes, quantised twin, triangle records, order, keys, grid); load creates a
+ * new scene from the file -- committed if the file holds the BVH, otherwise
+ * built by the first query (the build is deterministic: same tree either way). */
+#define QSMRT_SAVE_BVH 1u
+int qsmrt_scene_save(qsmrt_scene *scene, const char *path, uint32_t flags);
+int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out);
 
 /* scene.add_triangles(mesh)  -- ray_casting.py:66,156,219,242,276,317.
  * Copies V x 3 float32 positions and T x 3 uint32 indices (Open3D copies
@@ -110,10 +150,19 @@ int qsmrt_cast_rays_host(qsmrt_scene *scene, const float *rays_host, uint64_t N,
                          float *t_hit, uint32_t *geometry_ids, uint32_t *primitive_ids,
                          float *primitive_uvs, float *primitive_normals);
 
+/* cast_rays with HOST rays where every result either goes to host memory
+ * (host_out[k]), stays on the device for a later fetch (dev_out[k], a
+ * full-length device array; wins over host_out[k]) or is skipped (both NULL).
+ * k = 0..4: t_hit, geometry_ids, primitive_ids, primitive_uvs,
+ * primitive_normals.  The reference only reads t_hit and primitive_ids
+ * (ray_casting.py:280-289,320-322): 8 instead of 32 bytes per ray cross PCIe. */
+int qsmrt_cast_rays_host_split(qsmrt_scene *scene, const float *rays_host, uint64_t N,
+                               void *const host_out[5], void *const dev_out[5]);
+
 /* scene.count_intersections(rays)  -- the engine under list_intersections
  * (ray_casting.py:168) and compute_occupancy (:69).  counts[N] int32.
- * Never synchronises: a ray with more distinct hits than the in-register set
- * holds is finished exactly by the same thread (one traversal per hit). */
+ * Never synchronises: a ray with more distinct hits than the on-chip set
+ * holds is finished exactly by a second kernel (one traversal per hit). */
 int qsmrt_count_intersections(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
                               int32_t *counts, void *stream);
 
@@ -121,6 +170,12 @@ int qsmrt_count_intersections(qsmrt_scene *scene, const float *rays_dev, uint64_
  * tnear < t <= tfar. */
 int qsmrt_test_occlusions(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
                           float tnear, float tfar, uint8_t *out, void *stream);
+
+/* The two calls above with HOST buffers, through the same three-stream pipe as
+ * qsmrt_cast_rays_host.  Synchronise. */
+int qsmrt_count_intersections_host(qsmrt_scene *scene, const float *rays_host, uint64_t N, int32_t *counts);
+int qsmrt_test_occlusions_host(qsmrt_scene *scene, const float *rays_host, uint64_t N,
+                               float tnear, float tfar, uint8_t *out);
 
 /* scene.list_intersections(rays)  -- ray_casting.py:168.  Two phases:
  *   _count  fills ray_splits[N+1] (int64, exclusive scan of the per-ray
@@ -161,6 +216,12 @@ int qsmrt_accumulate_hits(qsmrt_scene *scene, const uint32_t *geometry_ids,
                           const uint32_t *primitive_ids, uint64_t N,
                           uint32_t *tri_counts, void *stream);
 
+/* Per-vertex exposure from per-triangle exposure (ray_casting.py:289-292:
+ * hit_tris = triangles[prim_ids]; hit_vert_ids = np.unique(hit_tris)):
+ * vert_counts[v] += tri_counts[t] for the three corners of every triangle t
+ * (scene order, vertices numbered through the geometries in the order added). */
+int qsmrt_vertex_exposure(qsmrt_scene *scene, const uint32_t *tri_counts, uint32_t *vert_counts, void *stream);
+
 /* scene.compute_closest_points / compute_distance  (Open3D; the engine under
  * compute_signed_distance, ray_casting.py:250,255).  query points [N x 3]
  * float32 on the device.  closest[N x 3], distance[N] (inf for an empty
@@ -176,7 +237,7 @@ int qsmrt_closest_points(qsmrt_scene *scene, const float *points_dev, uint64_t N
 int qsmrt_signed_distance(qsmrt_scene *scene, const float *points_dev, uint64_t N,
                           float *distance, void *stream);
 
-/* Environmental drivers (README.md:131 "sunlight angle, cloud cover and rain
+/* Environmental drivers (README.md:127 "sunlight angle, cloud cover and rain
  * angle"; data/notes/methods.md:16,53-55): the rays are generated inside the
  * traversal kernel and the results reduced on the device, so no 24 B/ray of
  * input or 32 B/ray of output ever touches HBM.
@@ -188,17 +249,29 @@ int qsmrt_signed_distance(qsmrt_scene *scene, const float *points_dev, uint64_t 
  *   offset * normal; normals may be NULL) directions dir_begin ..
  *   dir_begin+dir_count-1 of a seeded uniform sample of the upper hemisphere
  *   (about +z) are tested for occlusion; unoccluded[p] += number of free
- *   directions.  Gap fraction = unoccluded / directions.
+ *   directions.  Gap fraction = unoccluded / directions.  Direction k of
+ *   point p is a hash of (seed, point_base + p, k): a block of points cut
+ *   out of a larger set (a rank's share, a test's subsample) sees the same
+ *   directions when point_base is the block's offset in that set.
  * qsmrt_gen_hemisphere_rays materialises exactly those rays
  *   (rays[n_points * dir_count][6]) for inspection and parity tests. */
 int qsmrt_sun_exposure(qsmrt_scene *scene, uint64_t nu, uint64_t nv, const float origin0[3],
                        const float du[3], const float dv[3], const float dir[3],
                        uint32_t *tri_counts, void *stream);
+/* A whole sweep in ONE launch: n_grids parallel grids, all nu x nv, grid a
+ * given by grids_host[a][12] = origin0, du, dv, dir (ordinary host memory).
+ * count_stride = 0 adds every grid into tri_counts[T]; otherwise grid a adds
+ * into tri_counts[a * count_stride + t].  Same counts as n_grids calls of
+ * qsmrt_sun_exposure, without their kernel tails and host round trips.
+ * Sweeps of one scene must be issued on one stream. */
+int qsmrt_sun_exposure_sweep(qsmrt_scene *scene, uint32_t n_grids, const float *grids_host,
+                             uint64_t nu, uint64_t nv, uint32_t *tri_counts, uint64_t count_stride,
+                             void *stream);
 int qsmrt_sky_visibility(qsmrt_scene *scene, const float *points_dev, const float *normals_dev,
-                         uint64_t n_points, uint64_t seed, float offset, uint32_t dir_begin,
+                         uint64_t n_points, uint64_t point_base, uint64_t seed, float offset, uint32_t dir_begin,
                          uint32_t dir_count, uint32_t *unoccluded, void *stream);
 int qsmrt_gen_hemisphere_rays(float *rays_dev, const float *points_dev, const float *normals_dev,
-                              uint64_t n_points, uint64_t seed, float offset, uint32_t dir_begin,
+                              uint64_t n_points, uint64_t point_base, uint64_t seed, float offset, uint32_t dir_begin,
                               uint32_t dir_count, void *stream);
 
 /* "Raycasting projection" of data/notes/methods.md:53-55 and
@@ -215,55 +288,21 @@ int qsmrt_peel_projection(qsmrt_scene *scene, uint64_t nu, uint64_t nv, const fl
 
 int qsmrt_get_stats(qsmrt_scene *scene, qsmrt_stats *out);
 
+/* Measurement utility (bench.py's roofline denominators): reads `bytes` of a
+ * device buffer `reps` times with the 256-bit loads the traversal kernel uses,
+ * on the current device.  Time it with events: a buffer well inside L2 gives
+ * the L2 -> SM read peak, one far above it the HBM read rate. */
+int qsmrt_util_read_sweep(const void *buf_dev, uint64_t bytes, uint32_t reps, uint32_t *sink_dev, void *stream);
+
 /* Builder introspection (parity tests of the LBVH builder; host outputs,
  * any may be NULL).  keys[T] uint64 sorted Morton keys; order[T] sorted
  * position -> input triangle; nodes[(2T-1) x 8] float32/int32 words of the
  * 32-byte binary nodes (lo.xyz,left,hi.xyz,right; internal 0..T-2, leaves
  * after).  The builder only materialises the complete binary node array when
- * qsmrt_debug_set_keep_binary_nodes(1) was in force at the commit (the product
- * path writes the traversal nodes straight from registers); asking for `nodes`
- * otherwise is an error. */
+ * QSMRT_OPT_KEEP_BINARY_NODES was set at the commit (the product path writes
+ * the traversal nodes straight from registers); asking for `nodes` otherwise
+ * is an error. */
 int qsmrt_debug_get_build(qsmrt_scene *scene, uint64_t *keys, uint32_t *order, void *nodes);
-int qsmrt_debug_set_keep_binary_nodes(int keep);
-/* Caps the list of open subtrees the hierarchy kernel hands to the climb kernel (0 = default, triangles / 4 + 1024);
- * subtrees that do not fit climb inside the first kernel.  Test hook for that overflow path. */
-int qsmrt_debug_set_climb_capacity(int items);
-/* The next commits use the 32-byte quantised nodes when 6 grid cells <= frac x the mean leaf-box diagonal
- * (default 0.15; <= 0 restores it).  A/B hook: results are identical either way. */
-int qsmrt_debug_set_quant_threshold(float frac);
-/* Closest-point batches of up to max_points queries use one warp per query (default 16384; 0 = always the
- * one-thread-per-query kernel).  Results are identical. */
-int qsmrt_debug_set_cp_warp_max(int max_points);
-
-/* Tuning hook for A/B measurements: 1 = one independent loop per thread (the
- * first kernel, kept as the simple reference), 2 = the persistent warp-uniform
- * kernel (default).  Results are identical. */
-int qsmrt_debug_set_variant(int variant);
-
-/* Thresholds of the persistent kernel (refill_thresh idle lanes trigger a
- * refill; the node phase ends below want_thresh searching lanes; `speculate`
- * is the triangle-phase early-exit threshold tri_min) and its fetch
- * counters: with counters != 0 every cast_rays launch counts the node records
- * and triangles it actually fetched; qsmrt_debug_get_counters reads the last
- * launch's totals (synchronises). */
-int qsmrt_debug_set_tuning(int refill_thresh, int want_thresh, int speculate, int counters);
-int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out);
-/* All 16 counters of the last counted launch: [0] node fetches, [1] triangle
- * tests, [2] node-phase iterations, [3..6] lanes per iteration that step /
- * are idle / hold a second leaf / finished descending, [7] triangle-phase
- * iterations, [8] lanes testing a triangle. */
-int qsmrt_debug_get_census(uint64_t out[16]);
-/* Radix sort of the builder: 0 = histogram / scan / scatter kernels per pass,
- * 1 = one kernel per pass with decoupled look-back (default).  Same result. */
-int qsmrt_debug_set_sort(int variant);
-/* 0 forces the 64-byte fp32 nodes even where the 32-byte quantised nodes
- * qualify (A/B measurements; results are identical either way). */
-int qsmrt_debug_set_quantised_nodes(int allow);
-/* Node fetch path of the persistent kernel: 0 = 256-bit LSU loads (default),
- * 1 = texture fetches, 2 = half and half (L1 data-pipe experiment). */
-int qsmrt_debug_set_node_path(int path);
-/* Triangles per collapsed leaf (1..4) used by the next qsmrt_commit. */
-int qsmrt_debug_set_leaf_max(int leaf_max);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqsmrt.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -26,6 +26,14 @@ class Stats(C.Structure):
         ("leaf_max", C.c_uint32), ("bvh_height", C.c_uint32), ("quantised_nodes", C.c_uint32), ("full_sort", C.c_uint32),
     ]
 
+
+# enum qsmrt_option (include/qsmrt.h)
+OPT = {
+    "leaf_max": 1, "keep_binary_nodes": 2, "quant_threshold": 3, "climb_capacity": 4, "sort_variant": 5,
+    "quantised_nodes": 16, "traversal_variant": 17, "refill": 18, "want": 19, "tri_min": 20, "counters": 21,
+    "node_path": 22, "cp_warp_max": 23,
+}
+SAVE_BVH = 1
 
 # name -> (restype, argtypes); every symbol include/qsmrt.h declares
 _vp, _u64, _f = C.c_void_p, C.c_uint64, C.c_float
@@ -53,25 +61,24 @@ SYMBOLS = {
     "qsmrt_closest_points": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qsmrt_signed_distance": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "qsmrt_sun_exposure": (C.c_int, [_vp, _u64, _u64, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
-    "qsmrt_sky_visibility": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp, _vp]),
-    "qsmrt_gen_hemisphere_rays": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp]),
+    "qsmrt_sun_exposure_sweep": (C.c_int, [_vp, C.c_uint32, C.POINTER(_f), _u64, _u64, _vp, _u64, _vp]),
+    "qsmrt_sky_visibility": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "qsmrt_gen_hemisphere_rays": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _u64, _f, C.c_uint32, C.c_uint32, _vp]),
     "qsmrt_peel_projection": (C.c_int, [_vp, _u64, _u64, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), C.c_int, _vp,
                                         C.POINTER(C.c_double), C.POINTER(C.c_int), _vp]),
+    "qsmrt_util_read_sweep": (C.c_int, [_vp, _u64, C.c_uint32, _vp, _vp]),
     "qsmrt_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "qsmrt_debug_get_build": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qsmrt_release_cached_memory": (C.c_int, []),
-    "qsmrt_debug_set_keep_binary_nodes": (C.c_int, [C.c_int]),
-    "qsmrt_debug_set_climb_capacity": (C.c_int, [C.c_int]),
-    "qsmrt_debug_set_quant_threshold": (C.c_int, [C.c_float]),
-    "qsmrt_debug_set_cp_warp_max": (C.c_int, [C.c_int]),
-    "qsmrt_debug_set_variant": (C.c_int, [C.c_int]),
-    "qsmrt_debug_set_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "qsmrt_debug_set_sort": (C.c_int, [C.c_int]),
-    "qsmrt_debug_set_quantised_nodes": (C.c_int, [C.c_int]),
-    "qsmrt_debug_set_node_path": (C.c_int, [C.c_int]),
-    "qsmrt_debug_set_leaf_max": (C.c_int, [C.c_int]),
-    "qsmrt_debug_get_census": (C.c_int, [C.POINTER(C.c_uint64)]),
-    "qsmrt_debug_get_counters": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "qsmrt_scene_set_option": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "qsmrt_scene_get_option": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
+    "qsmrt_scene_get_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "qsmrt_scene_save": (C.c_int, [_vp, C.c_char_p, C.c_uint32]),
+    "qsmrt_scene_load": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_vp)]),
+    "qsmrt_cast_rays_host_split": (C.c_int, [_vp, _vp, _u64, C.POINTER(_vp), C.POINTER(_vp)]),
+    "qsmrt_count_intersections_host": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "qsmrt_test_occlusions_host": (C.c_int, [_vp, _vp, _u64, _f, _f, _vp]),
+    "qsmrt_vertex_exposure": (C.c_int, [_vp, _vp, _vp, _vp]),
 }
 
 

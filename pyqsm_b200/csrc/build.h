@@ -18,6 +18,9 @@ struct LbvhBuildArgs {
     const uint64_t *geom_offsets;   // [ngeoms+1] first triangle of each geometry
     uint32_t        ngeoms;
     int             leaf_max;       // 1..QSMRT_LEAF_MAX triangles per collapsed leaf
+    int             sort_variant;   // 0 classic (3 kernels per pass, 8 passes), 1 onesweep (decoupled look-back; ships)
+    int             climb_capacity; // > 0: cap of the climb work list (test hook for its overflow path)
+    float           quant_frac;     // 6 grid cells <= this share of the mean leaf diagonal -> 32-byte nodes
     // outputs / scratch (device)
     uint32_t   *bounds_ord;         // [6]
     BuildParams *params;
@@ -36,11 +39,8 @@ struct LbvhBuildArgs {
     cudaEvent_t ev_sort0, ev_sort1; // optional
 };
 
-extern int g_sort_variant;
-extern int g_climb_cap_override;
-extern float g_quant_frac;
 size_t lbvh_sort_scratch_bytes(uint64_t n);
 size_t lbvh_climb_bytes(uint64_t n);
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
-                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow = nullptr);
+                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant);
 int lbvh_build(const LbvhBuildArgs &args, cudaStream_t st);

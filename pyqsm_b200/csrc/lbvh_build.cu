@@ -888,7 +888,6 @@ __global__ void k_emit_single(const BNode *__restrict__ bn, TNode *__restrict__ 
 } // namespace
 
 // -------------------------------------------------------------- host side
-int g_sort_variant = 1;      // 0 classic (3 kernels per pass), 1 onesweep (decoupled look-back)
 
 size_t lbvh_sort_scratch_bytes(uint64_t n)
 {
@@ -903,22 +902,19 @@ size_t lbvh_sort_scratch_bytes(uint64_t n)
 size_t lbvh_climb_items(uint64_t n) { return (size_t)(n / 4 + 1024); }
 size_t lbvh_climb_bytes(uint64_t n) { return lbvh_climb_items(n) * sizeof(ClimbItem); }
 
-float g_quant_frac = 0.15f;      // qsmrt_debug_set_quant_threshold: 6 grid cells <= this share of the mean leaf diagonal -> 32-byte nodes
-int g_climb_cap_override = 0;    // qsmrt_debug_set_climb_capacity: shrink the climb list to exercise its overflow path
-int g_sort_min_onesweep = 0;     // keys from which the onesweep variant is used (qsmrt_debug_set_sort)
 
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
-                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow)
+                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant)
 {
     if (n == 0) return 0;
     uint32_t ntiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
     uint32_t *tile_hist = scratch, *digit_tot = scratch + (uint64_t)ntiles * 256;
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
-    if (g_sort_variant == 1 && n >= (uint64_t)g_sort_min_onesweep) {
+    if (sort_variant == 1) {
         const uint32_t os_tiles = (uint32_t)((n + OS_TILE - 1) / OS_TILE);
-        static const cudaError_t carve = cudaFuncSetAttribute(k_os_pass, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        (void)carve;            // OS_CTAS x 45 KB only fit with the largest shared-memory split
+        // OS_CTAS x 45 KB only fit with the largest shared-memory split (a per-device function attribute; setting it is idempotent)
+        CUDA_TRY(cudaFuncSetAttribute(k_os_pass, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         uint32_t *status = scratch, *ghist = scratch + 8ull * os_tiles * 256, *counters = ghist + 8 * 256;
         // With `overflow`: five passes over the top 40 bits, then k_sort_fixup orders the (short) runs of keys
         // that agree in them -- three fewer trips of 12 B per key through HBM for the same final order.
@@ -961,17 +957,17 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order);
     CUDA_TRY(cudaGetLastError());
     if (A.ev_sort0) CUDA_TRY(cudaEventRecord(A.ev_sort0, st));
-    if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st, A.full_sort ? nullptr : A.counters + 4)) return 1;
+    if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st, A.full_sort ? nullptr : A.counters + 4, A.sort_variant)) return 1;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
     if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
     const int keep = (A.keep_bnodes || n == 1) ? 1 : 0;
-    const unsigned work_cap = g_climb_cap_override > 0 ? std::min<unsigned>((unsigned)g_climb_cap_override, (unsigned)lbvh_climb_items(n))
+    const unsigned work_cap = A.climb_capacity > 0 ? std::min<unsigned>((unsigned)A.climb_capacity, (unsigned)lbvh_climb_items(n))
                                                        : (unsigned)lbvh_climb_items(n);
     unsigned *work_count = reinterpret_cast<unsigned *>(A.counters + 3);
     ClimbItem *work = reinterpret_cast<ClimbItem *>(A.climb_work);
     k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(
         A.verts, A.idx, (int64_t)n, A.keys, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
-        A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap, g_quant_frac);
+        A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap, A.quant_frac);
     k_hierarchy_climb<<<std::min((work_cap + CL_BLOCK - 1) / CL_BLOCK, 148u * 32u), CL_BLOCK, 0, st>>>(
         (int64_t)n, A.params, A.bnodes, A.flags, A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap);
     if (n == 1) k_emit_single<<<1, 1, 0, st>>>(A.bnodes, A.tnodes, A.qnodes, A.params, A.counters);

@@ -20,10 +20,7 @@
 #include "traverse.h"
 
 static thread_local char g_err[512] = "";
-static int g_allow_qnodes = 1;              // qsmrt_debug_set_quantised_nodes
-static bool g_keep_bnodes = false;          // qsmrt_debug_set_keep_binary_nodes
 constexpr int QSMRT_MAX_DEVICES = 64;
-static int g_leaf_max = 2;                  // triangles per leaf (qsmrt_debug_set_leaf_max); 2 measured best on C2
 
 void qsmrt_set_error(const char *fmt, ...)
 {
@@ -40,13 +37,22 @@ struct Geometry {
     uint64_t V = 0, T = 0;
 };
 
-struct HostPipe {            // staging for qsmrt_cast_rays_host
+struct HostPipe {            // device staging of the *_host entry points: rays in, up to 32 B/ray of results out
     static constexpr int NBUF = 3;
-    uint64_t chunk = 0;
-    float *rays[NBUF] = {}; float *t[NBUF] = {}; uint32_t *g[NBUF] = {}; uint32_t *p[NBUF] = {};
-    float *uv[NBUF] = {}; float *nrm[NBUF] = {};
+    uint64_t chunk = 0; size_t out_bytes = 0;       // rays per stage; result bytes per ray the staging holds
+    float *rays[NBUF] = {}; char *out[NBUF] = {};
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
     cudaEvent_t e_in[NBUF] = {}, e_run[NBUF] = {}, e_out[NBUF] = {};
+};
+
+// Builder options of a scene (qsmrt_scene_set_option), read at the next commit.
+struct BuildOptions {
+    int leaf_max = 2;            // triangles per collapsed leaf; 2 measured best on C2
+    int keep_bnodes = 0;         // materialise the complete 32-byte binary node array (builder-vs-oracle test)
+    float quant_frac = 0.15f;    // 32-byte nodes when 6 grid cells <= this share of the mean leaf diagonal
+    int climb_capacity = 0;      // > 0: cap of the climb work list (test hook)
+    int sort_variant = 1;        // 0 classic radix passes, 1 onesweep
+    int allow_qnodes = 1;        // traversal may read the 32-byte nodes when the build made them
 };
 
 struct qsmrt_scene {
@@ -63,11 +69,14 @@ struct qsmrt_scene {
     QNode *qnodes = nullptr; bool use_qnodes = false; float glo[3] = {}, cell[3] = {};
     BuildParams *params = nullptr;
     qsmrt_stats stats{};
+    BuildOptions bopt;
+    TrvState trv;
     cudaTextureObject_t node_tex = 0;
     // list_intersections cache between _count and _fill
     const float *list_rays = nullptr; uint64_t list_n = 0;
     int64_t *list_raw_off = nullptr; HitRec *list_raw = nullptr;
     HostPipe pipe;
+    float *sweep_dev = nullptr; uint32_t sweep_cap = 0;     // per-grid constants of qsmrt_sun_exposure_sweep
 };
 
 namespace {
@@ -169,7 +178,7 @@ void free_build(qsmrt_scene *s)
 void free_pipe(HostPipe &hp)
 {
     for (int b = 0; b < HostPipe::NBUF; ++b) {
-        dfree(hp.rays[b]); dfree(hp.t[b]); dfree(hp.g[b]); dfree(hp.p[b]); dfree(hp.uv[b]); dfree(hp.nrm[b]);
+        dfree(hp.rays[b]); dfree(hp.out[b]);
         if (hp.e_in[b]) cudaEventDestroy(hp.e_in[b]);
         if (hp.e_run[b]) cudaEventDestroy(hp.e_run[b]);
         if (hp.e_out[b]) cudaEventDestroy(hp.e_out[b]);
@@ -179,7 +188,24 @@ void free_pipe(HostPipe &hp)
     if (hp.s_run) cudaStreamDestroy(hp.s_run);
     if (hp.s_out) cudaStreamDestroy(hp.s_out);
     hp.s_in = hp.s_run = hp.s_out = nullptr;
-    hp.chunk = 0;
+    hp.chunk = 0; hp.out_bytes = 0;
+}
+
+// Read-bandwidth probe (qsmrt_util_read_sweep): every thread streams 32-byte chunks of the buffer, grid-stride,
+// `reps` times; XOR keeps the loads alive.  A buffer well inside the 126 MB L2 gives the L2 -> SM read peak the
+// traversal kernel's node / triangle fetches are measured against, a buffer far above it the HBM read rate.
+__global__ void __launch_bounds__(256)
+k_read_sweep(const uint4 *__restrict__ buf, uint64_t n32, uint32_t reps, uint32_t *sink)
+{
+    uint32_t acc = 0;
+    for (uint32_t r = 0; r < reps; ++r)
+        for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n32; i += (uint64_t)gridDim.x * 256ull) {
+            uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+            asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "l"(buf + 2 * i));
+            acc ^= w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+        }
+    if (acc == 0x9E3779B9u) *sink = acc;        // practically never: the compiler cannot drop the loads
 }
 
 __global__ void k_rebase_idx(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t n3, uint32_t add)
@@ -253,12 +279,22 @@ k_cylinders(const float *__restrict__ rec, uint64_t n, uint32_t res, uint32_t sp
     }
 }
 
-int use_device(qsmrt_scene *s)
-{
-    if (!s) FAIL("null scene");
-    CUDA_TRY(cudaSetDevice(s->device));
-    return 0;
-}
+// Every ABI entry runs on the scene's device and hands the caller's current device back on return (a process
+// that drives several GPUs -- or torch, whose current device we must not move -- never sees it change).
+struct DeviceGuard {
+    int prev = -1; cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) err = cudaSetDevice(dev);
+        if (prev == dev) prev = -1;                 // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define SCENE_ENTER(s) \
+    if (!(s)) FAIL("null scene"); \
+    DeviceGuard device_guard_((s)->device); \
+    if (device_guard_.err != cudaSuccess) FAIL("cudaSetDevice(%d): %s", (s)->device, cudaGetErrorString(device_guard_.err))
 
 int check_rays(const float *rays, uint64_t N)
 {
@@ -269,9 +305,9 @@ int check_rays(const float *rays, uint64_t N)
 
 SceneView view_of(qsmrt_scene *s)
 {
-    if (g_trv_node_path != 0 && !s->node_tex && s->tnodes) {
+    if (s->trv.opt.node_path != 0 && !s->node_tex && s->tnodes) {
         // float4 texture view of the node array, made on first use: only the TEX-path experiment
-        // (qsmrt_debug_set_node_path) reads it, and creating it cost every commit a driver call
+        // (QSMRT_OPT_NODE_PATH) reads it, and creating it cost every commit a driver call
         cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = s->tnodes;
         rd.res.linear.desc = cudaCreateChannelDesc<float4>();
         rd.res.linear.sizeInBytes = std::max<uint64_t>(s->ntris - 1, 1) * sizeof(TNode);
@@ -281,44 +317,41 @@ SceneView view_of(qsmrt_scene *s)
     SceneView v;
     v.nodes = s->tnodes; v.tris = s->tris; v.ntris = (uint32_t)s->ntris; v.height = s->stats.bvh_height;
     v.node_tex = s->node_tex;
-    v.qnodes = (s->use_qnodes && g_allow_qnodes) ? s->qnodes : nullptr;
+    v.qnodes = (s->use_qnodes && s->bopt.allow_qnodes) ? s->qnodes : nullptr;
     for (int a = 0; a < 3; ++a) { v.glo[a] = s->glo[a]; v.cell[a] = s->cell[a]; }
     return v;
 }
 
-int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
+// Scratch of one commit; everything here goes back to the block cache on every exit path.
+struct CommitScratch {
+    uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr, *bounds = nullptr;
+    unsigned long long *flags = nullptr, *counters = nullptr; uint32_t *climb = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, es0 = nullptr, es1 = nullptr;
+    ~CommitScratch()
+    {
+        dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags); dfree(counters); dfree(climb);
+        if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (es0) cudaEventDestroy(es0); if (es1) cudaEventDestroy(es1);
+    }
+};
+
+int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
 {
-    if (s->committed) { if (build_ms_out) *build_ms_out = s->stats.build_ms; return 0; }
-    SyncedFrees batch;          // covers the re-commit teardown here and, after the build's own event wait, the scratch frees
-    free_build(s);
     const uint32_t G = (uint32_t)s->geoms.size();
-    uint64_t T = 0, V = 0;
+    const uint64_t T = s->ntris, V = s->nverts;
     std::vector<uint64_t> goff(G + 1, 0), voff(G + 1, 0);
-    for (uint32_t g = 0; g < G; ++g) { goff[g] = T; voff[g] = V; T += s->geoms[g].T; V += s->geoms[g].V; }
-    goff[G] = T; voff[G] = V;
-    if (T >= (1ull << 29)) FAIL("scene has %llu triangles; the leaf encoding holds 2^29", (unsigned long long)T);
-    if (V >= (1ull << 32)) FAIL("scene has %llu vertices; indices are 32-bit", (unsigned long long)V);
-    s->ntris = T; s->nverts = V;
-    memset(&s->stats, 0, sizeof(s->stats));
-    s->stats.num_triangles = T; s->stats.num_geometries = G; s->stats.leaf_max = (uint32_t)g_leaf_max;
-    s->committed = true;
-    if (T == 0) { if (build_ms_out) *build_ms_out = 0.0f; return 0; }
-
-    cudaEvent_t e0, e1, es0, es1;
-    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventCreate(&es0)); CUDA_TRY(cudaEventCreate(&es1));
-
+    { uint64_t t = 0, v = 0; for (uint32_t g = 0; g < G; ++g) { goff[g] = t; voff[g] = v; t += s->geoms[g].T; v += s->geoms[g].V; } goff[G] = t; voff[G] = v; }
+    CUDA_TRY(cudaEventCreate(&cs.e0)); CUDA_TRY(cudaEventCreate(&cs.e1));
+    CUDA_TRY(cudaEventCreate(&cs.es0)); CUDA_TRY(cudaEventCreate(&cs.es1));
     if (dmalloc(&s->goff, G + 1) || dmalloc(&s->voff, G + 1)) return 1;
     CUDA_TRY(cudaMemcpyAsync(s->goff, goff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->voff, voff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));        // goff / voff are locals
     // allocate everything before the timed region
-    uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr, *bounds = nullptr;
-    unsigned long long *flags = nullptr, *counters = nullptr; uint32_t *climb = nullptr;
-    if (dmalloc(&s->keys, T) || dmalloc(&keys_tmp, T) || dmalloc(&s->order, T) || dmalloc(&order_tmp, T) ||
-        dmalloc(&sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&bounds, 8) ||
-        dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&flags, T) || dmalloc(&s->tris, T) ||
+    if (dmalloc(&s->keys, T) || dmalloc(&cs.keys_tmp, T) || dmalloc(&s->order, T) || dmalloc(&cs.order_tmp, T) ||
+        dmalloc(&cs.sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&cs.bounds, 8) ||
+        dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&cs.flags, T) || dmalloc(&s->tris, T) ||
         dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(T - 1, 1)) ||
-        dmalloc(&counters, 5) || dmalloc(&climb, lbvh_climb_bytes(T) / sizeof(uint32_t)))
+        dmalloc(&cs.counters, 5) || dmalloc(&cs.climb, lbvh_climb_bytes(T) / sizeof(uint32_t)))
         return 1;
     if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
     else {
@@ -326,7 +359,7 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         s->own_concat = true;
     }
 
-    CUDA_TRY(cudaEventRecord(e0, st));
+    CUDA_TRY(cudaEventRecord(cs.e0, st));
     if (G > 1) {
         for (uint32_t g = 0; g < G; ++g) {
             const Geometry &ge = s->geoms[g];
@@ -335,61 +368,81 @@ int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
         }
     }
     LbvhBuildArgs A{};
-    A.leaf_max = g_leaf_max;
+    A.leaf_max = s->bopt.leaf_max; A.sort_variant = s->bopt.sort_variant; A.climb_capacity = s->bopt.climb_capacity;
+    A.quant_frac = s->bopt.quant_frac;
     A.verts = s->verts; A.idx = s->idx; A.ntris = T; A.geom_offsets = s->goff; A.ngeoms = G;
-    A.bounds_ord = bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = keys_tmp;
-    A.order = s->order; A.order_tmp = order_tmp; A.sort_scratch = sort_scratch;
-    A.bnodes = s->bnodes; A.flags = flags; A.keep_bnodes = g_keep_bnodes ? 1 : 0; A.climb_work = climb;
+    A.bounds_ord = cs.bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = cs.keys_tmp;
+    A.order = s->order; A.order_tmp = cs.order_tmp; A.sort_scratch = cs.sort_scratch;
+    A.bnodes = s->bnodes; A.flags = cs.flags; A.keep_bnodes = s->bopt.keep_bnodes ? 1 : 0; A.climb_work = cs.climb;
     A.qnodes = s->qnodes;
-    A.tris = s->tris; A.tnodes = s->tnodes; A.counters = counters; A.ev_sort0 = es0; A.ev_sort1 = es1;
-    int rc = 0;
+    A.tris = s->tris; A.tnodes = s->tnodes; A.counters = cs.counters; A.ev_sort0 = cs.es0; A.ev_sort1 = cs.es1;
     unsigned long long cnt[5] = {};
     // The sort normally runs over the top 40 key bits plus an exact fix-up of short runs; a scene with a run of more
     // than 64 triangles in one 2^-13 cell (thousands of coincident triangles) reports an overflow and is built again
     // with all eight passes.  Both attempts are inside the timed region.
-    for (int attempt = 0; attempt < 2 && !rc; ++attempt) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
         A.full_sort = attempt;
-        rc = lbvh_build(A, st);
-        if (rc) break;
-        CUDA_TRY(cudaEventRecord(e1, st));
-        CUDA_TRY(cudaEventSynchronize(e1));
-        CUDA_TRY(cudaMemcpy(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+        if (lbvh_build(A, st)) return 1;
+        CUDA_TRY(cudaEventRecord(cs.e1, st));
+        CUDA_TRY(cudaEventSynchronize(cs.e1));
+        CUDA_TRY(cudaMemcpy(cnt, cs.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
         if (!cnt[4]) break;
     }
     s->stats.full_sort = (uint32_t)A.full_sort;
-    if (!rc) {
-        CUDA_TRY(cudaEventElapsedTime(&s->stats.build_ms, e0, e1));
-        CUDA_TRY(cudaEventElapsedTime(&s->stats.sort_ms, es0, es1));
-        BuildParams bp;
-        CUDA_TRY(cudaMemcpy(&bp, s->params, sizeof(bp), cudaMemcpyDeviceToHost));
-        for (int a = 0; a < 3; ++a) { s->stats.scene_lo[a] = bp.slo[a]; s->stats.scene_hi[a] = bp.shi[a]; }
-        s->stats.box_pad = bp.pad;
-        s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];
-        s->use_qnodes = bp.use_q != 0;                      // decided on the device (k_decide_quant)
-        if (!s->use_qnodes) dfree(s->qnodes);
-        if (!g_keep_bnodes) dfree(s->bnodes);               // only the hand-over boxes of the build were in it
-        for (int a = 0; a < 3; ++a) { s->glo[a] = bp.glo[a]; s->cell[a] = bp.cell[a]; }
-        s->stats.quantised_nodes = s->use_qnodes ? 1u : 0u;
-        s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + T * sizeof(TriRec);
+    CUDA_TRY(cudaEventElapsedTime(&s->stats.build_ms, cs.e0, cs.e1));
+    CUDA_TRY(cudaEventElapsedTime(&s->stats.sort_ms, cs.es0, cs.es1));
+    BuildParams bp;
+    CUDA_TRY(cudaMemcpy(&bp, s->params, sizeof(bp), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < 3; ++a) { s->stats.scene_lo[a] = bp.slo[a]; s->stats.scene_hi[a] = bp.shi[a]; }
+    s->stats.box_pad = bp.pad;
+    s->stats.num_bvh_nodes = cnt[0]; s->stats.num_bvh_leaves = cnt[1]; s->stats.bvh_height = (uint32_t)cnt[2];
+    s->use_qnodes = bp.use_q != 0;                      // decided on the device (k_hierarchy_refit_emit)
+    if (!s->use_qnodes) dfree(s->qnodes);
+    if (!s->bopt.keep_bnodes) dfree(s->bnodes);         // only the hand-over boxes of the build were in it
+    for (int a = 0; a < 3; ++a) { s->glo[a] = bp.glo[a]; s->cell[a] = bp.cell[a]; }
+    s->stats.quantised_nodes = s->use_qnodes ? 1u : 0u;
+    s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + T * sizeof(TriRec);
+    return 0;
+}
+
+int do_commit(qsmrt_scene *s, cudaStream_t st, float *build_ms_out)
+{
+    if (s->committed) { if (build_ms_out) *build_ms_out = s->stats.build_ms; return 0; }
+    SyncedFrees batch;          // covers the re-commit teardown here and, after the build's own event wait, the scratch frees
+    free_build(s);
+    uint64_t T = 0, V = 0;
+    for (const Geometry &g : s->geoms) { T += g.T; V += g.V; }
+    if (T >= (1ull << 29)) FAIL("scene has %llu triangles; the leaf encoding holds 2^29", (unsigned long long)T);
+    if (V >= (1ull << 32)) FAIL("scene has %llu vertices; indices are 32-bit", (unsigned long long)V);
+    s->ntris = T; s->nverts = V;
+    memset(&s->stats, 0, sizeof(s->stats));
+    s->stats.num_triangles = T; s->stats.num_geometries = s->geoms.size(); s->stats.leaf_max = (uint32_t)s->bopt.leaf_max;
+    if (T) {
+        // `committed` is only set after a complete build: a failed one (out of memory on a large scene, say) frees
+        // whatever it had allocated and leaves the scene uncommitted, so the next query builds again instead of
+        // traversing null or half-written nodes
+        CommitScratch cs;
+        if (build_scene(s, st, cs)) {
+            cudaDeviceSynchronize();            // kernels of the failed build may still be in flight
+            cudaGetLastError();
+            free_build(s);
+            return 1;
+        }
     }
-    if (rc) cudaDeviceSynchronize();        // a failed build may still have kernels in flight
-    dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags);
-    dfree(counters); dfree(climb);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(es0); cudaEventDestroy(es1);
-    if (rc) { s->committed = false; return 1; }
+    s->committed = true;
     if (build_ms_out) *build_ms_out = s->stats.build_ms;
     return 0;
 }
 
-int ensure_pipe(qsmrt_scene *s, uint64_t chunk)
+int ensure_pipe(qsmrt_scene *s, uint64_t chunk, size_t out_bytes)
 {
     HostPipe &hp = s->pipe;
-    if (hp.chunk >= chunk) return 0;
+    if (hp.chunk >= chunk && hp.out_bytes >= out_bytes) return 0;
+    chunk = std::max(chunk, hp.chunk); out_bytes = std::max(out_bytes, hp.out_bytes);
+    SyncedFrees batch;
     free_pipe(hp);
     for (int b = 0; b < HostPipe::NBUF; ++b) {
-        if (dmalloc(&hp.rays[b], 6 * chunk) || dmalloc(&hp.t[b], chunk) || dmalloc(&hp.g[b], chunk) ||
-            dmalloc(&hp.p[b], chunk) || dmalloc(&hp.uv[b], 2 * chunk) || dmalloc(&hp.nrm[b], 3 * chunk))
-            return 1;
+        if (dmalloc(&hp.rays[b], 6 * chunk) || dmalloc(&hp.out[b], chunk * out_bytes)) return 1;
         CUDA_TRY(cudaEventCreateWithFlags(&hp.e_in[b], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&hp.e_run[b], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&hp.e_out[b], cudaEventDisableTiming));
@@ -397,7 +450,50 @@ int ensure_pipe(qsmrt_scene *s, uint64_t chunk)
     CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
-    hp.chunk = chunk;
+    hp.chunk = chunk; hp.out_bytes = out_bytes;
+    return 0;
+}
+
+// One result array of a *_host call: `bytes` per ray, copied back to `host` (NULL: not wanted).  When `keep` is set
+// the kernel writes the array for the whole batch there (device memory) instead: the caller fetches it later or never.
+struct HostOut { void *host; void *keep; size_t bytes; };
+
+// Host rays in, host results out: the batch is cut into chunks and host->device copy, traversal and device->host
+// copy of consecutive chunks overlap on three streams (triple-buffered device staging).  `launch(rays_dev, n, dst[],
+// stream)` enqueues the traversal of one chunk; dst[k] is where output k of that chunk goes.
+template <int NOUT, class Launch>
+int run_host_pipe(qsmrt_scene *s, const float *rays, uint64_t N, const HostOut (&outs)[NOUT], Launch launch)
+{
+    uint64_t chunk_rays = 1ull << 20;                       // QSMRT_HOST_CHUNK overrides (rays per pipeline stage)
+    if (const char *e = getenv("QSMRT_HOST_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk_rays = (uint64_t)v; }
+    const uint64_t chunk = std::min<uint64_t>(N, chunk_rays);
+    size_t stage_bytes = 0, off_of[NOUT];
+    for (int k = 0; k < NOUT; ++k) { off_of[k] = stage_bytes; if (outs[k].host && !outs[k].keep) stage_bytes += (outs[k].bytes + 15) & ~(size_t)15; }
+    if (ensure_pipe(s, chunk, std::max<size_t>(stage_bytes, 16))) return 1;
+    HostPipe &hp = s->pipe;
+    const uint64_t nchunks = (N + chunk - 1) / chunk;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c % HostPipe::NBUF);
+        const uint64_t off = c * chunk, n = std::min(chunk, N - off);
+        if (c >= HostPipe::NBUF) CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.e_out[b], 0));   // buffer drained
+        CUDA_TRY(cudaMemcpyAsync(hp.rays[b], rays + 6 * off, 6 * n * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
+        CUDA_TRY(cudaEventRecord(hp.e_in[b], hp.s_in));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_run, hp.e_in[b], 0));
+        void *dst[NOUT];
+        for (int k = 0; k < NOUT; ++k)
+            dst[k] = outs[k].keep ? static_cast<char *>(outs[k].keep) + off * outs[k].bytes
+                   : outs[k].host ? hp.out[b] + off_of[k] * hp.chunk : nullptr;
+        if (launch(hp.rays[b], n, dst, hp.s_run)) return 1;
+        CUDA_TRY(cudaEventRecord(hp.e_run[b], hp.s_run));
+        CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.e_run[b], 0));
+        for (int k = 0; k < NOUT; ++k)
+            if (outs[k].host && !outs[k].keep)
+                CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(outs[k].host) + off * outs[k].bytes, dst[k], n * outs[k].bytes, cudaMemcpyDeviceToHost, hp.s_out));
+        CUDA_TRY(cudaEventRecord(hp.e_out[b], hp.s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(hp.s_out));
+    CUDA_TRY(cudaStreamSynchronize(hp.s_run));
+    CUDA_TRY(cudaStreamSynchronize(hp.s_in));
     return 0;
 }
 
@@ -417,13 +513,15 @@ int qsmrt_scene_create(int cuda_device, qsmrt_scene **out)
     if (e != cudaSuccess || ndev == 0)
         FAIL("no CUDA device (%s); libqsmrt has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     if (cuda_device < 0 || cuda_device >= ndev) FAIL("cuda_device %d out of range (0..%d)", cuda_device, ndev - 1);
-    CUDA_TRY(cudaSetDevice(cuda_device));
+    DeviceGuard guard(cuda_device);
+    if (guard.err != cudaSuccess) FAIL("cudaSetDevice(%d): %s", cuda_device, cudaGetErrorString(guard.err));
     int major = 0, minor = 0;       // two attribute reads, not cudaGetDeviceProperties (2.4 ms per new scene)
     CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cuda_device));
     CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, cuda_device));
     if (major != 10) FAIL("device %d is sm_%d%d; libqsmrt is built for sm_100a only", cuda_device, major, minor);
     qsmrt_scene *s = new qsmrt_scene();
     s->device = cuda_device;
+    s->trv.device = cuda_device;
     *out = s;
     return 0;
 }
@@ -431,10 +529,12 @@ int qsmrt_scene_create(int cuda_device, qsmrt_scene **out)
 int qsmrt_scene_destroy(qsmrt_scene *s)
 {
     if (!s) return 0;
-    cudaSetDevice(s->device);
+    DeviceGuard guard(s->device);
     SyncedFrees batch;
     free_build(s);
     free_pipe(s->pipe);
+    dfree(s->sweep_dev);
+    trv_state_free(s->trv);
     for (Geometry &g : s->geoms) { dfree(g.verts); dfree(g.idx); }
     delete s;
     return 0;
@@ -443,27 +543,33 @@ int qsmrt_scene_destroy(qsmrt_scene *s)
 int qsmrt_add_triangles(qsmrt_scene *s, const float *verts, uint64_t V, const uint32_t *idx, uint64_t T,
                         int on_device, uint32_t *geom_id_out)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if ((V && !verts) || (T && !idx)) FAIL("null vertex or index pointer");
     if (V >= (1ull << 32)) FAIL("too many vertices");
     Geometry g;
     g.V = V; g.T = T;
-    if (dmalloc(&g.verts, 3 * V) || dmalloc(&g.idx, 3 * T)) { dfree(g.verts); dfree(g.idx); return 1; }
-    cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (V) CUDA_TRY(cudaMemcpy(g.verts, verts, 3 * V * sizeof(float), kind));
-    if (T) CUDA_TRY(cudaMemcpy(g.idx, idx, 3 * T * sizeof(uint32_t), kind));
-    // Embree would read out of bounds; reject instead
+    uint32_t *d_max = nullptr;
     uint32_t maxi = 0;
-    if (T) {
-        uint32_t *d = nullptr;
-        if (dmalloc(&d, 1)) { dfree(g.verts); dfree(g.idx); return 1; }
-        cudaMemset(d, 0, sizeof(uint32_t));
-        k_max_index<<<(unsigned)std::min<uint64_t>((3 * T + 255) / 256, 1184), 256>>>(g.idx, 3 * T, d);
-        cudaError_t e = cudaMemcpy(&maxi, d, sizeof(uint32_t), cudaMemcpyDeviceToHost);
-        dfree(d);
-        if (e != cudaSuccess) { dfree(g.verts); dfree(g.idx); FAIL("index check failed: %s", cudaGetErrorString(e)); }
-        if (maxi >= V) { dfree(g.verts); dfree(g.idx); FAIL("triangle index %u out of range (%llu vertices)", maxi, (unsigned long long)V); }
-    }
+    // copies and the index check run on the legacy default stream, which orders them after work already enqueued on
+    // blocking streams; callers that produce the mesh on a non-blocking stream synchronise it first (the Python
+    // front end does)
+    auto body = [&]() -> int {
+        if (dmalloc(&g.verts, 3 * V) || dmalloc(&g.idx, 3 * T)) return 1;
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (V) CUDA_TRY(cudaMemcpy(g.verts, verts, 3 * V * sizeof(float), kind));
+        if (T) CUDA_TRY(cudaMemcpy(g.idx, idx, 3 * T * sizeof(uint32_t), kind));
+        if (T) {        // Embree would read out of bounds; reject instead
+            if (dmalloc(&d_max, 1)) return 1;
+            CUDA_TRY(cudaMemset(d_max, 0, sizeof(uint32_t)));
+            k_max_index<<<(unsigned)std::min<uint64_t>((3 * T + 255) / 256, 1184), 256>>>(g.idx, 3 * T, d_max);
+            CUDA_TRY(cudaMemcpy(&maxi, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            if (maxi >= V) { qsmrt_set_error("triangle index %u out of range (%llu vertices)", maxi, (unsigned long long)V); return 1; }
+        }
+        return 0;
+    };
+    const int rc = body();
+    dfree(d_max);
+    if (rc) { dfree(g.verts); dfree(g.idx); return 1; }
     if (s->committed || s->verts) free_build(s);
     s->geoms.push_back(g);
     if (geom_id_out) *geom_id_out = (uint32_t)(s->geoms.size() - 1);
@@ -473,7 +579,7 @@ int qsmrt_add_triangles(qsmrt_scene *s, const float *verts, uint64_t V, const ui
 int qsmrt_add_cylinders(qsmrt_scene *s, const float *records, uint64_t n, uint32_t resolution, uint32_t split,
                         int on_device, uint32_t *geom_id_out)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (n && !records) FAIL("null records pointer");
     if (resolution < 3 || split < 1 || resolution > 4096 || split > 4096) FAIL("resolution must be >= 3 and split >= 1");
     const uint64_t V = (uint64_t)resolution * (split + 1) + 2, T = 2ull * resolution * (1 + split);
@@ -486,7 +592,10 @@ int qsmrt_add_cylinders(qsmrt_scene *s, const float *records, uint64_t n, uint32
         const float *rec = records;
         if (!on_device) {
             if (dmalloc(&rec_dev, 8 * n)) { dfree(g.verts); dfree(g.idx); return 1; }
-            CUDA_TRY(cudaMemcpy(rec_dev, records, 8 * n * sizeof(float), cudaMemcpyHostToDevice));
+            if (cudaMemcpy(rec_dev, records, 8 * n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                dfree(rec_dev); dfree(g.verts); dfree(g.idx);
+                FAIL("cylinder records upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
             rec = rec_dev;
         }
         k_cylinders<<<(unsigned)n, 128>>>(rec, n, resolution, split, g.verts, g.idx);
@@ -511,7 +620,7 @@ int qsmrt_geometry_size(qsmrt_scene *s, uint32_t geom_id, uint64_t *V_out, uint6
 
 int qsmrt_copy_geometry(qsmrt_scene *s, uint32_t geom_id, float *verts_dev, uint32_t *idx_dev, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (geom_id >= s->geoms.size()) FAIL("geometry id %u out of range", geom_id);
     const Geometry &g = s->geoms[geom_id];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -522,57 +631,106 @@ int qsmrt_copy_geometry(qsmrt_scene *s, uint32_t geom_id, float *verts_dev, uint
 
 int qsmrt_commit(qsmrt_scene *s, void *stream, float *build_ms_out)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     return do_commit(s, static_cast<cudaStream_t>(stream), build_ms_out);
 }
 
 int qsmrt_cast_rays(qsmrt_scene *s, const float *rays, uint64_t N, float *t_hit, uint32_t *geom, uint32_t *prim,
                     float *uv, float *nrm, void *stream)
 {
-    if (use_device(s) || check_rays(rays, N)) return 1;
+    SCENE_ENTER(s);
+    if (check_rays(rays, N)) return 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
     if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
-    return trv_cast_rays(view_of(s), rays, N, 0, t_hit, geom, prim, uv, nrm, st);
+    return trv_cast_rays(s->trv, view_of(s), rays, N, 0, t_hit, geom, prim, uv, nrm, st);
 }
 
 int qsmrt_cast_rays_2d(qsmrt_scene *s, const float *rays, uint32_t width, uint64_t height, float *t_hit, uint32_t *geom,
                        uint32_t *prim, float *uv, float *nrm, void *stream)
 {
-    if (use_device(s) || check_rays(rays, (uint64_t)width * height)) return 1;
+    SCENE_ENTER(s);
+    if (check_rays(rays, (uint64_t)width * height)) return 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
     if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
-    return trv_cast_rays(view_of(s), rays, (uint64_t)width * height, width, t_hit, geom, prim, uv, nrm, st);
+    return trv_cast_rays(s->trv, view_of(s), rays, (uint64_t)width * height, width, t_hit, geom, prim, uv, nrm, st);
 }
 
-int qsmrt_debug_set_variant(int variant)
+int qsmrt_scene_set_option(qsmrt_scene *s, int key, double value)
 {
-    if (variant != 1 && variant != 2) FAIL("unknown traversal variant %d (1 = per-thread loop, 2 = persistent kernel)", variant);
-    g_trv_variant = variant;
+    if (!s) FAIL("null scene");
+    const int iv = (int)value;
+    BuildOptions &b = s->bopt; TrvOptions &t = s->trv.opt;
+    bool rebuild = false;
+    switch (key) {
+    case QSMRT_OPT_LEAF_MAX:
+        if (iv < 1 || iv > QSMRT_LEAF_MAX) FAIL("leaf_max must be in 1..%d", QSMRT_LEAF_MAX);
+        rebuild = b.leaf_max != iv; b.leaf_max = iv; break;
+    case QSMRT_OPT_KEEP_BINARY_NODES: rebuild = b.keep_bnodes != (iv != 0); b.keep_bnodes = iv != 0; break;
+    case QSMRT_OPT_QUANT_THRESHOLD: { const float f = value > 0.0 ? (float)value : 0.15f; rebuild = b.quant_frac != f; b.quant_frac = f; break; }
+    case QSMRT_OPT_CLIMB_CAPACITY: rebuild = b.climb_capacity != std::max(iv, 0); b.climb_capacity = std::max(iv, 0); break;
+    case QSMRT_OPT_SORT_VARIANT:
+        if (iv != 0 && iv != 1) FAIL("sort variant must be 0 (classic) or 1 (onesweep)");
+        rebuild = b.sort_variant != iv; b.sort_variant = iv; break;
+    case QSMRT_OPT_QUANTISED_NODES: b.allow_qnodes = iv != 0; break;
+    case QSMRT_OPT_TRAVERSAL_VARIANT:
+        if (iv != 1 && iv != 2) FAIL("unknown traversal variant %d (1 = per-thread loop, 2 = persistent kernel)", iv);
+        t.variant = iv; break;
+    case QSMRT_OPT_REFILL: if (iv < 1 || iv > 32) FAIL("thresholds must be in 1..32"); t.refill = iv; break;
+    case QSMRT_OPT_WANT: if (iv < 1 || iv > 32) FAIL("thresholds must be in 1..32"); t.want = iv; break;
+    case QSMRT_OPT_TRI_MIN: if (iv < 1 || iv > 32) FAIL("thresholds must be in 1..32"); t.tri_min = iv; break;
+    case QSMRT_OPT_COUNTERS: t.counters = iv != 0; break;
+    case QSMRT_OPT_NODE_PATH: if (iv < 0 || iv > 2) FAIL("node path must be 0, 1 or 2"); t.node_path = iv; break;
+    case QSMRT_OPT_CP_WARP_MAX: t.cp_warp_max = std::max(iv, 0); break;
+    default: FAIL("unknown option %d", key);
+    }
+    if (rebuild && s->committed) { SCENE_ENTER(s); free_build(s); }     // the next query builds with the new option
     return 0;
 }
 
-int qsmrt_debug_set_tuning(int refill_thresh, int want_thresh, int speculate, int counters)
+int qsmrt_scene_get_option(qsmrt_scene *s, int key, double *value)
 {
-    if (refill_thresh < 1 || refill_thresh > 32 || want_thresh < 1 || want_thresh > 32) FAIL("thresholds must be in 1..32");
-    g_trv_tuning[0] = refill_thresh; g_trv_tuning[1] = want_thresh; g_trv_tuning[2] = speculate != 0; g_trv_tuning[3] = counters != 0;
+    if (!s || !value) FAIL("null pointer");
+    const BuildOptions &b = s->bopt; const TrvOptions &t = s->trv.opt;
+    switch (key) {
+    case QSMRT_OPT_LEAF_MAX: *value = b.leaf_max; break;
+    case QSMRT_OPT_KEEP_BINARY_NODES: *value = b.keep_bnodes; break;
+    case QSMRT_OPT_QUANT_THRESHOLD: *value = b.quant_frac; break;
+    case QSMRT_OPT_CLIMB_CAPACITY: *value = b.climb_capacity; break;
+    case QSMRT_OPT_SORT_VARIANT: *value = b.sort_variant; break;
+    case QSMRT_OPT_QUANTISED_NODES: *value = b.allow_qnodes; break;
+    case QSMRT_OPT_TRAVERSAL_VARIANT: *value = t.variant; break;
+    case QSMRT_OPT_REFILL: *value = t.refill; break;
+    case QSMRT_OPT_WANT: *value = t.want; break;
+    case QSMRT_OPT_TRI_MIN: *value = t.tri_min; break;
+    case QSMRT_OPT_COUNTERS: *value = t.counters; break;
+    case QSMRT_OPT_NODE_PATH: *value = t.node_path; break;
+    case QSMRT_OPT_CP_WARP_MAX: *value = t.cp_warp_max; break;
+    default: FAIL("unknown option %d", key);
+    }
     return 0;
 }
 
-int qsmrt_debug_get_counters(uint64_t *nodes_out, uint64_t *tris_out)
+int qsmrt_scene_get_counters(qsmrt_scene *s, uint64_t out[16])
 {
-    unsigned long long h[2] = { 0, 0 };
-    if (g_trv_stats_dev) CUDA_TRY(cudaMemcpy(h, g_trv_stats_dev, sizeof(h), cudaMemcpyDeviceToHost));
-    if (nodes_out) *nodes_out = h[0];
-    if (tris_out) *tris_out = h[1];
+    SCENE_ENTER(s);
+    if (!out) FAIL("null pointer");
+    unsigned long long h[16];
+    if (trv_read_counters(s->trv, h)) return 1;
+    for (int k = 0; k < 16; ++k) out[k] = h[k];
     return 0;
 }
 
-int qsmrt_debug_set_sort(int variant)
+int qsmrt_util_read_sweep(const void *buf_dev, uint64_t bytes, uint32_t reps, uint32_t *sink_dev, void *stream)
 {
-    if (variant != 0 && variant != 1) FAIL("sort variant must be 0 (classic) or 1 (onesweep)");
-    g_sort_variant = variant;
+    if (!buf_dev || !sink_dev) FAIL("null pointer");
+    if (reinterpret_cast<uintptr_t>(buf_dev) & 31u) FAIL("buffer must be 32-byte aligned");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    k_read_sweep<<<(unsigned)(sms * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4 *>(buf_dev), bytes / 32, reps, sink_dev);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -584,119 +742,88 @@ int qsmrt_release_cached_memory(void)
     return 0;
 }
 
-int qsmrt_debug_set_cp_warp_max(int max_points)
-{
-    g_trv_cp_warp_max = max_points < 0 ? 0 : max_points;
-    return 0;
-}
+// results of cast_rays in ABI order: t_hit, geometry_ids, primitive_ids, primitive_uvs, primitive_normals
+static const size_t CAST_BYTES[5] = { 4, 4, 4, 8, 12 };
 
-int qsmrt_debug_set_quant_threshold(float frac)
+int qsmrt_cast_rays_host_split(qsmrt_scene *s, const float *rays, uint64_t N, void *const host_out[5], void *const dev_out[5])
 {
-    g_quant_frac = frac > 0.0f ? frac : 0.15f;
-    return 0;
-}
-
-int qsmrt_debug_set_climb_capacity(int items)
-{
-    g_climb_cap_override = items > 0 ? items : 0;
-    return 0;
-}
-
-int qsmrt_debug_set_keep_binary_nodes(int keep)
-{
-    g_keep_bnodes = keep != 0;
-    return 0;
-}
-
-int qsmrt_debug_set_quantised_nodes(int allow)
-{
-    g_allow_qnodes = allow != 0;
-    return 0;
-}
-
-int qsmrt_debug_set_node_path(int path)
-{
-    if (path < 0 || path > 2) FAIL("node path must be 0, 1 or 2");
-    g_trv_node_path = path;
-    return 0;
-}
-
-int qsmrt_debug_set_leaf_max(int leaf_max)
-{
-    if (leaf_max < 1 || leaf_max > QSMRT_LEAF_MAX) FAIL("leaf_max must be in 1..%d", QSMRT_LEAF_MAX);
-    g_leaf_max = leaf_max;
-    return 0;
-}
-
-int qsmrt_debug_get_census(uint64_t out[16])
-{
-    if (!out) FAIL("null pointer");
-    memset(out, 0, 16 * sizeof(uint64_t));
-    if (g_trv_stats_dev) CUDA_TRY(cudaMemcpy(out, g_trv_stats_dev, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    return 0;
+    SCENE_ENTER(s);
+    if (N && !rays) FAIL("rays pointer is null");
+    if (!host_out) FAIL("null output table");
+    if (do_commit(s, nullptr, nullptr)) return 1;
+    if (N == 0) return 0;
+    HostOut outs[5];
+    for (int k = 0; k < 5; ++k) {
+        void *keep = dev_out ? dev_out[k] : nullptr;
+        outs[k] = HostOut{ keep ? keep : host_out[k], keep, CAST_BYTES[k] };       // `host` non-null marks the output as wanted
+    }
+    if (dev_out && dev_out[3] && (reinterpret_cast<uintptr_t>(dev_out[3]) & 7u)) FAIL("primitive_uvs must be 8-byte aligned");
+    const SceneView sv = view_of(s);
+    return run_host_pipe<5>(s, rays, N, outs, [&](const float *r, uint64_t n, void **dst, cudaStream_t st) {
+        return trv_cast_rays(s->trv, sv, r, n, 0, static_cast<float *>(dst[0]), static_cast<uint32_t *>(dst[1]),
+                             static_cast<uint32_t *>(dst[2]), static_cast<float *>(dst[3]), static_cast<float *>(dst[4]), st);
+    });
 }
 
 int qsmrt_cast_rays_host(qsmrt_scene *s, const float *rays, uint64_t N, float *t_hit, uint32_t *geom,
                          uint32_t *prim, float *uv, float *nrm)
 {
-    if (use_device(s)) return 1;
-    if (N && !rays) FAIL("rays pointer is null");
+    void *const host[5] = { t_hit, geom, prim, uv, nrm };
+    return qsmrt_cast_rays_host_split(s, rays, N, host, nullptr);
+}
+
+int qsmrt_count_intersections_host(qsmrt_scene *s, const float *rays, uint64_t N, int32_t *counts)
+{
+    SCENE_ENTER(s);
+    if (N && (!rays || !counts)) FAIL("null pointer");
     if (do_commit(s, nullptr, nullptr)) return 1;
     if (N == 0) return 0;
-    uint64_t chunk_rays = 1ull << 20;                       // QSMRT_HOST_CHUNK overrides (rays per pipeline stage)
-    if (const char *e = getenv("QSMRT_HOST_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk_rays = (uint64_t)v; }
-    const uint64_t chunk = std::min<uint64_t>(N, chunk_rays);
-    if (ensure_pipe(s, chunk)) return 1;
-    HostPipe &hp = s->pipe;
-    SceneView sv = view_of(s);
-    uint64_t nchunks = (N + chunk - 1) / chunk;
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        int b = (int)(c % HostPipe::NBUF);
-        uint64_t off = c * chunk, n = std::min(chunk, N - off);
-        if (c >= HostPipe::NBUF) CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.e_out[b], 0));   // buffer drained
-        CUDA_TRY(cudaMemcpyAsync(hp.rays[b], rays + 6 * off, 6 * n * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
-        CUDA_TRY(cudaEventRecord(hp.e_in[b], hp.s_in));
-        CUDA_TRY(cudaStreamWaitEvent(hp.s_run, hp.e_in[b], 0));
-        if (trv_cast_rays(sv, hp.rays[b], n, 0, t_hit ? hp.t[b] : nullptr, geom ? hp.g[b] : nullptr,
-                          prim ? hp.p[b] : nullptr, uv ? hp.uv[b] : nullptr, nrm ? hp.nrm[b] : nullptr, hp.s_run))
-            return 1;
-        CUDA_TRY(cudaEventRecord(hp.e_run[b], hp.s_run));
-        CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.e_run[b], 0));
-        if (t_hit) CUDA_TRY(cudaMemcpyAsync(t_hit + off, hp.t[b], n * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
-        if (geom) CUDA_TRY(cudaMemcpyAsync(geom + off, hp.g[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, hp.s_out));
-        if (prim) CUDA_TRY(cudaMemcpyAsync(prim + off, hp.p[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, hp.s_out));
-        if (uv) CUDA_TRY(cudaMemcpyAsync(uv + 2 * off, hp.uv[b], 2 * n * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
-        if (nrm) CUDA_TRY(cudaMemcpyAsync(nrm + 3 * off, hp.nrm[b], 3 * n * sizeof(float), cudaMemcpyDeviceToHost, hp.s_out));
-        CUDA_TRY(cudaEventRecord(hp.e_out[b], hp.s_out));
-    }
-    CUDA_TRY(cudaStreamSynchronize(hp.s_out));
-    CUDA_TRY(cudaStreamSynchronize(hp.s_run));
-    CUDA_TRY(cudaStreamSynchronize(hp.s_in));
-    return 0;
+    const HostOut outs[1] = { HostOut{ counts, nullptr, sizeof(int32_t) } };
+    const SceneView sv = view_of(s);
+    const uint32_t ngeoms = (uint32_t)s->geoms.size();
+    return run_host_pipe<1>(s, rays, N, outs, [&](const float *r, uint64_t n, void **dst, cudaStream_t st) {
+        return trv_count(s->trv, sv, r, n, static_cast<int32_t *>(dst[0]), ngeoms, st);
+    });
+}
+
+int qsmrt_test_occlusions_host(qsmrt_scene *s, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out)
+{
+    SCENE_ENTER(s);
+    if (N && (!rays || !out)) FAIL("null pointer");
+    if (do_commit(s, nullptr, nullptr)) return 1;
+    if (N == 0) return 0;
+    const HostOut outs[1] = { HostOut{ out, nullptr, sizeof(uint8_t) } };
+    const SceneView sv = view_of(s);
+    return run_host_pipe<1>(s, rays, N, outs, [&](const float *r, uint64_t n, void **dst, cudaStream_t st) {
+        return trv_occluded(s->trv, sv, r, n, tnear, tfar, static_cast<uint8_t *>(dst[0]), st);
+    });
 }
 
 int qsmrt_count_intersections(qsmrt_scene *s, const float *rays, uint64_t N, int32_t *counts, void *stream)
 {
-    if (use_device(s) || check_rays(rays, N)) return 1;
+    SCENE_ENTER(s);
+    if (check_rays(rays, N)) return 1;
     if (N && !counts) FAIL("counts pointer is null");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
-    return trv_count(view_of(s), rays, N, counts, (uint32_t)s->geoms.size(), st);
+    return trv_count(s->trv, view_of(s), rays, N, counts, (uint32_t)s->geoms.size(), st);
 }
 
 int qsmrt_test_occlusions(qsmrt_scene *s, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, void *stream)
 {
-    if (use_device(s) || check_rays(rays, N)) return 1;
+    SCENE_ENTER(s);
+    if (check_rays(rays, N)) return 1;
     if (N && !out) FAIL("output pointer is null");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
-    return trv_occluded(view_of(s), rays, N, tnear, tfar, out, st);
+    return trv_occluded(s->trv, view_of(s), rays, N, tnear, tfar, out, st);
 }
 
 int qsmrt_list_intersections_count(qsmrt_scene *s, const float *rays, uint64_t N, int64_t *ray_splits,
                                    int64_t *total_out, void *stream)
 {
-    if (use_device(s) || check_rays(rays, N)) return 1;
+    SCENE_ENTER(s);
+    if (check_rays(rays, N)) return 1;
     if (!ray_splits || !total_out) FAIL("null output pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
@@ -725,7 +852,7 @@ int qsmrt_list_intersections_count(qsmrt_scene *s, const float *rays, uint64_t N
 int qsmrt_list_intersections_fill(qsmrt_scene *s, const float *rays, uint64_t N, const int64_t *ray_splits,
                                   int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (!s->list_raw_off || s->list_rays != rays || s->list_n != N)
         FAIL("list_intersections_fill must follow list_intersections_count on the same rays");
     if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
@@ -768,7 +895,7 @@ int qsmrt_gen_pinhole_rays(float *rays, uint32_t w, uint32_t h, const double K[9
 int qsmrt_mark_hit_primitives(qsmrt_scene *s, const uint32_t *geom, const uint32_t *prim, uint64_t N,
                               uint8_t *tri_hit, uint8_t *vert_hit, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (!prim) FAIL("primitive_ids pointer is null");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
@@ -779,7 +906,7 @@ int qsmrt_mark_hit_primitives(qsmrt_scene *s, const uint32_t *geom, const uint32
 int qsmrt_accumulate_hits(qsmrt_scene *s, const uint32_t *geom, const uint32_t *prim, uint64_t N,
                           uint32_t *tri_counts, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (!prim || !tri_counts) FAIL("null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
@@ -790,26 +917,26 @@ int qsmrt_accumulate_hits(qsmrt_scene *s, const uint32_t *geom, const uint32_t *
 int qsmrt_closest_points(qsmrt_scene *s, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
                          uint32_t *prim, float *uv, float *nrm, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (N && !pts) FAIL("query points pointer is null");
     if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
-    return trv_closest_points(view_of(s), pts, N, closest, dist, geom, prim, uv, nrm, st);
+    return trv_closest_points(s->trv, view_of(s), pts, N, closest, dist, geom, prim, uv, nrm, st);
 }
 
 int qsmrt_signed_distance(qsmrt_scene *s, const float *pts, uint64_t N, float *dist, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (N && (!pts || !dist)) FAIL("null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
     if (N == 0) return 0;
     float *rays = nullptr; int32_t *counts = nullptr;
     if (dmalloc(&rays, 6 * N) || dmalloc(&counts, N)) { dfree(rays); dfree(counts); return 1; }
-    int rc = trv_closest_points(view_of(s), pts, N, nullptr, dist, nullptr, nullptr, nullptr, nullptr, st) ||
+    int rc = trv_closest_points(s->trv, view_of(s), pts, N, nullptr, dist, nullptr, nullptr, nullptr, nullptr, st) ||
              trv_points_to_rays(pts, rays, N, st) ||
-             trv_count(view_of(s), rays, N, counts, (uint32_t)s->geoms.size(), st) ||
+             trv_count(s->trv, view_of(s), rays, N, counts, (uint32_t)s->geoms.size(), st) ||
              trv_apply_sign(dist, counts, N, st);
     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { qsmrt_set_error("signed_distance: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
     dfree(rays); dfree(counts);
@@ -819,37 +946,58 @@ int qsmrt_signed_distance(qsmrt_scene *s, const float *pts, uint64_t N, float *d
 int qsmrt_sun_exposure(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
                        const float dv[3], const float dir[3], uint32_t *tri_counts, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (!o0 || !du || !dv || !dir || !tri_counts) FAIL("null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
-    return trv_sun_exposure(view_of(s), nu, nv, o0, du, dv, dir, s->geoms.size() > 1 ? s->goff : nullptr, tri_counts, st);
+    return trv_sun_exposure(s->trv, view_of(s), nu, nv, o0, du, dv, dir, s->geoms.size() > 1 ? s->goff : nullptr, tri_counts, st);
 }
 
-int qsmrt_sky_visibility(qsmrt_scene *s, const float *points, const float *normals, uint64_t n_points,
+int qsmrt_sun_exposure_sweep(qsmrt_scene *s, uint32_t n_grids, const float *grids, uint64_t nu, uint64_t nv,
+                             uint32_t *tri_counts, uint64_t count_stride, void *stream)
+{
+    SCENE_ENTER(s);
+    if (!grids || !tri_counts) FAIL("null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    if (n_grids == 0) return 0;
+    if (s->sweep_cap < n_grids) {
+        if (s->sweep_dev) { SyncedFrees batch; dfree(s->sweep_dev); }
+        s->sweep_cap = 0;
+        if (dmalloc(&s->sweep_dev, 12ull * std::max<uint32_t>(n_grids, 64))) return 1;
+        s->sweep_cap = std::max<uint32_t>(n_grids, 64);
+    }
+    // `grids` is ordinary host memory: the runtime stages it before the call returns; the copy is ordered on `stream`
+    // behind earlier sweeps of this scene, which read the same buffer
+    CUDA_TRY(cudaMemcpyAsync(s->sweep_dev, grids, 12ull * n_grids * sizeof(float), cudaMemcpyHostToDevice, st));
+    return trv_sun_exposure_sweep(s->trv, view_of(s), n_grids, s->sweep_dev, nu, nv, s->geoms.size() > 1 ? s->goff : nullptr,
+                                  tri_counts, count_stride, st);
+}
+
+int qsmrt_sky_visibility(qsmrt_scene *s, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
                          uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count,
                          uint32_t *unoccluded, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (!points || !unoccluded) FAIL("null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
-    return trv_sky_visibility(view_of(s), points, normals, n_points, seed, offset, dir_begin, dir_count, unoccluded, st);
+    return trv_sky_visibility(s->trv, view_of(s), points, normals, n_points, point_base, seed, offset, dir_begin, dir_count, unoccluded, st);
 }
 
-int qsmrt_gen_hemisphere_rays(float *rays, const float *points, const float *normals, uint64_t n_points,
+int qsmrt_gen_hemisphere_rays(float *rays, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
                               uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, void *stream)
 {
     if (!rays || !points) FAIL("null pointer");
     if (reinterpret_cast<uintptr_t>(rays) & 7u) FAIL("rays must be 8-byte aligned");
-    return trv_gen_hemisphere(rays, points, normals, n_points, seed, offset, dir_begin, dir_count, static_cast<cudaStream_t>(stream));
+    return trv_gen_hemisphere(rays, points, normals, n_points, point_base, seed, offset, dir_begin, dir_count, static_cast<cudaStream_t>(stream));
 }
 
 int qsmrt_peel_projection(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
                           const float dv[3], const float dir[3], int max_layers, int32_t *layer_of,
                           double *layer_stats, int *n_layers_out, void *stream)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (!o0 || !du || !dv || !dir || !layer_stats || !n_layers_out || max_layers < 1) FAIL("bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
@@ -865,7 +1013,7 @@ int qsmrt_peel_projection(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float 
     for (int layer = 0; !rc && layer < max_layers; ++layer) {
         double h[3] = { 0, 0, 0 };
         if (cudaMemsetAsync(sums, 0, 3 * sizeof(double), st) != cudaSuccess) { rc = 1; break; }
-        rc = trv_peel_cast(sv, nu, nv, o0, du, dv, dir, alive, hit, st) ||
+        rc = trv_peel_cast(s->trv, sv, nu, nv, o0, du, dv, dir, alive, hit, st) ||
              trv_peel_update(sv, s->order, alive, hit, layer_of, layer, dir, sums, st);
         if (!rc && (cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                     cudaStreamSynchronize(st) != cudaSuccess)) rc = 1;
@@ -876,6 +1024,164 @@ int qsmrt_peel_projection(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float 
     if (rc && !g_err[0]) qsmrt_set_error("peel_projection: %s", cudaGetErrorString(cudaGetLastError()));
     dfree(alive); dfree(hit); dfree(sums);
     return rc;
+}
+
+// ---- scene files --------------------------------------------------------------------------------------------
+// The reference's idiom for built search structures is pickling them next to the data (pyQSM/utils/io.py:44-60,
+// tree_isolation.py:114,136).  Here: the geometries as added plus, with QSMRT_SAVE_BVH, the committed LBVH
+// (traversal nodes, quantised twin, triangle records, order, keys, grid).  A file without the BVH is rebuilt on the
+// first query after loading -- the build is deterministic, so both routes give the identical tree.
+namespace {
+struct SceneFileHeader {
+    char     magic[8];           // "QSMRTSC1"
+    uint32_t version, flags;
+    uint64_t ngeoms, ntris, nverts;
+    int32_t  leaf_max, use_q;
+    float    quant_frac, glo[3], cell[3];
+    qsmrt_stats stats;
+};
+constexpr size_t IO_CHUNK = 64u << 20;
+
+struct FileIO {
+    FILE *f = nullptr; void *bounce = nullptr;
+    ~FileIO() { if (f) fclose(f); if (bounce) cudaFreeHost(bounce); }
+    int open(const char *path, const char *mode)
+    {
+        f = fopen(path, mode);
+        if (!f) { qsmrt_set_error("cannot open %s", path); return 1; }
+        CUDA_TRY(cudaMallocHost(&bounce, IO_CHUNK));
+        return 0;
+    }
+    int put(const void *dev, size_t bytes)
+    {
+        for (size_t o = 0; o < bytes; o += IO_CHUNK) {
+            const size_t n = std::min(IO_CHUNK, bytes - o);
+            CUDA_TRY(cudaMemcpy(bounce, static_cast<const char *>(dev) + o, n, cudaMemcpyDeviceToHost));
+            if (fwrite(bounce, 1, n, f) != n) { qsmrt_set_error("short write"); return 1; }
+        }
+        return 0;
+    }
+    int get(void *dev, size_t bytes)
+    {
+        for (size_t o = 0; o < bytes; o += IO_CHUNK) {
+            const size_t n = std::min(IO_CHUNK, bytes - o);
+            if (fread(bounce, 1, n, f) != n) { qsmrt_set_error("scene file is truncated"); return 1; }
+            CUDA_TRY(cudaMemcpy(static_cast<char *>(dev) + o, bounce, n, cudaMemcpyHostToDevice));
+        }
+        return 0;
+    }
+};
+} // namespace
+
+int qsmrt_scene_save(qsmrt_scene *s, const char *path, uint32_t flags)
+{
+    SCENE_ENTER(s);
+    if (!path) FAIL("null path");
+    const bool with_bvh = (flags & QSMRT_SAVE_BVH) != 0;
+    if (with_bvh && do_commit(s, nullptr, nullptr)) return 1;
+    CUDA_TRY(cudaDeviceSynchronize());
+    FileIO io;
+    if (io.open(path, "wb")) return 1;
+    SceneFileHeader h{};
+    memcpy(h.magic, "QSMRTSC1", 8);
+    h.version = 1; h.flags = (with_bvh && s->ntris) ? QSMRT_SAVE_BVH : 0u;
+    h.ngeoms = s->geoms.size();
+    for (const Geometry &g : s->geoms) { h.ntris += g.T; h.nverts += g.V; }
+    h.leaf_max = s->bopt.leaf_max; h.quant_frac = s->bopt.quant_frac;
+    if (h.flags) {
+        h.use_q = s->use_qnodes ? 1 : 0; h.stats = s->stats;
+        for (int a = 0; a < 3; ++a) { h.glo[a] = s->glo[a]; h.cell[a] = s->cell[a]; }
+    }
+    if (fwrite(&h, sizeof(h), 1, io.f) != 1) FAIL("short write");
+    for (const Geometry &g : s->geoms) {
+        const uint64_t vt[2] = { g.V, g.T };
+        if (fwrite(vt, sizeof(vt), 1, io.f) != 1) FAIL("short write");
+        if (io.put(g.verts, 3 * g.V * sizeof(float)) || io.put(g.idx, 3 * g.T * sizeof(uint32_t))) return 1;
+    }
+    if (h.flags) {
+        const uint64_t T = s->ntris, NN = std::max<uint64_t>(T - 1, 1);
+        if (io.put(s->params, sizeof(BuildParams)) || io.put(s->tnodes, NN * sizeof(TNode)) ||
+            (s->use_qnodes && io.put(s->qnodes, NN * sizeof(QNode))) || io.put(s->tris, T * sizeof(TriRec)) ||
+            io.put(s->order, T * sizeof(uint32_t)) || io.put(s->keys, T * sizeof(uint64_t)))
+            return 1;
+    }
+    return 0;
+}
+
+int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out)
+{
+    if (!out || !path) FAIL("null pointer");
+    *out = nullptr;
+    qsmrt_scene *s = nullptr;
+    if (qsmrt_scene_create(cuda_device, &s)) return 1;
+    auto body = [&]() -> int {
+        SCENE_ENTER(s);
+        FileIO io;
+        if (io.open(path, "rb")) return 1;
+        SceneFileHeader h;
+        if (fread(&h, sizeof(h), 1, io.f) != 1 || memcmp(h.magic, "QSMRTSC1", 8) != 0 || h.version != 1)
+            FAIL("%s is not a qsmrt scene file (version 1)", path);
+        if (h.ntris >= (1ull << 29) || h.nverts >= (1ull << 32) || h.leaf_max < 1 || h.leaf_max > QSMRT_LEAF_MAX) FAIL("corrupt scene file header");
+        uint64_t T = 0, V = 0;
+        for (uint64_t gi = 0; gi < h.ngeoms; ++gi) {
+            uint64_t vt[2];
+            if (fread(vt, sizeof(vt), 1, io.f) != 1) FAIL("scene file is truncated");
+            if (vt[0] > h.nverts || vt[1] > h.ntris) FAIL("corrupt scene file");
+            Geometry g; g.V = vt[0]; g.T = vt[1];
+            if (dmalloc(&g.verts, 3 * g.V) || dmalloc(&g.idx, 3 * g.T) ||
+                io.get(g.verts, 3 * g.V * sizeof(float)) || io.get(g.idx, 3 * g.T * sizeof(uint32_t))) { dfree(g.verts); dfree(g.idx); return 1; }
+            s->geoms.push_back(g);
+            T += g.T; V += g.V;
+        }
+        if (T != h.ntris || V != h.nverts) FAIL("corrupt scene file (geometry sizes)");
+        s->bopt.leaf_max = h.leaf_max; s->bopt.quant_frac = h.quant_frac;
+        if (!(h.flags & QSMRT_SAVE_BVH) || T == 0) return 0;        // geometry only: the first query builds
+        const uint32_t G = (uint32_t)s->geoms.size();
+        const uint64_t NN = std::max<uint64_t>(T - 1, 1);
+        s->ntris = T; s->nverts = V;
+        std::vector<uint64_t> goff(G + 1, 0), voff(G + 1, 0);
+        { uint64_t t = 0, v = 0; for (uint32_t g = 0; g < G; ++g) { goff[g] = t; voff[g] = v; t += s->geoms[g].T; v += s->geoms[g].V; } goff[G] = t; voff[G] = v; }
+        if (dmalloc(&s->goff, G + 1) || dmalloc(&s->voff, G + 1) || dmalloc(&s->params, 1) || dmalloc(&s->tnodes, NN) ||
+            (h.use_q && dmalloc(&s->qnodes, NN)) || dmalloc(&s->tris, T) || dmalloc(&s->order, T) || dmalloc(&s->keys, T))
+            return 1;
+        CUDA_TRY(cudaMemcpy(s->goff, goff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->voff, voff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
+        else {
+            if (dmalloc(&s->verts, 3 * V) || dmalloc(&s->idx, 3 * T)) return 1;
+            s->own_concat = true;
+            for (uint32_t g = 0; g < G; ++g) {
+                const Geometry &ge = s->geoms[g];
+                if (ge.V) CUDA_TRY(cudaMemcpy(s->verts + 3 * voff[g], ge.verts, 3 * ge.V * sizeof(float), cudaMemcpyDeviceToDevice));
+                if (ge.T) k_rebase_idx<<<(unsigned)((3 * ge.T + 255) / 256), 256>>>(ge.idx, s->idx + 3 * goff[g], 3 * ge.T, (uint32_t)voff[g]);
+            }
+        }
+        if (io.get(s->params, sizeof(BuildParams)) || io.get(s->tnodes, NN * sizeof(TNode)) ||
+            (h.use_q && io.get(s->qnodes, NN * sizeof(QNode))) || io.get(s->tris, T * sizeof(TriRec)) ||
+            io.get(s->order, T * sizeof(uint32_t)) || io.get(s->keys, T * sizeof(uint64_t)))
+            return 1;
+        CUDA_TRY(cudaDeviceSynchronize());
+        s->use_qnodes = h.use_q != 0;
+        s->stats = h.stats;
+        for (int a = 0; a < 3; ++a) { s->glo[a] = h.glo[a]; s->cell[a] = h.cell[a]; }
+        s->committed = true;
+        return 0;
+    };
+    if (body()) { qsmrt_scene_destroy(s); return 1; }
+    *out = s;
+    return 0;
+}
+
+// per-vertex exposure from per-triangle exposure: vert_counts[v] += tri_counts[t] for the three corners of t
+// (ray_casting.py:289-292: hit_tris = triangles[prim_ids]; hit_vert_ids = np.unique(hit_tris))
+int qsmrt_vertex_exposure(qsmrt_scene *s, const uint32_t *tri_counts, uint32_t *vert_counts, void *stream)
+{
+    SCENE_ENTER(s);
+    if (!tri_counts || !vert_counts) FAIL("null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (do_commit(s, st, nullptr)) return 1;
+    if (s->ntris == 0) return 0;
+    return trv_vertex_exposure(s->idx, s->ntris, tri_counts, vert_counts, st);
 }
 
 int qsmrt_get_stats(qsmrt_scene *s, qsmrt_stats *out)
@@ -891,13 +1197,13 @@ int qsmrt_get_stats(qsmrt_scene *s, qsmrt_stats *out)
 
 int qsmrt_debug_get_build(qsmrt_scene *s, uint64_t *keys, uint32_t *order, void *nodes)
 {
-    if (use_device(s)) return 1;
+    SCENE_ENTER(s);
     if (do_commit(s, nullptr, nullptr)) return 1;
     uint64_t T = s->ntris;
     if (T == 0) return 0;
     if (keys) CUDA_TRY(cudaMemcpy(keys, s->keys, T * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (order) CUDA_TRY(cudaMemcpy(order, s->order, T * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (nodes && !s->bnodes) FAIL("binary nodes were not kept: call qsmrt_debug_set_keep_binary_nodes(1) before the commit");
+    if (nodes && !s->bnodes) FAIL("binary nodes were not kept: set QSMRT_OPT_KEEP_BINARY_NODES before the commit");
     if (nodes) CUDA_TRY(cudaMemcpy(nodes, s->bnodes, (2 * T - 1) * sizeof(BNode), cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -30,6 +30,8 @@
 //   1  parallel grid: origin0 + i*du + j*dv, direction dir  (same arithmetic as k_gen_parallel)
 //   2  hemisphere Monte-Carlo about +z from points[n][3] (+ offset along normals[n][3]),
 //      direction k of point p from a counter-based hash of (seed, p, k) (same as k_gen_hemisphere)
+//   3  a sweep of parallel grids in ONE launch: grid a of `sweep[a][12]` = (origin0, du, dv, dir), all nu x nv;
+//      ray index = a * per_grid_rays + the index inside grid a (a solar sweep without 63 kernel tails)
 
 __device__ __forceinline__ void ld256f(const void *p, float4 &a, float4 &b)
 {
@@ -72,7 +74,9 @@ struct RaySource {
     const float *rays;                          // 0
     f3 o0, du, dv, dir; uint64_t nu;            // 1
     const float *points, *normals; uint64_t seed; float offset;                     // 2
+    uint64_t point_base;                        // 2: index of points[0] in the sample (hash of (seed, point_base + p, k))
     uint32_t dir_begin, dir_count;              // 2: this launch draws directions [dir_begin, dir_begin + dir_count) of each point
+    const float *sweep; uint64_t per_grid_rays, per_grid_slots;                    // 3 (nu as in 1)
 };
 
 __device__ __forceinline__ Ray source_ray(const RaySource &S, uint64_t i)
@@ -85,6 +89,16 @@ __device__ __forceinline__ Ray source_ray(const RaySource &S, uint64_t i)
                  __fmaf_rn(fu, S.du.z, __fmaf_rn(fv, S.dv.z, S.o0.z)) };
         return make_ray(O, S.dir);
     }
+    if (S.kind == 3) {
+        const uint64_t a = i / S.per_grid_rays, li = i - a * S.per_grid_rays;
+        const float4 *g = reinterpret_cast<const float4 *>(S.sweep + 12 * a);      // the same arithmetic as kind 1
+        const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);          // o0.xyz du.x | du.yz dv.xy | dv.z dir.xyz
+        float fu = (float)(li % S.nu), fv = (float)(li / S.nu);
+        f3 O = { __fmaf_rn(fu, g0.w, __fmaf_rn(fv, g1.z, g0.x)),
+                 __fmaf_rn(fu, g1.x, __fmaf_rn(fv, g1.w, g0.y)),
+                 __fmaf_rn(fu, g1.y, __fmaf_rn(fv, g2.x, g0.z)) };
+        return make_ray(O, f3{ g2.y, g2.z, g2.w });
+    }
     const uint64_t p = i / S.dir_count;
     const uint32_t k = S.dir_begin + (uint32_t)(i - p * S.dir_count);
     f3 O = { S.points[3 * p], S.points[3 * p + 1], S.points[3 * p + 2] };
@@ -93,7 +107,7 @@ __device__ __forceinline__ Ray source_ray(const RaySource &S, uint64_t i)
         O.y = __fmaf_rn(S.offset, S.normals[3 * p + 1], O.y);
         O.z = __fmaf_rn(S.offset, S.normals[3 * p + 2], O.z);
     }
-    return make_ray(O, hemisphere_dir(S.seed, p, k));
+    return make_ray(O, hemisphere_dir(S.seed, S.point_base + p, k));
 }
 
 struct TraceArgs {
@@ -102,7 +116,7 @@ struct TraceArgs {
     uint64_t N; uint32_t row_len; uint64_t nslots;
     CastOut out; uint8_t *occluded; float tnear, tfar;          // MODE 0 / 1
     int32_t *counts;                                            // MODE 2
-    uint32_t *accum; const uint64_t *goff;                      // MODE 3 / 4
+    uint32_t *accum; const uint64_t *goff; uint64_t accum_stride;   // MODE 3 / 4 (stride: one row of counts per grid of a sweep, 0 = one row)
     const uint8_t *alive; uint8_t *hitflag;                     // MODE 5 (both indexed by sorted triangle)
     unsigned long long *cursor, *stats;
     int refill, want, tri_min, node_path;
@@ -177,6 +191,22 @@ k_trace5(const TraceArgs A)
         const bool idle = (cur == TR_SENTINEL) && (tri_i >= tri_end);
         const unsigned im = __ballot_sync(FULL, idle);
         if (im == FULL || (!exhausted && __popc(im) >= A.refill)) {
+            if (MODE == 3 || MODE == 4) {
+                // hit / miss aggregation (north_star item 4): the lanes retiring together are neighbours of a ray tile
+                // (MODE 3: they mostly hit the same few triangles) or directions of one query point (MODE 4), so the
+                // lanes with equal targets are grouped with MATCH.ANY and each group sends ONE atomicAdd of its popc
+                const bool add = idle && have_ray && ((MODE == 3) == (best_prim != QSMRT_INVALID));
+                const unsigned am = __ballot_sync(FULL, add);
+                if (add) {
+                    unsigned long long key;
+                    if (MODE == 3) key = (A.goff ? A.goff[best_geom] : 0ull) + best_prim +
+                                         (A.src.kind == 3 ? (ray_i / A.src.per_grid_rays) * A.accum_stride : 0ull);
+                    else key = ray_i / A.src.dir_count;
+                    const unsigned grp = __match_any_sync(am, key);
+                    if ((grp & lt) == 0u) atomicAdd(&A.accum[key], (uint32_t)__popc(grp));
+                }
+                if (idle) have_ray = false;
+            }
             if (idle && have_ray) {
                 have_ray = false;
                 if (MODE == 0) {
@@ -201,11 +231,7 @@ k_trace5(const TraceArgs A)
                     A.occluded[ray_i] = best_prim != QSMRT_INVALID ? 1 : 0;
                 } else if (MODE == 2) {
                     A.counts[ray_i] = overflow ? -1 : cnt;           // -1: k_count_fix recounts this ray exactly
-                } else if (MODE == 3) {
-                    if (best_prim != QSMRT_INVALID) atomicAdd(&A.accum[(A.goff ? A.goff[best_geom] : 0ull) + best_prim], 1u);
-                } else if (MODE == 4) {
-                    if (best_prim == QSMRT_INVALID) atomicAdd(&A.accum[ray_i / A.src.dir_count], 1u);     // unoccluded sky ray
-                } else {
+                } else if (MODE == 5) {
                     if (best_prim != QSMRT_INVALID) A.hitflag[best_tri] = 1;
                 }
             }
@@ -219,8 +245,14 @@ k_trace5(const TraceArgs A)
                 exhausted = base + (unsigned long long)need >= A.nslots;
                 if (idle) {
                     const uint64_t slot = base + __popc(im & lt);
-                    uint64_t i;
-                    if (slot < A.nslots && ray_index_of_slot(slot, A.N, A.row_len, i)) {
+                    uint64_t i = 0;
+                    bool ok = slot < A.nslots;
+                    if (A.src.kind == 3) {          // sweep: slot -> (grid, slot inside the grid)
+                        const uint64_t a = slot / A.src.per_grid_slots;
+                        ok = ok && ray_index_of_slot(slot - a * A.src.per_grid_slots, A.src.per_grid_rays, A.row_len, i);
+                        i += a * A.src.per_grid_rays;
+                    } else ok = ok && ray_index_of_slot(slot, A.N, A.row_len, i);
+                    if (ok) {
                         r = source_ray(A.src, i);
                         if (QUANT) {
                             const float ax = A.sc.cell[0] * r.idx, ay = A.sc.cell[1] * r.idy, az = A.sc.cell[2] * r.idz;

@@ -13,6 +13,7 @@
 // traffic on the hot path) and spills to a local array only below depth
 // TR_SSTACK.  Nodes are fetched as four 16-byte loads, triangles as three.
 #include <algorithm>
+#include <cstring>
 #include "common.cuh"
 #include "traverse.h"
 
@@ -592,6 +593,18 @@ k_accumulate_hits(const uint32_t *__restrict__ geom, const uint32_t *__restrict_
     atomicAdd(&tri_counts[goff[g] + p], 1u);
 }
 
+// per-vertex exposure: a vertex inherits the hits of every triangle it is a corner of (scene order; the
+// concatenated index array is already rebased into scene vertex numbering)
+__global__ void __launch_bounds__(256)
+k_vertex_exposure(const uint32_t *__restrict__ idx, uint64_t ntris, const uint32_t *__restrict__ tri_counts, uint32_t *__restrict__ vert_counts)
+{
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= ntris) return;
+    const uint32_t c = tri_counts[t];
+    if (c == 0u) return;
+    atomicAdd(&vert_counts[idx[3 * t]], c); atomicAdd(&vert_counts[idx[3 * t + 1]], c); atomicAdd(&vert_counts[idx[3 * t + 2]], c);
+}
+
 // ------------------------------------------------------------ closest points
 // Open3D ComputeClosestPoints / ComputeDistance (rtcPointQuery + ClosestPointFunc;
 // reference: compute_signed_distance at pyQSM/viz/ray_casting.py:250,255).
@@ -853,47 +866,43 @@ k_closest_points_warp(SceneView sc, const float *__restrict__ pts, uint64_t N, f
 }
 
 // --------------------------------------------------------------- launchers
-int g_trv_variant = 2;      // 1 = one independent loop per thread, 2 = persistent warp-uniform kernel (ships)
-int g_trv_tuning[4] = { 12, 16, 1, 0 }; // refill, want, tri_min, counters -- tuned on C2 (profiles/r01_tuning.txt)
-unsigned long long *g_trv_stats_dev = nullptr;
-int g_trv_cp_warp_max = 16384;          // closest-point queries up to this many points run one warp per query (qsmrt_debug_set_cp_warp_max)
-int g_trv_node_path = 0;                // 0 LSU 256-bit loads, 1 TEX, 2 half/half (qsmrt_debug_set_node_path)
-
-// work cursors of the persistent kernels: a per-device ring so launches in flight never share one
+// All launch state is per scene (TrvState, traverse.h): tuning, the ring of work cursors of the persistent
+// kernels (launches in flight never share one), the fetch-counter buffer and the occupancy cache.
 namespace {
 constexpr int CURSOR_RING = 256;
-unsigned long long *g_cursor_ring[64] = {};
-unsigned g_cursor_next[64] = {};
 
-int next_cursor(unsigned long long **out, cudaStream_t st)
+int next_cursor(TrvState &ts, unsigned long long **out, cudaStream_t st)
 {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) { qsmrt_set_error("device index %d out of range", dev); return 1; }
-    if (!g_cursor_ring[dev]) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g_cursor_ring[dev]), CURSOR_RING * sizeof(unsigned long long)));
-    unsigned k = g_cursor_next[dev]++ % CURSOR_RING;
-    *out = g_cursor_ring[dev] + k;
+    if (!ts.cursor_ring) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&ts.cursor_ring), CURSOR_RING * sizeof(unsigned long long)));
+    unsigned k = ts.cursor_next++ % CURSOR_RING;
+    *out = ts.cursor_ring + k;
     CUDA_TRY(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
     return 0;
 }
 
-template <int MODE, bool COUNTERS, bool QUANT>
-int launch_trace5_q(TraceArgs &a, size_t smem, int per_sm, int sms, cudaStream_t st)
+int stats_buffer(TrvState &ts, unsigned long long **out, cudaStream_t st)
 {
-    // occupancy of this instantiation at this stack size: queried once per device (small launches are latency bound)
-    static size_t cached_smem[64] = {};
-    static int cached_per_sm[64] = {};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || cached_smem[dev] != smem || cached_per_sm[dev] == 0) {
+    if (!ts.stats) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&ts.stats), 16 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(ts.stats, 0, 16 * sizeof(unsigned long long), st));
+    *out = ts.stats;
+    return 0;
+}
+
+template <int MODE, bool COUNTERS, bool QUANT>
+int launch_trace5_q(TrvState &ts, TraceArgs &a, size_t smem, cudaStream_t st)
+{
+    // occupancy of this instantiation at this stack size: queried once per scene (small launches are latency bound)
+    const void *fn = reinterpret_cast<const void *>(&k_trace5<MODE, COUNTERS, QUANT>);
+    int per_sm = 0;
+    for (const TrvState::Occ &o : ts.occ) if (o.fn == fn && o.smem == smem) per_sm = o.per_sm;
+    if (per_sm == 0) {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_trace5<MODE, COUNTERS, QUANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace5<MODE, COUNTERS, QUANT>, TR_BLOCK, smem));
-        if (dev >= 0 && dev < 64) { cached_smem[dev] = smem; cached_per_sm[dev] = per_sm; }
-    } else {
-        per_sm = cached_per_sm[dev];
+        if (per_sm < 1) { qsmrt_set_error("persistent kernel does not fit (smem %zu)", smem); return 1; }
+        ts.occ.push_back(TrvState::Occ{ fn, smem, per_sm });
     }
-    if (per_sm < 1) { qsmrt_set_error("persistent kernel does not fit (smem %zu)", smem); return 1; }
-    unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
+    if (ts.sms == 0) CUDA_TRY(cudaDeviceGetAttribute(&ts.sms, cudaDevAttrMultiProcessorCount, ts.device));
+    unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * ts.sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
     k_trace5<MODE, COUNTERS, QUANT><<<g, TR_BLOCK, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -901,20 +910,17 @@ int launch_trace5_q(TraceArgs &a, size_t smem, int per_sm, int sms, cudaStream_t
 
 // common launch of the persistent kernel: tuning, work cursor, occupancy-sized grid
 template <int MODE, bool COUNTERS>
-int launch_trace5(TraceArgs &a, size_t smem, cudaStream_t st)
+int launch_trace5(TrvState &ts, TraceArgs &a, size_t smem, cudaStream_t st)
 {
-    a.refill = g_trv_tuning[0]; a.want = std::max(1, g_trv_tuning[1]); a.tri_min = std::max(1, g_trv_tuning[2]);
-    a.node_path = a.sc.node_tex ? g_trv_node_path : 0;
-    if (next_cursor(&a.cursor, st)) return 1;
-    int dev = 0, per_sm = 0, sms = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (a.sc.qnodes) return launch_trace5_q<MODE, COUNTERS, true>(a, smem, per_sm, sms, st);
-    return launch_trace5_q<MODE, COUNTERS, false>(a, smem, per_sm, sms, st);
+    a.refill = ts.opt.refill; a.want = std::max(1, ts.opt.want); a.tri_min = std::max(1, ts.opt.tri_min);
+    a.node_path = a.sc.node_tex ? ts.opt.node_path : 0;
+    if (next_cursor(ts, &a.cursor, st)) return 1;
+    if (a.sc.qnodes) return launch_trace5_q<MODE, COUNTERS, true>(ts, a, smem, st);
+    return launch_trace5_q<MODE, COUNTERS, false>(ts, a, smem, st);
 }
 
 inline size_t stack_bytes(const SceneView &sc) { return (size_t)((int)sc.height + 2) * TR_BLOCK * sizeof(int); }
-inline bool use_v5(const SceneView &sc, size_t smem) { return g_trv_variant == 2 && sc.ntris && smem <= 96 * 1024; }
+inline bool use_v5(const TrvState &ts, const SceneView &sc, size_t smem) { return ts.opt.variant == 2 && sc.ntris && smem <= 96 * 1024; }
 
 uint64_t slots_for(uint64_t N, uint32_t row_len)
 {
@@ -924,7 +930,21 @@ uint64_t slots_for(uint64_t N, uint32_t row_len)
 }
 } // namespace
 
-int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,
+void trv_state_free(TrvState &ts)
+{
+    if (ts.cursor_ring) cudaFree(ts.cursor_ring);
+    if (ts.stats) cudaFree(ts.stats);
+    ts.cursor_ring = nullptr; ts.stats = nullptr; ts.occ.clear();
+}
+
+int trv_read_counters(TrvState &ts, unsigned long long out[16])
+{
+    memset(out, 0, 16 * sizeof(unsigned long long));
+    if (ts.stats) CUDA_TRY(cudaMemcpy(out, ts.stats, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int trv_cast_rays(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,
                   uint32_t *prim, float *uv, float *nrm, cudaStream_t st)
 {
     if (N == 0) return 0;
@@ -934,17 +954,15 @@ int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t r
         uint64_t rows = N / row_len, warps = (uint64_t)((row_len + 7u) / 8u) * ((rows + 3) / 4);
         grid = (unsigned)((warps + TR_BLOCK / 32 - 1) / (TR_BLOCK / 32));
     }
-    if (use_v5(sc, stack_bytes(sc))) {
+    if (use_v5(ts, sc, stack_bytes(sc))) {
         TraceArgs a{};
         a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = row_len; a.nslots = slots_for(N, row_len);
         a.out = CastOut{ t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm };
         a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
-        if (g_trv_tuning[3]) {
-            if (!g_trv_stats_dev) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g_trv_stats_dev), 16 * sizeof(unsigned long long)));
-            CUDA_TRY(cudaMemsetAsync(g_trv_stats_dev, 0, 16 * sizeof(unsigned long long), st));
-            a.stats = g_trv_stats_dev;
-            if (launch_trace5<0, true>(a, stack_bytes(sc), st)) return 1;
-        } else if (launch_trace5<0, false>(a, stack_bytes(sc), st)) return 1;
+        if (ts.opt.counters) {
+            if (stats_buffer(ts, &a.stats, st)) return 1;
+            if (launch_trace5<0, true>(ts, a, stack_bytes(sc), st)) return 1;
+        } else if (launch_trace5<0, false>(ts, a, stack_bytes(sc), st)) return 1;
     } else {
         // per-thread loop: the simple kernel (A/B reference; also used when the LBVH is too deep for the shared-memory stack)
         k_cast_rays<<<grid, TR_BLOCK, 0, st>>>(sc, rays, N, row_len, t_hit, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
@@ -953,17 +971,17 @@ int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t r
     return 0;
 }
 
-int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st)
+int trv_count(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st)
 {
     if (N == 0) return 0;
     const int depth = (int)sc.height + 2;
     const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * CNT_SET) * TR_BLOCK * sizeof(int);
-    if (use_v5(sc, smem)) {
+    if (use_v5(ts, sc, smem)) {
         TraceArgs a{};
         a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
         a.counts = out; a.depth = depth; a.multi_geom = ngeoms > 1;
-        if (launch_trace5<2, false>(a, smem, st)) return 1;
-        int sms = 148;
+        if (launch_trace5<2, false>(ts, a, smem, st)) return 1;
+        const int sms = ts.sms ? ts.sms : 148;
         k_count_fix<<<(unsigned)std::min<uint64_t>(grid_for(N, TR_BLOCK), (uint64_t)sms * 8), TR_BLOCK, 0, st>>>(sc, rays, N, out);
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -973,14 +991,14 @@ int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, 
     return 0;
 }
 
-int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st)
+int trv_occluded(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st)
 {
     if (N == 0) return 0;
-    if (use_v5(sc, stack_bytes(sc))) {
+    if (use_v5(ts, sc, stack_bytes(sc))) {
         TraceArgs a{};
         a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
         a.occluded = out; a.tnear = tnear; a.tfar = tfar; a.depth = (int)sc.height + 2;
-        if (launch_trace5<1, false>(a, stack_bytes(sc), st)) return 1;
+        if (launch_trace5<1, false>(ts, a, stack_bytes(sc), st)) return 1;
     } else {
         k_test_occlusions<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, tnear, tfar, out);
     }
@@ -1072,57 +1090,81 @@ int trv_accumulate_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, 
     return 0;
 }
 
+int trv_vertex_exposure(const uint32_t *idx, uint64_t ntris, const uint32_t *tri_counts, uint32_t *vert_counts, cudaStream_t st)
+{
+    if (ntris == 0) return 0;
+    k_vertex_exposure<<<grid_for(ntris, 256), 256, 0, st>>>(idx, ntris, tri_counts, vert_counts);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // Fused drivers: rays generated inside the persistent kernel, results reduced on the device.
-int trv_sun_exposure(const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+int trv_sun_exposure(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
                      const float dv[3], const float dir[3], const uint64_t *goff, uint32_t *tri_counts, cudaStream_t st)
 {
     if (nu * nv == 0 || sc.ntris == 0) return 0;
-    if (!use_v5(sc, stack_bytes(sc))) { qsmrt_set_error("sun_exposure needs the persistent kernel (BVH height %u too deep?)", sc.height); return 1; }
+    if (!use_v5(ts, sc, stack_bytes(sc))) { qsmrt_set_error("sun_exposure needs the persistent kernel (BVH height %u too deep?)", sc.height); return 1; }
     TraceArgs a{};
     a.sc = sc; a.src.kind = 1; a.src.nu = nu;
     a.src.o0 = f3{ o0[0], o0[1], o0[2] }; a.src.du = f3{ du[0], du[1], du[2] };
     a.src.dv = f3{ dv[0], dv[1], dv[2] }; a.src.dir = f3{ dir[0], dir[1], dir[2] };
     a.N = nu * nv; a.row_len = nu >= 8 && nu < (1ull << 32) ? (uint32_t)nu : 0; a.nslots = slots_for(a.N, a.row_len);
     a.accum = tri_counts; a.goff = goff; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
-    return launch_trace5<3, false>(a, stack_bytes(sc), st);
+    return launch_trace5<3, false>(ts, a, stack_bytes(sc), st);
 }
 
-static RaySource hemisphere_source(const float *points, const float *normals, uint32_t dir_begin, uint32_t dir_count,
-                                    uint64_t seed, float offset)
+// a whole sweep of parallel grids (solar angles) in one launch: sweep_dev[n_grids][12] = origin0, du, dv, dir
+int trv_sun_exposure_sweep(TrvState &ts, const SceneView &sc, uint32_t n_grids, const float *sweep_dev, uint64_t nu, uint64_t nv,
+                           const uint64_t *goff, uint32_t *tri_counts, uint64_t count_stride, cudaStream_t st)
+{
+    if (n_grids == 0 || nu * nv == 0 || sc.ntris == 0) return 0;
+    if (!use_v5(ts, sc, stack_bytes(sc))) { qsmrt_set_error("sun_exposure needs the persistent kernel (BVH height %u too deep?)", sc.height); return 1; }
+    TraceArgs a{};
+    a.sc = sc; a.src.kind = 3; a.src.nu = nu; a.src.sweep = sweep_dev;
+    a.src.per_grid_rays = nu * nv;
+    a.row_len = nu >= 8 && nu < (1ull << 32) ? (uint32_t)nu : 0;
+    a.src.per_grid_slots = slots_for(a.src.per_grid_rays, a.row_len);
+    a.N = a.src.per_grid_rays * n_grids; a.nslots = a.src.per_grid_slots * n_grids;
+    a.accum = tri_counts; a.goff = goff; a.accum_stride = count_stride; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
+    return launch_trace5<3, false>(ts, a, stack_bytes(sc), st);
+}
+
+static RaySource hemisphere_source(const float *points, const float *normals, uint64_t point_base, uint32_t dir_begin,
+                                    uint32_t dir_count, uint64_t seed, float offset)
 {
     RaySource s{};
     s.kind = 2; s.points = points; s.normals = normals; s.dir_begin = dir_begin; s.dir_count = dir_count;
-    s.seed = seed; s.offset = offset;
+    s.seed = seed; s.offset = offset; s.point_base = point_base;
     return s;
 }
 
-int trv_sky_visibility(const SceneView &sc, const float *points, const float *normals, uint64_t n_points,
+int trv_sky_visibility(TrvState &ts, const SceneView &sc, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st)
 {
     if (n_points == 0 || dir_count == 0) return 0;
-    if (g_trv_variant != 2 || stack_bytes(sc) > 96 * 1024) { qsmrt_set_error("sky_visibility needs the persistent kernel"); return 1; }
+    if (ts.opt.variant != 2 || stack_bytes(sc) > 96 * 1024) { qsmrt_set_error("sky_visibility needs the persistent kernel"); return 1; }
     TraceArgs a{};
-    a.sc = sc; a.src = hemisphere_source(points, normals, dir_begin, dir_count, seed, offset);
+    a.sc = sc; a.src = hemisphere_source(points, normals, point_base, dir_begin, dir_count, seed, offset);
     a.N = n_points * (uint64_t)dir_count; a.row_len = 0; a.nslots = a.N;
     a.accum = unoccluded; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
-    return launch_trace5<4, false>(a, stack_bytes(sc), st);
+    return launch_trace5<4, false>(ts, a, stack_bytes(sc), st);
 }
 
-int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points,
+int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, cudaStream_t st)
 {
     uint64_t n = n_points * (uint64_t)dir_count;
     if (n == 0) return 0;
-    k_gen_hemisphere<<<grid_for(n, 256), 256, 0, st>>>(rays, hemisphere_source(points, normals, dir_begin, dir_count, seed, offset), n);
+    k_gen_hemisphere<<<grid_for(n, 256), 256, 0, st>>>(rays, hemisphere_source(points, normals, point_base, dir_begin, dir_count, seed, offset), n);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-int trv_closest_points(const SceneView &sc, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
+int trv_closest_points(TrvState &ts, const SceneView &sc, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
                        uint32_t *prim, float *uv, float *nrm, cudaStream_t st)
 {
     if (N == 0) return 0;
-    if (N <= (uint64_t)g_trv_cp_warp_max && sc.height + 2u <= 160u)       // small batch: one warp per query (latency), else one thread (throughput)
+    if (N <= (uint64_t)ts.opt.cp_warp_max && sc.height + 2u <= 160u)       // small batch: one warp per query (latency), else one thread (throughput)
         k_closest_points_warp<<<(unsigned)((N + CPW_WARPS - 1) / CPW_WARPS), TR_BLOCK, 0, st>>>(sc, pts, N, closest, dist, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
     else
     k_closest_points<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, pts, N, closest, dist, geom, prim, reinterpret_cast<float2 *>(uv), nrm);
@@ -1147,18 +1189,18 @@ int trv_apply_sign(float *dist, const int32_t *counts, uint64_t N, cudaStream_t 
 }
 
 // one layer of the peel projection: cast the grid against the triangles still alive, flag the owners of the closest hits
-int trv_peel_cast(const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3], const float dv[3],
+int trv_peel_cast(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3], const float dv[3],
                   const float dir[3], const uint8_t *alive, uint8_t *hitflag, cudaStream_t st)
 {
     if (nu * nv == 0 || sc.ntris == 0) return 0;
-    if (!use_v5(sc, stack_bytes(sc))) { qsmrt_set_error("peel projection needs the persistent kernel"); return 1; }
+    if (!use_v5(ts, sc, stack_bytes(sc))) { qsmrt_set_error("peel projection needs the persistent kernel"); return 1; }
     TraceArgs a{};
     a.sc = sc; a.src.kind = 1; a.src.nu = nu;
     a.src.o0 = f3{ o0[0], o0[1], o0[2] }; a.src.du = f3{ du[0], du[1], du[2] };
     a.src.dv = f3{ dv[0], dv[1], dv[2] }; a.src.dir = f3{ dir[0], dir[1], dir[2] };
     a.N = nu * nv; a.row_len = nu >= 8 && nu < (1ull << 32) ? (uint32_t)nu : 0; a.nslots = slots_for(a.N, a.row_len);
     a.alive = alive; a.hitflag = hitflag; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
-    return launch_trace5<5, false>(a, stack_bytes(sc), st);
+    return launch_trace5<5, false>(ts, a, stack_bytes(sc), st);
 }
 
 int trv_peel_update(const SceneView &sc, const uint32_t *order, uint8_t *alive, uint8_t *hitflag, int32_t *layer_of,

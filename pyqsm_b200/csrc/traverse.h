@@ -1,18 +1,37 @@
 // traverse.h -- launchers of the traversal / scan / ray-generator kernels.
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 struct HitRec { float t, u, v; uint32_t geom, prim; };   // 20-byte raw hit (list_intersections scratch)
 
-extern int g_trv_variant;
-extern int g_trv_node_path;
-extern int g_trv_cp_warp_max;
-extern int g_trv_tuning[4];
-extern unsigned long long *g_trv_stats_dev;
-int trv_cast_rays(const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,
+// Per-scene traversal options (qsmrt_scene_set_option), read at every launch.
+struct TrvOptions {
+    int variant = 2;        // 1 = one independent loop per thread, 2 = persistent warp-uniform kernel (ships)
+    int refill = 12;        // idle lanes that trigger a refill          } tuned on C2
+    int want = 16;          // node phase ends below this many searching lanes } (profiles/r01_tuning.txt)
+    int tri_min = 1;        // triangle-phase early-exit threshold
+    int counters = 0;       // 1: cast_rays launches count the node records / triangles they fetch
+    int node_path = 0;      // 0 LSU 256-bit loads, 1 TEX, 2 half/half (L1 data-pipe experiment)
+    int cp_warp_max = 16384;// closest-point batches up to this size run one warp per query
+};
+
+// Per-scene launch state: options, the ring of work cursors of the persistent kernels, the counter buffer and
+// the occupancy cache.  Owned by the scene, so two scenes (or two threads with their own scenes) never share it.
+struct TrvState {
+    int device = 0, sms = 0;
+    TrvOptions opt;
+    unsigned long long *cursor_ring = nullptr; unsigned cursor_next = 0;
+    unsigned long long *stats = nullptr;
+    struct Occ { const void *fn; size_t smem; int per_sm; };
+    std::vector<Occ> occ;
+};
+void trv_state_free(TrvState &ts);
+int trv_read_counters(TrvState &ts, unsigned long long out[16]);
+int trv_cast_rays(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, uint32_t row_len, float *t_hit, uint32_t *geom,
                   uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
-int trv_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st);
-int trv_occluded(const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st);
+int trv_count(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st);
+int trv_occluded(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st);
 int trv_raw_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st);
 int trv_raw_fill_sort(const SceneView &sc, const float *rays, uint64_t N, const int64_t *raw_off,
                       HitRec *raw, int32_t *cnt, cudaStream_t st);
@@ -28,17 +47,20 @@ int trv_mark_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const 
                   uint8_t *vert_hit, cudaStream_t st);
 int trv_accumulate_hits(const uint32_t *geom, const uint32_t *prim, uint64_t N, const uint64_t *goff,
                         uint32_t ngeoms, uint32_t *tri_counts, cudaStream_t st);
-int trv_sun_exposure(const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
+int trv_vertex_exposure(const uint32_t *idx, uint64_t ntris, const uint32_t *tri_counts, uint32_t *vert_counts, cudaStream_t st);
+int trv_sun_exposure(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],
                      const float dv[3], const float dir[3], const uint64_t *goff, uint32_t *tri_counts, cudaStream_t st);
-int trv_sky_visibility(const SceneView &sc, const float *points, const float *normals, uint64_t n_points,
+int trv_sun_exposure_sweep(TrvState &ts, const SceneView &sc, uint32_t n_grids, const float *sweep_dev, uint64_t nu, uint64_t nv,
+                           const uint64_t *goff, uint32_t *tri_counts, uint64_t count_stride, cudaStream_t st);
+int trv_sky_visibility(TrvState &ts, const SceneView &sc, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st);
-int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points,
+int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, cudaStream_t st);
-int trv_closest_points(const SceneView &sc, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
+int trv_closest_points(TrvState &ts, const SceneView &sc, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
                        uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
 int trv_points_to_rays(const float *pts, float *rays, uint64_t N, cudaStream_t st);
 int trv_apply_sign(float *dist, const int32_t *counts, uint64_t N, cudaStream_t st);
-int trv_peel_cast(const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3], const float dv[3],
+int trv_peel_cast(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3], const float dv[3],
                   const float dir[3], const uint8_t *alive, uint8_t *hitflag, cudaStream_t st);
 int trv_peel_update(const SceneView &sc, const uint32_t *order, uint8_t *alive, uint8_t *hitflag, int32_t *layer_of,
                     int layer, const float dir[3], double *sums, cudaStream_t st);

@@ -1,9 +1,9 @@
 """Environmental ray-casting drivers: sunlight angle, rain angle and sky
 (cloud-cover / gap-fraction) simulations over a ``RaycastingScene``.
 
-The reference only states the intent -- ``README.md:131`` ("simulate ...
+The reference only states the intent -- ``README.md:127`` ("simulate ...
 sunlight angle, cloud cover and rain angle"), ``data/notes/methods.md:16,53-55``
-and ``data/notes/epiphyte_isolation_methods.md:17,43`` ("Ray casting: Parallel
+and ``data/notes/epiphyte_isolation_methods.md:17,45`` ("Ray casting: Parallel
 rays from nadir") -- and its only parallel-ray code is the 10 x 10 vertical
 grid of ``pyQSM/viz/ray_casting.py:159-165``.  These drivers are that pattern
 at scale: rays are generated inside the
@@ -36,17 +36,22 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def sun_exposure(scene, angles, grid=(4000, 4000), margin=0.05, shard=None, per_angle=False):
+def sun_exposure(scene, angles, grid=(4000, 4000), margin=0.05, shard=None, per_angle=False, per_vertex=False):
     """Sunlit-ray counts per triangle for a sweep of solar ``angles`` =
     [(elevation_deg, azimuth_deg), ...].
 
     For every angle a ``grid = (nu, nv)`` of parallel rays covering the scene
     bounds (as seen from the sun) is cast; a triangle's count is the number of
     rays whose *closest* hit it owns, i.e. its sunlit projected area in units
-    of one ray cell.  Returns ``{"counts": int32 [T] (or [A, T] with
-    per_angle), "cell_area": [A] m^2 per ray, "rays": total rays cast}`` on
-    the scene's device.  Triangles are in scene order (geometry offsets +
-    primitive id)."""
+    of one ray cell.  The whole sweep is ONE kernel launch
+    (``qsmrt_sun_exposure_sweep``): rays are generated in the kernel and hits
+    are added per triangle with warp-aggregated atomics.  Returns ``{"counts":
+    int32 [T] (or [A, T] with per_angle), "cell_area": [A] m^2 per ray,
+    "rays": total rays cast}`` on the scene's device; with ``per_vertex`` also
+    ``"vertex_counts"`` int32 [V] (or [A, V]): every vertex receives the counts
+    of the triangles it is a corner of (BASELINE config 2, "sunlight exposure
+    per leaf vertex"; ``ray_casting.py:289-292``).  Triangles and vertices are
+    in scene order (geometries in the order added)."""
     L = _lib.load()
     scene.commit()
     st = scene.stats()
@@ -61,18 +66,36 @@ def sun_exposure(scene, angles, grid=(4000, 4000), margin=0.05, shard=None, per_
         counts = torch.zeros(rows, max(ntri, 1), dtype=torch.int32, device=dev)
         cell = torch.zeros(len(angles), dtype=torch.float64)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        for k, (el, az) in mine:
+        grids = np.empty((len(mine), 12), np.float32)
+        for j, (k, (el, az)) in enumerate(mine):
             o0, du, dv, d = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), nu, nv, margin)
             cell[k] = float(np.linalg.norm(du.astype(np.float64)) * np.linalg.norm(dv.astype(np.float64)))
-            row = counts[k if per_angle else 0]
-            _lib.check(L.qsmrt_sun_exposure(scene._h, nu, nv, _f3(o0), _f3(du), _f3(dv), _f3(d), _ptr(row), stream))
+            grids[j] = np.concatenate([o0, du, dv, d])
+        if per_angle:
+            # one launch per contiguous run of this rank's angles (row a of the launch lands in row k0 + a)
+            j = 0
+            while j < len(mine):
+                e = j
+                while e + 1 < len(mine) and mine[e + 1][0] == mine[e][0] + 1:
+                    e += 1
+                blk = np.ascontiguousarray(grids[j:e + 1])
+                _lib.check(L.qsmrt_sun_exposure_sweep(scene._h, e + 1 - j, blk.ctypes.data_as(C.POINTER(C.c_float)), nu, nv,
+                                                      _ptr(counts[mine[j][0]]), counts.shape[1], stream))
+                j = e + 1
+        elif len(mine):
+            _lib.check(L.qsmrt_sun_exposure_sweep(scene._h, len(mine), grids.ctypes.data_as(C.POINTER(C.c_float)), nu, nv,
+                                                  _ptr(counts[0]), 0, stream))
         if shard:
             allreduce_sum(counts)
             cell_dev = cell.to(dev)
             allreduce_sum(cell_dev)
             cell = cell_dev.cpu()
         counts = counts[:, :ntri]
-    return {"counts": counts if per_angle else counts[0], "cell_area": cell, "rays": nu * nv * len(angles)}
+        out = {"counts": counts if per_angle else counts[0], "cell_area": cell, "rays": nu * nv * len(angles)}
+        if per_vertex:
+            vc = torch.stack([scene.vertex_exposure(counts[a]) for a in range(counts.shape[0])])
+            out["vertex_counts"] = vc if per_angle else vc[0]
+    return out
 
 
 def rain_interception(scene, angle_from_vertical_deg=20.0, azimuth_deg=0.0, grid=(10000, 10000), margin=0.05,
@@ -109,12 +132,14 @@ def rain_interception(scene, angle_from_vertical_deg=20.0, azimuth_deg=0.0, grid
             "mean_layers": float((hist.to(torch.float64) * layers).sum().item() / max(total, 1)), "rays": total}
 
 
-def sky_gap_fraction(scene, points, normals=None, n_dirs=1000, seed=5, offset=1e-4, shard=None):
+def sky_gap_fraction(scene, points, normals=None, n_dirs=1000, seed=5, offset=1e-4, shard=None, point_base=0):
     """Diffuse-sky (cloud cover) visibility: for each query point the share of
     ``n_dirs`` directions, uniform over the upper hemisphere about +z, along
     which no triangle is hit (any-hit occlusion from ``point + offset *
     normal``).  Directions come from a counter-based hash of (seed, point,
-    k), so a point sees the same sample however the work is sharded.
+    k), so a point sees the same sample however the work is sharded;
+    ``point_base`` is the index of ``points[0]`` in that sample (a block cut
+    out of a larger point set keeps its directions).
     Returns float32 ``[n_points]`` on the scene's device."""
     L = _lib.load()
     dev = scene.device
@@ -126,7 +151,7 @@ def sky_gap_fraction(scene, points, normals=None, n_dirs=1000, seed=5, offset=1e
         b, e = shard_range(int(n_dirs), *shard) if shard else (0, int(n_dirs))
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         if e > b and p.shape[0]:
-            _lib.check(L.qsmrt_sky_visibility(scene._h, _ptr(p), _ptr(nrm), p.shape[0], int(seed), float(offset), b, e - b,
+            _lib.check(L.qsmrt_sky_visibility(scene._h, _ptr(p), _ptr(nrm), p.shape[0], int(point_base), int(seed), float(offset), b, e - b,
                                               _ptr(free), stream))
         if shard:
             allreduce_sum(free)
@@ -163,7 +188,7 @@ def peel_projection(scene, direction=(0.0, 0.0, -1.0), grid=(2000, 2000), margin
             "layer_of": layer_of[:ntri]}
 
 
-def hemisphere_rays(points, normals=None, n_dirs=16, seed=5, offset=1e-4, dir_begin=0, device=None):
+def hemisphere_rays(points, normals=None, n_dirs=16, seed=5, offset=1e-4, dir_begin=0, device=None, point_base=0):
     """The exact rays ``sky_gap_fraction`` traces, materialised: float32 ``[n_points * n_dirs, 6]``."""
     L = _lib.load()
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -172,6 +197,6 @@ def hemisphere_rays(points, normals=None, n_dirs=16, seed=5, offset=1e-4, dir_be
         nrm = None if normals is None else torch.as_tensor(normals, dtype=torch.float32).to(dev).contiguous().reshape(-1, 3)
         rays = torch.empty(p.shape[0] * int(n_dirs), 6, dtype=torch.float32, device=dev)
         if rays.numel():
-            _lib.check(L.qsmrt_gen_hemisphere_rays(_ptr(rays), _ptr(p), _ptr(nrm), p.shape[0], int(seed), float(offset),
+            _lib.check(L.qsmrt_gen_hemisphere_rays(_ptr(rays), _ptr(p), _ptr(nrm), p.shape[0], int(point_base), int(seed), float(offset),
                                                    int(dir_begin), int(n_dirs), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         return rays

@@ -13,6 +13,12 @@ its C ABI with torch tensors as the zero-copy ray and hit buffers.
 Results are ``torch`` tensors: on the CPU by default (so ``.numpy()``,
 ``.isfinite()``, mask indexing and ``.reshape`` behave as the reference
 expects), or left on the GPU with ``output_device='cuda'``.
+
+``cast_rays`` returns all five Open3D keys, but only the two the reference
+reads (``t_hit``, ``primitive_ids``; ``ray_casting.py:280-289,320-322``) cross
+PCIe eagerly -- the other three stay on the GPU and are copied on first access
+(``CastResult``), 8 instead of 32 bytes per ray.  ``outputs="all"`` copies
+everything at once, ``outputs=("t_hit", ...)`` computes only the named keys.
 """
 from __future__ import annotations
 
@@ -74,6 +80,67 @@ def _to_host(t: torch.Tensor) -> torch.Tensor:
     return host
 
 
+CAST_KEYS = ("t_hit", "geometry_ids", "primitive_ids", "primitive_uvs", "primitive_normals")
+_CAST_DTYPE = {"t_hit": torch.float32, "geometry_ids": torch.uint32, "primitive_ids": torch.uint32,
+               "primitive_uvs": torch.float32, "primitive_normals": torch.float32}
+_CAST_TAIL = {"t_hit": (), "geometry_ids": (), "primitive_ids": (), "primitive_uvs": (2,), "primitive_normals": (3,)}
+EAGER_KEYS = ("t_hit", "primitive_ids")       # what the reference consumes (ray_casting.py:280-289,320-322)
+
+
+class CastResult(dict):
+    """``cast_rays`` result: a dict with Open3D's five keys.  Entries that were
+    left on the GPU are copied to the host the first time they are read; until
+    then they cost no PCIe traffic.  Behaves like a plain dict otherwise."""
+
+    def __init__(self, eager: dict, pending: dict):
+        super().__init__(eager)
+        self._pending = dict(pending)          # key -> device tensor (already shaped)
+
+    def _fetch(self, key):
+        t = _to_host(self._pending.pop(key))
+        dict.__setitem__(self, key, t)
+        return t
+
+    def __missing__(self, key):
+        if key in self._pending:
+            return self._fetch(key)
+        raise KeyError(key)
+
+    def _fetch_all(self):
+        for k in list(self._pending):
+            self._fetch(k)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._pending
+
+    def __iter__(self):
+        return iter([k for k in CAST_KEYS if k in self] + [k for k in dict.keys(self) if k not in CAST_KEYS])
+
+    def __len__(self):
+        return dict.__len__(self) + len(self._pending)
+
+    def keys(self):
+        return list(iter(self))
+
+    def items(self):
+        self._fetch_all()
+        return dict.items(self)
+
+    def values(self):
+        self._fetch_all()
+        return dict.values(self)
+
+    def pending(self):
+        """Keys still resident on the GPU (diagnostics / tests)."""
+        return tuple(self._pending)
+
+
 def _occupancy_directions(nsamples: int):
     """(1,1,1) first (the single-sample direction), then a fixed seeded set of unit vectors."""
     dirs = [(1.0, 1.0, 1.0)]
@@ -97,6 +164,13 @@ class RaycastingScene:
     INVALID_ID = INVALID_ID
 
     def __init__(self, nthreads: int = 0, device=None, output_device=None):
+        self._init_common(device, output_device)
+        h = C.c_void_p()
+        _lib.check(self._L.qsmrt_scene_create(self.device.index, C.byref(h)))
+        self._h = h
+
+    def _init_common(self, device, output_device):
+        self._h = None
         self._L = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("pyqsm_b200.RaycastingScene needs a CUDA device (B200); there is no CPU fallback")
@@ -110,10 +184,6 @@ class RaycastingScene:
         self.output_device = torch.device(output_device) if output_device is not None else torch.device("cpu")
         if self.output_device.type == "cuda":
             self.output_device = self.device
-        h = C.c_void_p()
-        _lib.check(self._L.qsmrt_scene_create(dev, C.byref(h)))
-        self._h = h
-        self._keep = []
 
     def __del__(self):
         try:
@@ -128,14 +198,31 @@ class RaycastingScene:
         """``add_triangles(mesh)`` or ``add_triangles(vertex_positions, triangle_indices)``;
         returns the geometry id (0, 1, ...).  The mesh is copied."""
         if triangle_indices is None:
+            # mesh overload: Open3D casts (GetVertexPositions().To(Float32), GetTriangleIndices().To(UInt32)) -- tensor
+            # meshes from from_legacy / create_cylinder carry Int64 indices -- only the two-tensor overload is strict
             vertex_positions, triangle_indices = _mesh_arrays(vertex_positions)
-        v = _to_torch(vertex_positions, torch.float32, "vertex_positions", self.device)
-        t = _to_torch(triangle_indices, torch.uint32, "triangle_indices", self.device)
+            idx = _unwrap(triangle_indices)
+            if idx is None:
+                idx = np.asarray(triangle_indices)
+            if isinstance(idx, np.ndarray):
+                idx = torch.from_numpy(np.ascontiguousarray(idx if idx.dtype != np.uint64 else idx.astype(np.int64)))
+            if idx.dtype not in (torch.uint32,) and idx.numel():
+                wide = idx.to(torch.int64)
+                if int(wide.min()) < 0 or int(wide.max()) > 0xFFFFFFFF:
+                    raise RuntimeError("triangle_indices do not fit in UInt32")
+            v = _to_torch(vertex_positions, torch.float32, "vertex_positions", self.device, strict=False)
+            t = _to_torch(idx, torch.uint32, "triangle_indices", self.device, strict=False)
+        else:
+            v = _to_torch(vertex_positions, torch.float32, "vertex_positions", self.device)
+            t = _to_torch(triangle_indices, torch.uint32, "triangle_indices", self.device)
         if v.ndim != 2 or v.shape[1] != 3:
             raise RuntimeError(f"vertex_positions has shape {tuple(v.shape)}, but it must be (N, 3)")
         if t.ndim != 2 or t.shape[1] != 3:
             raise RuntimeError(f"triangle_indices has shape {tuple(t.shape)}, but it must be (N, 3)")
         gid = C.c_uint32()
+        # the ABI copies on the legacy default stream: tensors produced on torch's current (possibly non-blocking)
+        # stream must be complete first
+        torch.cuda.current_stream(self.device).synchronize()
         _lib.check(self._L.qsmrt_add_triangles(self._h, _ptr(v), v.shape[0], _ptr(t), t.shape[0], 1, C.byref(gid)))
         return int(gid.value)
 
@@ -170,6 +257,38 @@ class RaycastingScene:
         _lib.check(self._L.qsmrt_commit(self._h, self._stream(), C.byref(ms)))
         return float(ms.value)
 
+    def set_option(self, name: str, value) -> None:
+        """Per-scene tuning / test hook (``enum qsmrt_option`` in ``include/qsmrt.h``): builder options take effect
+        at the next commit, traversal options at the next query.  Results never depend on them."""
+        _lib.check(self._L.qsmrt_scene_set_option(self._h, _lib.OPT[name], float(value)))
+
+    def get_option(self, name: str) -> float:
+        v = C.c_double()
+        _lib.check(self._L.qsmrt_scene_get_option(self._h, _lib.OPT[name], C.byref(v)))
+        return float(v.value)
+
+    def counters(self) -> list:
+        """The 16 fetch / lane counters of the last ``cast_rays`` launch made with ``set_option('counters', 1)``."""
+        out = (C.c_uint64 * 16)()
+        _lib.check(self._L.qsmrt_scene_get_counters(self._h, out))
+        return list(out)
+
+    def save(self, path: str, with_bvh: bool = True) -> None:
+        """Write the scene (geometries; with ``with_bvh`` also the committed LBVH) to ``path`` -- the counterpart
+        of the reference pickling its built search structures (``pyQSM/utils/io.py:44-60``)."""
+        _lib.check(self._L.qsmrt_scene_save(self._h, str(path).encode(), _lib.SAVE_BVH if with_bvh else 0))
+
+    @classmethod
+    def load(cls, path: str, device=None, output_device=None) -> "RaycastingScene":
+        """Scene from a file written by ``save``: committed at once if the file holds the BVH, otherwise rebuilt
+        (deterministically: the identical tree) by the first query."""
+        self = cls.__new__(cls)
+        self._init_common(device, output_device)
+        h = C.c_void_p()
+        _lib.check(self._L.qsmrt_scene_load(self.device.index, str(path).encode(), C.byref(h)))
+        self._h = h
+        return self
+
     def stats(self) -> dict:
         st = _lib.Stats()
         _lib.check(self._L.qsmrt_get_stats(self._h, C.byref(st)))
@@ -202,50 +321,69 @@ class RaycastingScene:
         return _to_host(t)
 
     # -------------------------------------------------------------- queries
-    def cast_rays(self, rays, nthreads: int = 0, grid_width: int = 0) -> dict:
+    def cast_rays(self, rays, nthreads: int = 0, grid_width: int = 0, outputs=None) -> dict:
         """Closest hit per ray.  Keys: ``t_hit`` (inf on miss), ``geometry_ids``,
         ``primitive_ids`` (INVALID_ID on miss), ``primitive_uvs``, ``primitive_normals``.
         Rays shaped ``[H, W, 6]`` (or flat with ``grid_width=W``) are traversed in
-        8x4 tiles; the results are the same either way."""
+        8x4 tiles; the results are the same either way.
+
+        ``outputs``: ``None`` (default) -- all five keys; with CPU results, ``t_hit`` and
+        ``primitive_ids`` are copied to the host at once and the other three on first
+        access (``CastResult``).  ``"all"`` -- all five copied at once (a plain dict, as
+        Open3D).  A tuple of key names -- only those are computed and returned."""
         r = self._rays(rays)
         shp = tuple(r.shape[:-1])
         n = int(np.prod(shp)) if shp else 1
-        if r.device.type == "cpu" and self.output_device.type == "cpu":
+        if outputs is None or outputs == "all":
+            keys = CAST_KEYS
+        else:
+            keys = tuple(outputs)
+            for k in keys:
+                if k not in CAST_KEYS:
+                    raise RuntimeError(f"cast_rays: unknown output {k!r}")
+        host_out = self.output_device.type == "cpu"
+        lazy = tuple(k for k in keys if k not in EAGER_KEYS) if (outputs is None and host_out and n >= (1 << 12)) else ()
+        shape_of = lambda k: shp + _CAST_TAIL[k]
+        if r.device.type == "cpu" and host_out:
             # host buffers in, host buffers out: chunked copy/compute overlap inside the C ABI
             r = r.contiguous()
             pin = n >= (1 << 16)
-            mk = lambda *s, dt: torch.empty(*s, dtype=dt, pin_memory=pin)
-            t_hit, gid, pid = mk(n, dt=torch.float32), mk(n, dt=torch.uint32), mk(n, dt=torch.uint32)
-            uv, nrm = mk(n, 2, dt=torch.float32), mk(n, 3, dt=torch.float32)
-            _lib.check(self._L.qsmrt_cast_rays_host(self._h, _ptr(r), n, _ptr(t_hit), _ptr(gid), _ptr(pid), _ptr(uv), _ptr(nrm)))
+            eager = {k: torch.empty((n,) + _CAST_TAIL[k], dtype=_CAST_DTYPE[k], pin_memory=pin) for k in keys if k not in lazy}
+            with torch.cuda.device(self.device):
+                pending = {k: torch.empty((n,) + _CAST_TAIL[k], dtype=_CAST_DTYPE[k], device=self.device) for k in lazy}
+            host_tab = (C.c_void_p * 5)(*[eager[k].data_ptr() if k in eager and n else None for k in CAST_KEYS])
+            dev_tab = (C.c_void_p * 5)(*[pending[k].data_ptr() if k in pending and n else None for k in CAST_KEYS])
+            _lib.check(self._L.qsmrt_cast_rays_host_split(self._h, _ptr(r), n, host_tab, dev_tab))
         else:
             with torch.cuda.device(self.device):
                 r = r.to(self.device).contiguous()
-                t_hit = torch.empty(n, dtype=torch.float32, device=self.device)
-                gid = torch.empty(n, dtype=torch.uint32, device=self.device)
-                pid = torch.empty(n, dtype=torch.uint32, device=self.device)
-                uv = torch.empty(n, 2, dtype=torch.float32, device=self.device)
-                nrm = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+                dev = {k: torch.empty((n,) + _CAST_TAIL[k], dtype=_CAST_DTYPE[k], device=self.device) for k in keys}
+                ptrs = [_ptr(dev.get(k)) for k in CAST_KEYS]
                 width = int(grid_width) if grid_width else (int(shp[-1]) if len(shp) >= 2 else 0)
                 if width >= 8 and n % width == 0 and n // width >= 4:
                     # image / grid shaped batch (create_rays_pinhole output): 8x4 ray tiles per warp
-                    _lib.check(self._L.qsmrt_cast_rays_2d(self._h, _ptr(r), width, n // width, _ptr(t_hit), _ptr(gid),
-                                                          _ptr(pid), _ptr(uv), _ptr(nrm), self._stream()))
+                    _lib.check(self._L.qsmrt_cast_rays_2d(self._h, _ptr(r), width, n // width, *ptrs, self._stream()))
                 else:
-                    _lib.check(self._L.qsmrt_cast_rays(self._h, _ptr(r), n, _ptr(t_hit), _ptr(gid), _ptr(pid), _ptr(uv), _ptr(nrm), self._stream()))
-                t_hit, gid, pid, uv, nrm = map(self._out, (t_hit, gid, pid, uv, nrm))
-        return {
-            "t_hit": t_hit.reshape(shp), "geometry_ids": gid.reshape(shp), "primitive_ids": pid.reshape(shp),
-            "primitive_uvs": uv.reshape(shp + (2,)), "primitive_normals": nrm.reshape(shp + (3,)),
-        }
+                    _lib.check(self._L.qsmrt_cast_rays(self._h, _ptr(r), n, *ptrs, self._stream()))
+                eager = {k: self._out(dev[k]) for k in keys if k not in lazy}
+                pending = {k: dev[k] for k in lazy}
+        eager = {k: t.reshape(shape_of(k)) for k, t in eager.items()}
+        if not lazy:
+            return {k: eager[k] for k in keys}
+        return CastResult({k: eager[k] for k in keys if k in eager}, {k: t.reshape(shape_of(k)) for k, t in pending.items()})
 
     def count_intersections(self, rays, nthreads: int = 0) -> torch.Tensor:
         """Number of intersections per ray (int32), Open3D dedup rule."""
         r = self._rays(rays)
         shp = tuple(r.shape[:-1])
+        n = r.numel() // 6
+        if r.device.type == "cpu" and self.output_device.type == "cpu" and n >= (1 << 16):
+            r = r.contiguous()
+            out = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            _lib.check(self._L.qsmrt_count_intersections_host(self._h, _ptr(r), n, _ptr(out)))
+            return out.reshape(shp)
         with torch.cuda.device(self.device):
             r = r.to(self.device).contiguous()
-            n = r.numel() // 6
             out = torch.empty(n, dtype=torch.int32, device=self.device)
             _lib.check(self._L.qsmrt_count_intersections(self._h, _ptr(r), n, _ptr(out), self._stream()))
             return self._out(out).reshape(shp)
@@ -254,9 +392,14 @@ class RaycastingScene:
         """True where any triangle is hit with tnear < t <= tfar."""
         r = self._rays(rays)
         shp = tuple(r.shape[:-1])
+        n = r.numel() // 6
+        if r.device.type == "cpu" and self.output_device.type == "cpu" and n >= (1 << 16):
+            r = r.contiguous()
+            out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            _lib.check(self._L.qsmrt_test_occlusions_host(self._h, _ptr(r), n, float(tnear), float(tfar), _ptr(out)))
+            return out.view(torch.bool).reshape(shp)
         with torch.cuda.device(self.device):
             r = r.to(self.device).contiguous()
-            n = r.numel() // 6
             out = torch.empty(n, dtype=torch.uint8, device=self.device)
             _lib.check(self._L.qsmrt_test_occlusions(self._h, _ptr(r), n, float(tnear), float(tfar), _ptr(out), self._stream()))
             return self._out(out.to(torch.bool)).reshape(shp)
@@ -287,9 +430,14 @@ class RaycastingScene:
         """1.0 inside / 0.0 outside (``ray_casting.py:69``): parity of the
         intersection count of a ray from each point.  ``nsamples == 1``: along
         (1,1,1), as Open3D's ``ComputeOccupancy``; odd ``nsamples > 1``: majority
-        vote over that many fixed directions (Open3D draws its directions from
-        ``std::mt19937(42)``; which directions are used only matters for meshes that
-        are not watertight)."""
+        vote over that many fixed directions.
+
+        KNOWN DIVERGENCE: Open3D draws the extra directions from ``std::mt19937(42)``;
+        here they come from numpy ``default_rng(42)`` (the C++ stream is not
+        reproduced).  For watertight meshes every direction gives the same parity, so
+        the answers agree; for meshes with holes ``nsamples > 1`` can differ from
+        Open3D's answer near the holes.  ``nsamples == 1`` (what the reference uses,
+        ``ray_casting.py:69``) is not affected."""
         if nsamples < 1 or nsamples % 2 != 1:
             raise RuntimeError("compute_occupancy: nsamples must be odd and >= 1")
         p = _unwrap(query_points)
@@ -382,19 +530,45 @@ class RaycastingScene:
                 d = torch.where(inside, -d, d)
             return self._out(d).reshape(shp)
 
-    def mark_hit_primitives(self, ans: dict):
-        """Device-side form of ``ray_casting.py:285-289``: uint8 flags of the
-        triangles (scene order) and vertices that own a closest hit."""
-        st = self.stats()
+    def mark_hit_primitives(self, ans: dict, vertices: bool = False):
+        """Device-side form of ``ray_casting.py:285-292``: uint8 flags of the
+        triangles (scene order) that own a closest hit -- ``np.unique(prim_ids)`` as a
+        mask -- and, with ``vertices=True``, also of their corner vertices
+        (``hit_vert_ids = np.unique(triangles[prim_ids])``): returns ``tri`` or
+        ``(tri, vert)``."""
         with torch.cuda.device(self.device):
             gid = ans["geometry_ids"].to(self.device).contiguous().reshape(-1)
             pid = ans["primitive_ids"].to(self.device).contiguous().reshape(-1)
             self.commit()
             nt = int(self.stats()["num_triangles"])
+            nv = sum(self.geometry_size(g)[0] for g in range(int(self.stats()["num_geometries"]))) if vertices else 0
             tri = torch.zeros(max(nt, 1), dtype=torch.uint8, device=self.device)
-            _lib.check(self._L.qsmrt_mark_hit_primitives(self._h, _ptr(gid), _ptr(pid), pid.numel(), _ptr(tri), None, self._stream()))
-            del st
+            vert = torch.zeros(max(nv, 1), dtype=torch.uint8, device=self.device) if vertices else None
+            _lib.check(self._L.qsmrt_mark_hit_primitives(self._h, _ptr(gid), _ptr(pid), pid.numel(), _ptr(tri), _ptr(vert), self._stream()))
+            if vertices:
+                return self._out(tri[:nt]), self._out(vert[:nv])
             return self._out(tri[:nt])
+
+    def geometry_size(self, geometry_id: int):
+        """(number of vertices, number of triangles) of a registered geometry."""
+        nv, nt = C.c_uint64(), C.c_uint64()
+        _lib.check(self._L.qsmrt_geometry_size(self._h, int(geometry_id), C.byref(nv), C.byref(nt)))
+        return int(nv.value), int(nt.value)
+
+    def vertex_exposure(self, tri_counts: torch.Tensor) -> torch.Tensor:
+        """Per-vertex exposure from per-triangle exposure (scene order): every vertex
+        receives the counts of the triangles it is a corner of -- BASELINE config 2's
+        "sunlight exposure per leaf vertex", the count form of ``ray_casting.py:289-292``."""
+        with torch.cuda.device(self.device):
+            self.commit()
+            st = self.stats()
+            nv = sum(self.geometry_size(g)[0] for g in range(int(st["num_geometries"])))
+            tc = tri_counts.to(self.device).contiguous().view(torch.int32)
+            if tc.numel() != int(st["num_triangles"]):
+                raise RuntimeError(f"tri_counts has {tc.numel()} entries, the scene {int(st['num_triangles'])} triangles")
+            out = torch.zeros(max(nv, 1), dtype=torch.int32, device=self.device)
+            _lib.check(self._L.qsmrt_vertex_exposure(self._h, _ptr(tc), _ptr(out), self._stream()))
+            return out[:nv]
 
     # ------------------------------------------------------- ray generators
     @staticmethod

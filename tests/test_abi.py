@@ -25,7 +25,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/qsmrt.h but not exported"
     assert set(declared) == set(_lib.SYMBOLS), "ctypes table and header disagree"
-    assert lib.qsmrt_abi_version() == 1
+    assert lib.qsmrt_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_no_torch_in_abi():

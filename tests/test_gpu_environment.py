@@ -80,7 +80,7 @@ def test_sky_gap_fraction_equals_occlusion(tree):
     p_d, n_d = torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda()
     parts = torch.zeros(300, dtype=torch.int32, device="cuda")
     for b, c in ((0, 20), (20, 30), (50, 14)):
-        _lib.check(L.qsmrt_sky_visibility(g._h, C.c_void_p(p_d.data_ptr()), C.c_void_p(n_d.data_ptr()), 300, 11, 1e-3, b, c,
+        _lib.check(L.qsmrt_sky_visibility(g._h, C.c_void_p(p_d.data_ptr()), C.c_void_p(n_d.data_ptr()), 300, 0, 11, 1e-3, b, c,
                                           C.c_void_p(parts.data_ptr()), None))
     torch.cuda.synchronize()
     assert torch.equal(parts.to(torch.float32) / n_dirs, gap)

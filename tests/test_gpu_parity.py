@@ -138,14 +138,10 @@ def test_builder_matches_oracle(c1):
     from pyqsm_b200 import _lib
     from pyqsm_b200 import RaycastingScene
     v, t, o, _ = c1
-    L = _lib.load()
-    _lib.check(L.qsmrt_debug_set_keep_binary_nodes(1))       # the product build keeps no binary node array
-    try:
-        g = RaycastingScene()
-        g.add_triangles(v, t)
-        g.commit()
-    finally:
-        _lib.check(L.qsmrt_debug_set_keep_binary_nodes(0))
+    g = RaycastingScene()
+    g.set_option("keep_binary_nodes", 1)                     # the product build keeps no binary node array
+    g.add_triangles(v, t)
+    g.commit()
     n = t.shape[0]
     keys = np.empty(n, np.uint64)
     order = np.empty(n, np.uint32)
@@ -168,7 +164,7 @@ def test_builder_matches_oracle(c1):
     assert np.array_equal(np.asarray(st["scene_lo"], np.float32), lo) and np.array_equal(np.asarray(st["scene_hi"], np.float32), hi)
 
 
-def _builder_topology(RS, oracle_mod, v, t, keep):
+def _builder_topology(RS, oracle_mod, v, t, keep, opts=None):
     """(left, right, lo, hi) of the GPU's binary tree next to the oracle's, plus a cast through the product nodes."""
     import ctypes as C
     from pyqsm_b200 import _lib
@@ -176,13 +172,12 @@ def _builder_topology(RS, oracle_mod, v, t, keep):
     o = oracle_mod.OracleScene()
     o.add_triangles(v, t)
     o.commit()
-    _lib.check(L.qsmrt_debug_set_keep_binary_nodes(1 if keep else 0))
-    try:
-        g = RS()
-        g.add_triangles(v, t)
-        g.commit()
-    finally:
-        _lib.check(L.qsmrt_debug_set_keep_binary_nodes(0))
+    g = RS()
+    g.set_option("keep_binary_nodes", 1 if keep else 0)
+    for name, value in (opts or {}).items():
+        g.set_option(name, value)
+    g.add_triangles(v, t)
+    g.commit()
     n = t.shape[0]
     if keep:
         keys, order = np.empty(n, np.uint64), np.empty(n, np.uint32)
@@ -392,47 +387,41 @@ def test_variants_tilings_and_leaf_sizes_agree(RS, oracle_mod):
     rays[301 * 120: 301 * 140, 3:] = np.array([-0.0, 1.0, 0.0], np.float32)
     ref = o.cast_rays(rays, 1)
     rays_img = torch.from_numpy(rays.reshape(203, 301, 6)).cuda()
-    try:
-        for leaf_max in (1, 2, 3, 4):
-            _lib.check(L.qsmrt_debug_set_leaf_max(leaf_max))
-            g = RS(output_device="cuda")
-            g.add_triangles(v, t)
-            g.commit()
-            assert g.stats()["leaf_max"] == leaf_max and g.stats()["bvh_height"] >= 10
-            assert g.stats()["quantised_nodes"] == 1                     # this mesh qualifies for the 32-byte nodes
-            for variant, quant in ((1, 1), (2, 1), (2, 0)):
-                _lib.check(L.qsmrt_debug_set_variant(variant))
-                _lib.check(L.qsmrt_debug_set_quantised_nodes(quant))     # only the persistent kernel reads them
-                for r in (rays_img, rays_img.reshape(-1, 6)):            # 2-D tiles / linear
-                    ans = {k: a.cpu().reshape((-1,) + tuple(a.shape[r.ndim - 1:])) for k, a in g.cast_rays(r).items()}
-                    assert_cast_equal(ans, ref, None, f"leaf{leaf_max}/v{variant}/q{quant}")
-            occ = g.test_occlusions(rays_img.reshape(-1, 6)).cpu().numpy()
-            assert np.array_equal(occ, np.isfinite(ref["t_hit"]))
-    finally:
-        _lib.check(L.qsmrt_debug_set_leaf_max(2))
-        _lib.check(L.qsmrt_debug_set_variant(2))
-        _lib.check(L.qsmrt_debug_set_quantised_nodes(1))
-        _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 0))
+    g = RS(output_device="cuda")
+    g.add_triangles(v, t)
+    for leaf_max in (1, 2, 3, 4):
+        g.set_option("leaf_max", leaf_max)                           # a changed builder option marks the scene for rebuilding
+        g.commit()
+        assert g.stats()["leaf_max"] == leaf_max and g.stats()["bvh_height"] >= 10
+        assert g.stats()["quantised_nodes"] == 1                     # this mesh qualifies for the 32-byte nodes
+        for variant, quant in ((1, 1), (2, 1), (2, 0)):
+            g.set_option("traversal_variant", variant)
+            g.set_option("quantised_nodes", quant)                   # only the persistent kernel reads them
+            for r in (rays_img, rays_img.reshape(-1, 6)):            # 2-D tiles / linear
+                ans = {k: a.cpu().reshape((-1,) + tuple(a.shape[r.ndim - 1:])) for k, a in g.cast_rays(r).items()}
+                assert_cast_equal(ans, ref, None, f"leaf{leaf_max}/v{variant}/q{quant}")
+        g.set_option("traversal_variant", 2)
+        g.set_option("quantised_nodes", 1)
+        occ = g.test_occlusions(rays_img.reshape(-1, 6)).cpu().numpy()
+        assert np.array_equal(occ, np.isfinite(ref["t_hit"]))
+    # options live in the scene: a fresh scene has the defaults whatever another scene was set to
+    g2 = RS()
+    assert g2.get_option("leaf_max") == 2 and g2.get_option("traversal_variant") == 2 and g.get_option("leaf_max") == 4
 
 
 def test_fetch_counters(RS):
-    """qsmrt_debug_set_tuning(counters=1): the kernel's own node / triangle fetch counts."""
-    import ctypes as C
-    from pyqsm_b200 import _lib
-    L = _lib.load()
+    """set_option('counters', 1): the kernel's own node / triangle fetch counts, per scene."""
     v, t = syn.qsm_tree_mesh(seed=1)
     g = RS(output_device="cuda")
     g.add_triangles(v, t)
     rays = torch.from_numpy(syn.materialize_grid(*syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(45, 135), 400, 400), 400, 400)).cuda()
-    try:
-        _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 1))
-        g.cast_rays(rays)
-        torch.cuda.synchronize()
-        nn, nt = C.c_uint64(), C.c_uint64()
-        _lib.check(L.qsmrt_debug_get_counters(C.byref(nn), C.byref(nt)))
-        assert 1 < nn.value / rays.shape[0] < 200 and 0 < nt.value / rays.shape[0] < 50
-    finally:
-        _lib.check(L.qsmrt_debug_set_tuning(12, 12, 1, 0))
+    g.set_option("counters", 1)
+    g.cast_rays(rays)
+    c = g.counters()
+    assert 1 < c[0] / rays.shape[0] < 200 and 0 < c[1] / rays.shape[0] < 50
+    assert c[3] <= 32 * c[2] and c[8] <= 32 * c[7]              # lanes per node / triangle iteration
+    other = RS(output_device="cuda")
+    assert other.counters() == [0] * 16                          # counters are per scene
 
 
 def test_closest_points_and_signed_distance(RS, oracle_mod):
@@ -657,15 +646,12 @@ def test_far_origins_and_offset_scenes(RS, oracle_mod):
         rays = np.concatenate([near, far])
         ref = o.cast_rays(rays, 0)                                     # brute force
         assert np.isfinite(ref["t_hit"][6000:]).sum() > 300
-        try:
-            for quant in (1, 0):
-                _lib.check(L.qsmrt_debug_set_quantised_nodes(quant))
-                g = RS()
-                g.add_triangles(vs, t)
-                assert_cast_equal(g.cast_rays(rays), ref, None, f"far/shift{shift[0]}/q{quant}")
-                assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 0))
-        finally:
-            _lib.check(L.qsmrt_debug_set_quantised_nodes(1))
+        for quant in (1, 0):
+            g = RS()
+            g.set_option("quantised_nodes", quant)
+            g.add_triangles(vs, t)
+            assert_cast_equal(g.cast_rays(rays), ref, None, f"far/shift{shift[0]}/q{quant}")
+            assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 0))
 
 
 @pytest.mark.parametrize("cap", [1, 7, 100])
@@ -679,13 +665,9 @@ def test_builder_climb_list_overflow(RS, oracle_mod, cap):
     v = (c[:, None, :] + rng.normal(0, 0.05, size=(n, 3, 3))).reshape(-1, 3).astype(np.float32)
     t = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
     rays = syn.random_rays((-3, -3, -3), (3, 3, 3), 3000, seed=cap)
-    _lib.check(L.qsmrt_debug_set_climb_capacity(cap))
-    try:
-        for keep in (True, False):
-            o, g = _builder_topology(RS, oracle_mod, v, t, keep)
-            assert_cast_equal(g.cast_rays(rays), o.cast_rays(rays, 1), o.edge_flags(rays, mode=1), f"climbcap{cap}")
-    finally:
-        _lib.check(L.qsmrt_debug_set_climb_capacity(0))
+    for keep in (True, False):
+        o, g = _builder_topology(RS, oracle_mod, v, t, keep, {"climb_capacity": cap})
+        assert_cast_equal(g.cast_rays(rays), o.cast_rays(rays, 1), o.edge_flags(rays, mode=1), f"climbcap{cap}")
 
 
 def test_scene_churn_reuses_device_blocks(RS, oracle_mod):
@@ -751,11 +733,9 @@ def test_closest_points_warp_and_thread_kernels_agree(RS, oracle_mod):
     q = np.concatenate([rng.uniform(lo, hi, size=(3000, 3)), rng.uniform(lo - 30, hi + 30, size=(1500, 3)),
                         v[rng.integers(0, len(v), 500)] + rng.normal(0, 1e-3, size=(500, 3))]).astype(np.float32)
     a = {k: x.numpy() for k, x in g.compute_closest_points(q).items()}
-    _lib.check(L.qsmrt_debug_set_cp_warp_max(0))
-    try:
-        b = {k: x.numpy() for k, x in g.compute_closest_points(q).items()}
-    finally:
-        _lib.check(L.qsmrt_debug_set_cp_warp_max(16384))
+    g.set_option("cp_warp_max", 0)
+    b = {k: x.numpy() for k, x in g.compute_closest_points(q).items()}
+    g.set_option("cp_warp_max", 16384)
     ref = o.compute_closest_points(q, 1)
     for k in a:
         assert np.array_equal(a[k], b[k]), k

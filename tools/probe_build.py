@@ -10,10 +10,9 @@ for ncan in ([int(a) for a in sys.argv[1:]] or [2, 10, 50]):
     vd, td = torch.from_numpy(v).cuda(), torch.from_numpy(t.view(np.int32)).cuda().view(torch.uint32)
     ref = None
     for variant in (0, 1):
-        _lib.check(L.qsmrt_debug_set_sort(variant))
         bs = []
         for i in range(4):
-            s = RaycastingScene(output_device="cuda"); s.add_triangles(vd, td); bs.append(s.commit()); st = s.stats()
+            s = RaycastingScene(output_device="cuda"); s.set_option("sort_variant", variant); s.add_triangles(vd, td); bs.append(s.commit()); st = s.stats()
             if i == 3:
                 n = t.shape[0]; keys = np.empty(n, np.uint64); order = np.empty(n, np.uint32)
                 _lib.check(L.qsmrt_debug_get_build(s._h, keys.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p), None))

@@ -22,25 +22,26 @@ def timeit(reps=3):
     for _ in range(reps):
         e0.record(); run(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
-cur_lm = 4
+cur_lm = 2
 for k in range(a.angles):
     el, az = sweep[(k * 27 + 5) % 64]
     g = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), a.grid, a.grid)
     _lib.check(L.qsmrt_gen_parallel_rays(P(rays), a.grid, a.grid, F3(g[0]), F3(g[1]), F3(g[2]), F3(g[3]), st))
-    _lib.check(L.qsmrt_debug_set_variant(1)); ms3 = timeit(); ref = (o[0].clone(), o[2].clone(), o[3].clone())
+    s.set_option("traversal_variant", 1); ms3 = timeit(); ref = (o[0].clone(), o[2].clone(), o[3].clone())
     print(f"el {el:.0f} az {az:.0f}: v1 {ms3:.2f} ms {n/ms3/1e3:.0f} Mr/s")
     for combo in a.combos.split(";"):
         var, rest = combo.split(":"); rf, wt, tm, lm, *npth = map(int, rest.split(","))
-        _lib.check(L.qsmrt_debug_set_node_path(npth[0] if npth else 0))
-        _lib.check(L.qsmrt_debug_set_quantised_nodes(npth[1] if len(npth) > 1 else 1))
+        s.set_option("node_path", npth[0] if npth else 0)
+        s.set_option("quantised_nodes", npth[1] if len(npth) > 1 else 1)
         if lm != cur_lm:
-            _lib.check(L.qsmrt_debug_set_leaf_max(lm)); cur_lm = lm
-            s = RaycastingScene(output_device="cuda"); s.add_triangles(v, t); s.commit()
-        _lib.check(L.qsmrt_debug_set_variant(int(var)))
-        _lib.check(L.qsmrt_debug_set_tuning(rf, wt, tm, 0)); ms = timeit()
+            s.set_option("leaf_max", lm); cur_lm = lm; s.commit()       # a changed builder option rebuilds
+        s.set_option("traversal_variant", int(var))
+        for k, x in (("refill", rf), ("want", wt), ("tri_min", tm), ("counters", 0)): s.set_option(k, x)
+        ms = timeit()
         same = torch.equal(ref[0], o[0]) and torch.equal(ref[1], o[2]) and torch.equal(ref[2], o[3])
-        _lib.check(L.qsmrt_debug_set_tuning(rf, wt, tm, 1)); run(); torch.cuda.synchronize()
-        nn, nt = C.c_uint64(), C.c_uint64(); _lib.check(L.qsmrt_debug_get_counters(C.byref(nn), C.byref(nt)))
-        cs = (C.c_uint64 * 16)(); _lib.check(L.qsmrt_debug_get_census(cs)); cs = list(cs)
+        s.set_option("counters", 1); run(); cs = s.counters(); s.set_option("counters", 0)
+        class _V:  # noqa: E701
+            def __init__(self, v): self.value = v
+        nn, nt = _V(cs[0]), _V(cs[1])
         if cs[2]: print(f"      node-phase iters/ray {cs[2]*32/n:.1f} lanes step {cs[3]/cs[2]:.1f} idle {cs[4]/cs[2]:.1f} leaf2 {cs[5]/cs[2]:.1f} done {cs[6]/cs[2]:.1f} | tri-phase iters/ray {cs[7]*32/n:.1f} lanes {cs[8]/max(cs[7],1):.1f}")
         print(f"   v{var} refill {rf:2d} want {wt:2d} trimin {tm:2d} leafmax {lm} path {npth[0] if npth else 0} quant {npth[1] if len(npth) > 1 else 1}: {ms:.2f} ms {n/ms/1e3:.0f} Mr/s {'=' if same else 'DIFF'}  nodes/ray {nn.value/n:.1f} tris/ray {nt.value/n:.2f}", flush=True)
