@@ -468,11 +468,19 @@ def run_ours(args):
             prof = json.load(open(prof_path))
         except Exception:
             prof = {}
-    inst_ray = prof.get("warp_inst_per_ray")              # ncu smsp__inst_executed.sum / rays, same command
-    lanes = prof.get("lanes_per_inst")                    # ncu smsp__thread_inst_executed_per_inst_executed
-    fetch_b = prof.get("fetch_bytes_per_ray")             # the kernel's own counters: 32 B node records + 48 B triangles
+    # per-angle table (tools/profile_angles.py): take the angles this run timed (a multi-GPU step mixes its angles evenly)
+    key = {(round(x["elevation"], 3), round(x["azimuth"], 3)): x for x in prof.get("angles", [])}
+    sel = [key.get((round(e, 3), round(z, 3))) for e, z in timed_angles]
+    if sel and all(x is not None for x in sel):
+        rpa = float(prof["rays_per_angle"])
+        inst_ray = float(np.mean([x["warp_inst"] for x in sel])) / rpa      # ncu smsp__inst_executed.sum / rays
+        lanes = float(sum(x["thread_inst"] for x in sel) / sum(x["warp_inst"] for x in sel))
+        fetch_b = float(np.mean([32 * x["nodes_per_ray"] + 48 * x["tris_per_ray"] for x in sel]))   # the kernel's own counters
+        traffic = float(np.mean([x["dram_bytes"] for x in sel]))
+    else:
+        inst_ray = lanes = fetch_b = traffic = None
     issue_peak = sms * 4 * sm_mhz * 1e6 / 1e9             # G warp-instructions / s
-    roofline = {"bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak, "traffic": prof.get("dram_bytes_per_launch"),
+    roofline = {"bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak, "traffic": traffic,
                 "kernel": "k_trace5<0> (cast_rays, persistent traversal)", "kernel_ms": k_ms, "kernel_mrays_s": n / (k_ms * 1e-3) / 1e6,
                 "peak_source": f"{sms} SMs x 4 schedulers x {sm_mhz:.0f} MHz (NVML, median inside the timed region)"}
     if inst_ray and lanes:

@@ -28,6 +28,10 @@
  *   mode 1  the canonical LBVH (63-bit Morton, Karras topology, one triangle
  *           per leaf, 32-byte nodes) traversed near-child-first.  Its fetch
  *           counters define the roofline bytes per ray.
+ *   mode 2  a top-down binned-SAH BVH over the same triangles (one per leaf,
+ *           same node format, same traversal).  Measurement only: its fetch
+ *           counters next to mode 1's say how much tree quality the LBVH
+ *           leaves on the table (baseline/canonical_counters.json).
  */
 #include <math.h>
 #include <stdint.h>
@@ -72,7 +76,20 @@ typedef struct {
     int32_t  *parent;                         /* parent of internal node */
     float     slo[3], shi[3];                 /* scene bounds (unpadded) */
     float     pad;                            /* box padding */
+    /* mode 2: binned-SAH tree, built on first use */
+    orc_tri  *sah_tris; orc_node *sah_nodes; float *sah_leaf_lo, *sah_leaf_hi;
 } orc_scene;
+
+/* the arrays a traversal reads: the canonical LBVH (mode 1) or the SAH tree (mode 2) */
+typedef struct { const orc_node *nodes; const float *leaf_lo, *leaf_hi; const orc_tri *stris; } orc_tree;
+static void build_sah(orc_scene *s);
+static inline orc_tree tree_of(const orc_scene *s, int mode)
+{
+    orc_tree t;
+    if (mode == 2) { t.nodes = s->sah_nodes; t.leaf_lo = s->sah_leaf_lo; t.leaf_hi = s->sah_leaf_hi; t.stris = s->sah_tris; }
+    else { t.nodes = s->nodes; t.leaf_lo = s->leaf_lo; t.leaf_hi = s->leaf_hi; t.stris = s->stris; }
+    return t;
+}
 
 /* ------------------------------------------------------------------ math */
 static inline v3 v3sub(v3 a, v3 b) { v3 r = { a.x - b.x, a.y - b.y, a.z - b.z }; return r; }
@@ -143,6 +160,8 @@ static void free_committed(orc_scene *s)
 {
     free(s->tris); free(s->stris); free(s->keys); free(s->order); free(s->nodes);
     free(s->leaf_lo); free(s->leaf_hi); free(s->parent);
+    free(s->sah_tris); free(s->sah_nodes); free(s->sah_leaf_lo); free(s->sah_leaf_hi);
+    s->sah_tris = NULL; s->sah_nodes = NULL; s->sah_leaf_lo = s->sah_leaf_hi = NULL;
     s->tris = s->stris = NULL; s->keys = NULL; s->order = NULL; s->nodes = NULL;
     s->leaf_lo = s->leaf_hi = NULL; s->parent = NULL; s->committed = 0;
 }
@@ -352,6 +371,107 @@ const orc_node *orc_nodes(const orc_scene *s) { return s->nodes; }
 float orc_box_pad(const orc_scene *s) { return s->pad; }
 void orc_scene_bounds(const orc_scene *s, float *lo, float *hi) { memcpy(lo, s->slo, 12); memcpy(hi, s->shi, 12); }
 
+/* ------------------------------------------------ binned-SAH tree (mode 2)
+ * Top-down, 32 centroid bins on the axis of the largest centroid extent, split
+ * where leftArea*leftCount + rightArea*rightCount is smallest (median split
+ * when all centroids coincide), down to one triangle per leaf.  Same padded
+ * leaf boxes and node format as the canonical LBVH, so the same traversal and
+ * the same counters apply: the difference in node visits is tree quality only. */
+#define SAH_BINS 32
+typedef struct { orc_scene *s; uint32_t *ids; float *clo, *chi, *cen; int32_t next_node; } sah_ctx;
+
+static inline float half_area(const float *lo, const float *hi)
+{
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+/* builds the subtree over ids[b, e); returns its child reference and writes its box */
+static int32_t sah_rec(sah_ctx *c, int64_t b, int64_t e, float *olo, float *ohi)
+{
+    orc_scene *s = c->s;
+    if (e - b == 1) {
+        uint32_t t = c->ids[b];
+        s->sah_tris[b] = s->tris[t];
+        for (int a = 0; a < 3; ++a) { s->sah_leaf_lo[3 * b + a] = olo[a] = c->clo[3 * t + a]; s->sah_leaf_hi[3 * b + a] = ohi[a] = c->chi[3 * t + a]; }
+        return ~(int32_t)b;
+    }
+    float cmin[3] = { INFINITY, INFINITY, INFINITY }, cmax[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int64_t i = b; i < e; ++i)
+        for (int a = 0; a < 3; ++a) { float x = c->cen[3 * c->ids[i] + a]; cmin[a] = fminf(cmin[a], x); cmax[a] = fmaxf(cmax[a], x); }
+    int ax = 0;
+    for (int a = 1; a < 3; ++a) if (cmax[a] - cmin[a] > cmax[ax] - cmin[ax]) ax = a;
+    int64_t mid = (b + e) / 2;
+    float ext = cmax[ax] - cmin[ax];
+    if (ext > 0.0f) {
+        float blo[SAH_BINS][3], bhi[SAH_BINS][3]; int64_t bcnt[SAH_BINS];
+        for (int k = 0; k < SAH_BINS; ++k) { bcnt[k] = 0; for (int a = 0; a < 3; ++a) { blo[k][a] = INFINITY; bhi[k][a] = -INFINITY; } }
+        float scale = (float)SAH_BINS / ext;
+        for (int64_t i = b; i < e; ++i) {
+            uint32_t t = c->ids[i];
+            int k = (int)((c->cen[3 * t + ax] - cmin[ax]) * scale); if (k >= SAH_BINS) k = SAH_BINS - 1; if (k < 0) k = 0;
+            bcnt[k]++;
+            for (int a = 0; a < 3; ++a) { blo[k][a] = fminf(blo[k][a], c->clo[3 * t + a]); bhi[k][a] = fmaxf(bhi[k][a], c->chi[3 * t + a]); }
+        }
+        float rarea[SAH_BINS]; int64_t rcnt[SAH_BINS];
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY }; int64_t cnt = 0;
+        for (int k = SAH_BINS - 1; k > 0; --k) {
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], blo[k][a]); hi[a] = fmaxf(hi[a], bhi[k][a]); }
+            cnt += bcnt[k]; rcnt[k] = cnt; rarea[k] = cnt ? half_area(lo, hi) : 0.0f;
+        }
+        for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+        cnt = 0;
+        float best = INFINITY; int bestk = -1;
+        for (int k = 0; k < SAH_BINS - 1; ++k) {
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], blo[k][a]); hi[a] = fmaxf(hi[a], bhi[k][a]); }
+            cnt += bcnt[k];
+            if (cnt == 0 || rcnt[k + 1] == 0) continue;
+            float cost = half_area(lo, hi) * (float)cnt + rarea[k + 1] * (float)rcnt[k + 1];
+            if (cost < best) { best = cost; bestk = k; }
+        }
+        if (bestk >= 0) {       /* partition ids[b, e) by bin <= bestk */
+            int64_t i = b, j = e - 1;
+            while (i <= j) {
+                uint32_t t = c->ids[i];
+                int k = (int)((c->cen[3 * t + ax] - cmin[ax]) * scale); if (k >= SAH_BINS) k = SAH_BINS - 1; if (k < 0) k = 0;
+                if (k <= bestk) ++i; else { c->ids[i] = c->ids[j]; c->ids[j] = t; --j; }
+            }
+            mid = i;
+            if (mid == b || mid == e) mid = (b + e) / 2;
+        }
+    }
+    int32_t me = c->next_node++;
+    float llo[3], lhi[3], rlo[3], rhi[3];
+    int32_t L = sah_rec(c, b, mid, llo, lhi), R = sah_rec(c, mid, e, rlo, rhi);
+    orc_node *nd = &s->sah_nodes[me];
+    nd->left = L; nd->right = R;
+    for (int a = 0; a < 3; ++a) { nd->lo[a] = olo[a] = fminf(llo[a], rlo[a]); nd->hi[a] = ohi[a] = fmaxf(lhi[a], rhi[a]); }
+    return me;
+}
+
+static void build_sah(orc_scene *s)
+{
+#pragma omp critical(orc_sah)
+    if (!s->sah_nodes && s->ntris > 1) {
+        uint64_t n = s->ntris;
+        sah_ctx c; c.s = s; c.next_node = 0;
+        c.ids = (uint32_t *)malloc(sizeof(uint32_t) * n);
+        c.clo = (float *)malloc(sizeof(float) * 3 * n); c.chi = (float *)malloc(sizeof(float) * 3 * n); c.cen = (float *)malloc(sizeof(float) * 3 * n);
+        s->sah_tris = (orc_tri *)malloc(sizeof(orc_tri) * n);
+        s->sah_leaf_lo = (float *)malloc(sizeof(float) * 3 * n); s->sah_leaf_hi = (float *)malloc(sizeof(float) * 3 * n);
+        orc_node *nodes = (orc_node *)malloc(sizeof(orc_node) * (n - 1));
+        for (uint64_t t = 0; t < n; ++t) {
+            float lo[3], hi[3]; tri_bounds(s, t, lo, hi);
+            c.ids[t] = (uint32_t)t;
+            for (int a = 0; a < 3; ++a) { c.clo[3 * t + a] = lo[a] - s->pad; c.chi[3 * t + a] = hi[a] + s->pad; c.cen[3 * t + a] = (lo[a] + hi[a]) * 0.5f; }
+        }
+        s->sah_nodes = nodes;
+        float lo[3], hi[3];
+        sah_rec(&c, 0, (int64_t)n, lo, hi);
+        free(c.ids); free(c.clo); free(c.chi); free(c.cen);
+    }
+}
+
 /* ------------------------------------------------------------ ray setup */
 typedef struct { v3 O, D; float idx, idy, idz; } ray_t;
 
@@ -415,6 +535,7 @@ static void cast_one(const orc_scene *s, const ray_t *y, int mode, best_t *b, or
     b->Ng.x = b->Ng.y = b->Ng.z = 0.0f;
     if (n == 0) return;
     if (mode == 0) { for (uint64_t i = 0; i < n; ++i) consider(&s->tris[i], y, b); return; }
+    const orc_tree T = tree_of(s, mode);
     float tn;
     if (n == 1) {
         c->nodes++;
@@ -423,16 +544,16 @@ static void cast_one(const orc_scene *s, const ray_t *y, int mode, best_t *b, or
     }
     int32_t stk[ORC_STACK]; float stn[ORC_STACK]; int sp = 0;
     c->nodes++;
-    if (!box_test(s->nodes[0].lo, s->nodes[0].hi, y, b->t, &tn)) return;
+    if (!box_test(T.nodes[0].lo, T.nodes[0].hi, y, b->t, &tn)) return;
     int32_t cur = 0;
     for (;;) {
         if (cur >= 0) {
-            const orc_node *nd = &s->nodes[cur];
+            const orc_node *nd = &T.nodes[cur];
             int32_t ch[2] = { nd->left, nd->right };
             float ctn[2]; int hit[2];
             for (int k = 0; k < 2; ++k) {
-                const float *lo = ch[k] < 0 ? s->leaf_lo + 3 * (~ch[k]) : s->nodes[ch[k]].lo;
-                const float *hi = ch[k] < 0 ? s->leaf_hi + 3 * (~ch[k]) : s->nodes[ch[k]].hi;
+                const float *lo = ch[k] < 0 ? T.leaf_lo + 3 * (~ch[k]) : T.nodes[ch[k]].lo;
+                const float *hi = ch[k] < 0 ? T.leaf_hi + 3 * (~ch[k]) : T.nodes[ch[k]].hi;
                 c->nodes++;
                 hit[k] = box_test(lo, hi, y, b->t, &ctn[k]);
             }
@@ -446,7 +567,7 @@ static void cast_one(const orc_scene *s, const ray_t *y, int mode, best_t *b, or
             if (hit[1]) { cur = ch[1]; continue; }
         } else {
             c->tris++;
-            consider(&s->stris[~cur], y, b);
+            consider(&T.stris[~cur], y, b);
         }
         /* pop, skipping entries the current best already excludes */
         for (;;) {
@@ -463,6 +584,7 @@ void orc_cast_rays(const orc_scene *s, const float *rays, uint64_t N, int mode,
                    orc_counters *counters)
 {
     uint64_t cn = 0, ct = 0;
+    if (mode == 2 && !s->sah_nodes) build_sah((orc_scene *)s);
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : cn, ct)
     for (int64_t i = 0; i < (int64_t)N; ++i) {
         ray_t y = load_ray(rays + 6 * i);
@@ -524,6 +646,7 @@ static void all_hits_ex(const orc_scene *s, const ray_t *y, int mode, float tnea
         for (uint64_t i = 0; i < n; ++i) { VISIT(&s->tris[i]); if (first_only && l->n) return; }
         return;
     }
+    const orc_tree T = tree_of(s, mode);
     float tn;
     if (n == 1) {
         c->nodes++;
@@ -532,16 +655,16 @@ static void all_hits_ex(const orc_scene *s, const ray_t *y, int mode, float tnea
     }
     int32_t stk[ORC_STACK]; int sp = 0;
     c->nodes++;
-    if (!box_test(s->nodes[0].lo, s->nodes[0].hi, y, tfar, &tn)) return;
+    if (!box_test(T.nodes[0].lo, T.nodes[0].hi, y, tfar, &tn)) return;
     int32_t cur = 0;
     for (;;) {
         if (cur >= 0) {
-            const orc_node *nd = &s->nodes[cur];
+            const orc_node *nd = &T.nodes[cur];
             int32_t ch[2] = { nd->left, nd->right };
             int hit[2];
             for (int k = 0; k < 2; ++k) {
-                const float *lo = ch[k] < 0 ? s->leaf_lo + 3 * (~ch[k]) : s->nodes[ch[k]].lo;
-                const float *hi = ch[k] < 0 ? s->leaf_hi + 3 * (~ch[k]) : s->nodes[ch[k]].hi;
+                const float *lo = ch[k] < 0 ? T.leaf_lo + 3 * (~ch[k]) : T.nodes[ch[k]].lo;
+                const float *hi = ch[k] < 0 ? T.leaf_hi + 3 * (~ch[k]) : T.nodes[ch[k]].hi;
                 c->nodes++;
                 hit[k] = box_test(lo, hi, y, tfar, &tn);
             }
@@ -550,7 +673,7 @@ static void all_hits_ex(const orc_scene *s, const ray_t *y, int mode, float tnea
             if (hit[1]) { cur = ch[1]; continue; }
         } else {
             c->tris++;
-            VISIT(&s->stris[~cur]);
+            VISIT(&T.stris[~cur]);
             if (first_only && l->n) return;
         }
         if (sp == 0) return;
@@ -584,6 +707,7 @@ void orc_count_intersections(const orc_scene *s, const float *rays, uint64_t N, 
                              int32_t *out, orc_counters *counters)
 {
     uint64_t cn = 0, ct = 0;
+    if (mode == 2 && !s->sah_nodes) build_sah((orc_scene *)s);
 #pragma omp parallel reduction(+ : cn, ct)
     {
         hit_list l = { NULL, 0, 0 };

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqsmrt.so")
+LIB_PATH = os.environ.get("QSMRT_LIB") or os.path.join(_HERE, "libqsmrt.so")      # QSMRT_LIB: an A/B build of the same ABI
 ABI_VERSION = 2
 
 _lib = None

@@ -97,7 +97,7 @@ struct Ray { f3 O, D; float idx, idy, idz, oodx, oody, oodz; };
 __device__ __forceinline__ float safe_inv(float d) {
     const float tiny = 8.271806125530277e-25f;   // 2^-80: 0 * inv is never NaN
     float a = fabsf(d) < tiny ? copysignf(tiny, d) : d;
-    return __fdiv_rn(1.0f, a);
+    return __frcp_rn(a);        // correctly rounded, i.e. the same value as 1.0f / a, in fewer instructions
 }
 
 __device__ __forceinline__ Ray load_ray(const float *__restrict__ rays, uint64_t i) {

@@ -74,7 +74,6 @@ struct qsmrt_scene {
     cudaTextureObject_t node_tex = 0;
     // list_intersections cache between _count and _fill
     const float *list_rays = nullptr; uint64_t list_n = 0;
-    int64_t *list_raw_off = nullptr; HitRec *list_raw = nullptr;
     HostPipe pipe;
     float *sweep_dev = nullptr; uint32_t sweep_cap = 0;     // per-grid constants of qsmrt_sun_exposure_sweep
 };
@@ -169,7 +168,6 @@ void free_build(qsmrt_scene *s)
     dfree(s->goff); dfree(s->voff); dfree(s->keys); dfree(s->order);
     dfree(s->bnodes); dfree(s->tnodes); dfree(s->tris); dfree(s->params); dfree(s->qnodes);
     s->use_qnodes = false;
-    dfree(s->list_raw_off); dfree(s->list_raw);
     s->list_rays = nullptr; s->list_n = 0;
     if (s->node_tex) { cudaDestroyTextureObject(s->node_tex); s->node_tex = 0; }
     s->committed = false;
@@ -827,24 +825,27 @@ int qsmrt_list_intersections_count(qsmrt_scene *s, const float *rays, uint64_t N
     if (!ray_splits || !total_out) FAIL("null output pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (do_commit(s, st, nullptr)) return 1;
-    dfree(s->list_raw_off); dfree(s->list_raw);
     s->list_rays = nullptr; s->list_n = 0;
-    int32_t *cnt = nullptr; void *scratch = nullptr;
-    if (dmalloc(&cnt, N) || dmalloc(&s->list_raw_off, N + 1) ||
-        dmalloc(reinterpret_cast<char **>(&scratch), trv_scan_scratch_bytes(N))) { dfree(cnt); return 1; }
-    SceneView sv = view_of(s);
-    int64_t raw_total = 0;
-    int rc = trv_raw_count(sv, rays, N, cnt, st) || trv_exclusive_scan(cnt, N, s->list_raw_off, scratch, st);
-    if (!rc && cudaMemcpyAsync(&raw_total, s->list_raw_off + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
-    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
-    if (!rc) rc = dmalloc(&s->list_raw, (uint64_t)raw_total);
-    if (!rc) rc = trv_raw_fill_sort(sv, rays, N, s->list_raw_off, s->list_raw, cnt, st) ||
-                  trv_exclusive_scan(cnt, N, ray_splits, scratch, st);
-    if (!rc && cudaMemcpyAsync(total_out, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = 1;
-    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
-    dfree(cnt);
-    { char *p = reinterpret_cast<char *>(scratch); dfree(p); }
-    if (rc) { if (!g_err[0]) qsmrt_set_error("list_intersections failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    *total_out = 0;
+    if (s->ntris == 0 || N == 0) {
+        CUDA_TRY(cudaMemsetAsync(ray_splits, 0, (N + 1) * sizeof(int64_t), st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        s->list_rays = rays; s->list_n = N;
+        return 0;
+    }
+    // first pass = count_intersections (the same distinct-(geometry, t) rule), scanned into the CSR offsets
+    int32_t *cnt = nullptr; char *scratch = nullptr;
+    auto body = [&]() -> int {
+        if (dmalloc(&cnt, N) || dmalloc(&scratch, trv_scan_scratch_bytes(N))) return 1;
+        if (trv_count(s->trv, view_of(s), rays, N, cnt, (uint32_t)s->geoms.size(), st) ||
+            trv_exclusive_scan(cnt, N, ray_splits, scratch, st)) return 1;
+        CUDA_TRY(cudaMemcpyAsync(total_out, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return 0;
+    };
+    const int rc = body();
+    dfree(cnt); dfree(scratch);
+    if (rc) return 1;
     s->list_rays = rays; s->list_n = N;
     return 0;
 }
@@ -853,14 +854,30 @@ int qsmrt_list_intersections_fill(qsmrt_scene *s, const float *rays, uint64_t N,
                                   int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, void *stream)
 {
     SCENE_ENTER(s);
-    if (!s->list_raw_off || s->list_rays != rays || s->list_n != N)
+    if (!s->committed || s->list_rays != rays || s->list_n != N)
         FAIL("list_intersections_fill must follow list_intersections_count on the same rays");
+    if (!ray_splits) FAIL("null ray_splits");
     if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = trv_list_compact(N, s->list_raw_off, s->list_raw, ray_splits, ray_ids, t_hit, geom, prim, uv, st);
-    if (!rc) CUDA_TRY(cudaStreamSynchronize(st));
-    dfree(s->list_raw_off); dfree(s->list_raw);
     s->list_rays = nullptr; s->list_n = 0;
+    if (s->ntris == 0 || N == 0) return 0;
+    // the fill writes t / geometry / primitive / uv of every hit while it deduplicates: outputs the caller skipped
+    // are staged in scratch
+    int64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (total == 0) return 0;
+    float *t_tmp = nullptr, *uv_tmp = nullptr; uint32_t *g_tmp = nullptr, *p_tmp = nullptr;
+    auto body = [&]() -> int {
+        if ((!t_hit && dmalloc(&t_tmp, (uint64_t)total)) || (!geom && dmalloc(&g_tmp, (uint64_t)total)) ||
+            (!prim && dmalloc(&p_tmp, (uint64_t)total)) || (!uv && dmalloc(&uv_tmp, 2 * (uint64_t)total))) return 1;
+        if (trv_list_fill(s->trv, view_of(s), rays, N, ray_splits, (uint32_t)s->geoms.size(), ray_ids, t_hit ? t_hit : t_tmp,
+                          geom ? geom : g_tmp, prim ? prim : p_tmp, uv ? uv : uv_tmp, st)) return 1;
+        if (t_tmp || g_tmp || p_tmp || uv_tmp) CUDA_TRY(cudaStreamSynchronize(st));
+        return 0;
+    };
+    const int rc = body();
+    dfree(t_tmp); dfree(g_tmp); dfree(p_tmp); dfree(uv_tmp);
     return rc;
 }
 

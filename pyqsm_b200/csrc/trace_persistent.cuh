@@ -25,6 +25,9 @@
 //   3  closest hit  -> atomicAdd(accum[triangle], 1)        (sun exposure: no 32 B/ray of results)
 //   4  any hit      -> atomicAdd(accum[ray / n_dirs], !hit) (sky visibility per query point)
 //   5  closest hit among the triangles still alive -> hitflag[sorted triangle] = 1   (peel projection)
+//   6  all hits     -> the distinct (geometry, t) hits of ray i written at list.* [splits[i] ...] (list_intersections,
+//                      second pass: the counts of MODE 2 are already scanned into splits); equal (geometry, t) keeps
+//                      the lowest primitive id.  Rays without hits, or with more than CNT_SET, are skipped here
 // SRC (where rays come from; a uniform runtime switch, only touched at refill)
 //   0  rays[N][6] in memory
 //   1  parallel grid: origin0 + i*du + j*dv, direction dir  (same arithmetic as k_gen_parallel)
@@ -79,27 +82,40 @@ struct RaySource {
     const float *sweep; uint64_t per_grid_rays, per_grid_slots;                    // 3 (nu as in 1)
 };
 
-__device__ __forceinline__ Ray source_ray(const RaySource &S, uint64_t i)
+// 64-bit / 32-bit-sized operands: the 64-bit software division is ~100 instructions, and every refill of the grid
+// and Monte-Carlo sources used to run up to four of them per lane (measured: the fused sun sweep 10 % behind
+// cast_rays + accumulate_hits for that reason alone); batches below 2^32 rays take the 32-bit path
+__device__ __forceinline__ uint64_t fast_div(uint64_t n, uint64_t d)
+{
+    if (((n | d) >> 32) == 0) return (uint64_t)((uint32_t)n / (uint32_t)d);
+    return n / d;
+}
+
+// x / y: column and row of ray i in its grid when the batch is walked in 2-D tiles (have_xy), which saves the grid
+// sources the division of i by the row length
+__device__ __forceinline__ Ray source_ray(const RaySource &S, uint64_t i, uint32_t x = 0, uint64_t y = 0, bool have_xy = false)
 {
     if (S.kind == 0) return load_ray(S.rays, i);
     if (S.kind == 1) {
-        float fu = (float)(i % S.nu), fv = (float)(i / S.nu);
+        if (!have_xy) { y = fast_div(i, S.nu); x = (uint32_t)(i - y * S.nu); }
+        float fu = (float)x, fv = (float)y;
         f3 O = { __fmaf_rn(fu, S.du.x, __fmaf_rn(fv, S.dv.x, S.o0.x)),
                  __fmaf_rn(fu, S.du.y, __fmaf_rn(fv, S.dv.y, S.o0.y)),
                  __fmaf_rn(fu, S.du.z, __fmaf_rn(fv, S.dv.z, S.o0.z)) };
         return make_ray(O, S.dir);
     }
     if (S.kind == 3) {
-        const uint64_t a = i / S.per_grid_rays, li = i - a * S.per_grid_rays;
+        const uint64_t a = fast_div(i, S.per_grid_rays);
         const float4 *g = reinterpret_cast<const float4 *>(S.sweep + 12 * a);      // the same arithmetic as kind 1
         const float4 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);          // o0.xyz du.x | du.yz dv.xy | dv.z dir.xyz
-        float fu = (float)(li % S.nu), fv = (float)(li / S.nu);
+        if (!have_xy) { const uint64_t li = i - a * S.per_grid_rays; y = fast_div(li, S.nu); x = (uint32_t)(li - y * S.nu); }
+        float fu = (float)x, fv = (float)y;
         f3 O = { __fmaf_rn(fu, g0.w, __fmaf_rn(fv, g1.z, g0.x)),
                  __fmaf_rn(fu, g1.x, __fmaf_rn(fv, g1.w, g0.y)),
                  __fmaf_rn(fu, g1.y, __fmaf_rn(fv, g2.x, g0.z)) };
         return make_ray(O, f3{ g2.y, g2.z, g2.w });
     }
-    const uint64_t p = i / S.dir_count;
+    const uint64_t p = fast_div(i, S.dir_count);
     const uint32_t k = S.dir_begin + (uint32_t)(i - p * S.dir_count);
     f3 O = { S.points[3 * p], S.points[3 * p + 1], S.points[3 * p + 2] };
     if (S.normals) {
@@ -116,6 +132,7 @@ struct TraceArgs {
     uint64_t N; uint32_t row_len; uint64_t nslots;
     CastOut out; uint8_t *occluded; float tnear, tfar;          // MODE 0 / 1
     int32_t *counts;                                            // MODE 2
+    const int64_t *splits; float *l_t; uint32_t *l_geom, *l_prim; float2 *l_uv;      // MODE 6
     uint32_t *accum; const uint64_t *goff; uint64_t accum_stride;   // MODE 3 / 4 (stride: one row of counts per grid of a sweep, 0 = one row)
     const uint8_t *alive; uint8_t *hitflag;                     // MODE 5 (both indexed by sorted triangle)
     unsigned long long *cursor, *stats;
@@ -128,11 +145,33 @@ struct TraceArgs {
 #define QSMRT_TRACE_MINB 10
 #endif
 // Node steps per phase vote (the vote only decides the phase, so voting less often saves the loop control all 32
-// lanes execute).  Measured on one box: 1 -> 2 +8 %, 2 -> 4 +2 %; 4 -> 8 another +2-3 % for cast_rays (whose retire
-// path -- 32 B of results, uv and normal recomputed -- profits from larger refill batches) but -5 ... -8 % for the
-// fused sun / sky kernels and the small-scene count, whose lanes retire cheaply and want prompt refills; 12 / 16 lose.
-template <int MODE> struct NodeSteps { static constexpr int value = MODE == 0 ? 8 : 4; };
+// lanes execute, but lanes that finish inside the block idle until its end).  Round 1 (before the sweep source and
+// the aggregated atomics): 1 -> 2 +8 %, 2 -> 4 +2 %, 4 -> 8 +2-3 % for cast_rays.  Re-measured in round 2
+// (profiles/r02_tuning.txt): cast_rays C2 4 = 8 (4568 vs 4583 Mrays/s) while the short rays of the C1 tree gain
+// 5-12 % with 4; the fused kernels, whose lanes retire cheaply and want prompt refills, prefer 2: sun sweep
+// 3511 / 3854 / 4086 and sky 2038 / 2184 / 2444 Mrays/s at 8 / 4 / 2.
+#ifndef QSMRT_STEPS_M0
+#define QSMRT_STEPS_M0 4
+#endif
+#ifndef QSMRT_STEPS_M3
+#define QSMRT_STEPS_M3 2
+#endif
+#ifndef QSMRT_STEPS_M4
+#define QSMRT_STEPS_M4 2
+#endif
+#ifndef QSMRT_STEPS_OTHER
+#define QSMRT_STEPS_OTHER 4
+#endif
+template <int MODE> struct NodeSteps {
+    static constexpr int value = MODE == 0 ? QSMRT_STEPS_M0 : MODE == 3 ? QSMRT_STEPS_M3 : MODE == 4 ? QSMRT_STEPS_M4 : QSMRT_STEPS_OTHER;
+};
 constexpr int TR_TRI_STEPS = 2;      // triangle tests per phase vote (1: -1.5 %, 3: same)
+// The FMA slab form t = plane * (1/d) - o * (1/d) rounds with an error of a few ulp OF THE CONSTANT o/d, which grows
+// with the distance of the ray origin from the scene, while the boxes' padding is a fixed 2^-17 of the scene size
+// (3 grid cells for the quantised nodes): for origins hundreds of scene sizes away the padding no longer covers it.
+// Widening every slab interval by 2^-20 of its own t (8 ulp) keeps the test conservative at any distance; the two
+// multiplications per child are immediate-form FMULs on the FMA pipe, which this ALU-bound loop leaves idle.
+constexpr float SLAB_NEAR = 0.99999905f, SLAB_FAR = 1.00000095f;
 constexpr int CNT_SET = 32;     // distinct (geometry, t) pairs a lane can hold before it defers to the exact slow path
 
 __device__ __forceinline__ void ld256u(const void *p, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
@@ -181,6 +220,7 @@ k_trace5(const TraceArgs A)
     float *const tset = reinterpret_cast<float *>(sstack + A.depth * TR_BLOCK) + threadIdx.x;      // MODE 2
     uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + CNT_SET) * TR_BLOCK) + threadIdx.x;
     int cnt = 0; bool overflow = false;
+    long long lbase = 0;                                        // MODE 6: first output slot of this lane's ray
     uint32_t snx = 0x7610u, sny = 0x7610u, snz = 0x7610u;       // QUANT: per-axis "near plane" byte selectors
 
 #define PARK_LEAF5() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; \
@@ -200,8 +240,8 @@ k_trace5(const TraceArgs A)
                 if (add) {
                     unsigned long long key;
                     if (MODE == 3) key = (A.goff ? A.goff[best_geom] : 0ull) + best_prim +
-                                         (A.src.kind == 3 ? (ray_i / A.src.per_grid_rays) * A.accum_stride : 0ull);
-                    else key = ray_i / A.src.dir_count;
+                                         (A.src.kind == 3 && A.accum_stride ? fast_div(ray_i, A.src.per_grid_rays) * A.accum_stride : 0ull);
+                    else key = fast_div(ray_i, A.src.dir_count);
                     const unsigned grp = __match_any_sync(am, key);
                     if ((grp & lt) == 0u) atomicAdd(&A.accum[key], (uint32_t)__popc(grp));
                 }
@@ -245,15 +285,21 @@ k_trace5(const TraceArgs A)
                 exhausted = base + (unsigned long long)need >= A.nslots;
                 if (idle) {
                     const uint64_t slot = base + __popc(im & lt);
-                    uint64_t i = 0;
+                    uint64_t i = 0, gy = 0;
+                    uint32_t gx = 0;
                     bool ok = slot < A.nslots;
                     if (A.src.kind == 3) {          // sweep: slot -> (grid, slot inside the grid)
-                        const uint64_t a = slot / A.src.per_grid_slots;
-                        ok = ok && ray_index_of_slot(slot - a * A.src.per_grid_slots, A.src.per_grid_rays, A.row_len, i);
+                        const uint64_t a = fast_div(slot, A.src.per_grid_slots);
+                        ok = ok && ray_index_of_slot(slot - a * A.src.per_grid_slots, A.src.per_grid_rays, A.row_len, i, gx, gy);
                         i += a * A.src.per_grid_rays;
-                    } else ok = ok && ray_index_of_slot(slot, A.N, A.row_len, i);
+                    } else ok = ok && ray_index_of_slot(slot, A.N, A.row_len, i, gx, gy);
+                    if (MODE == 6 && ok) {          // nothing to list (or too much for the on-chip set: k_list_slow does those)
+                        lbase = A.splits[i];
+                        const long long k = A.splits[i + 1] - lbase;
+                        ok = k > 0 && k <= CNT_SET;
+                    }
                     if (ok) {
-                        r = source_ray(A.src, i);
+                        r = source_ray(A.src, i, gx, gy, A.row_len != 0);
                         if (QUANT) {
                             const float ax = A.sc.cell[0] * r.idx, ay = A.sc.cell[1] * r.idy, az = A.sc.cell[2] * r.idz;
                             r.oodx = fmaf(8388608.0f, ax, -((A.sc.glo[0] - r.O.x) * r.idx));
@@ -317,13 +363,13 @@ k_trace5(const TraceArgs A)
                     float nx = fmaf(QPL(w0, snx), r.idx, -r.oodx), fx = fmaf(QPL(w0, sfx), r.idx, -r.oodx);
                     float ny = fmaf(QPL(w1, sny), r.idy, -r.oody), fy = fmaf(QPL(w1, sfy), r.idy, -r.oody);
                     float nz = fmaf(QPL(w2, snz), r.idz, -r.oodz), fz = fmaf(QPL(w2, sfz), r.idz, -r.oodz);
-                    t0 = fmaxf(fmax3(nx, ny, nz), 0.0f);
-                    h0 = t0 <= fminf(fmin3(fx, fy, fz), best_t);
+                    t0 = fmaxf(fmax3(nx, ny, nz) * SLAB_NEAR, 0.0f);
+                    h0 = t0 <= fminf(fmin3(fx, fy, fz) * SLAB_FAR, best_t);
                     nx = fmaf(QPL(w3, snx), r.idx, -r.oodx); fx = fmaf(QPL(w3, sfx), r.idx, -r.oodx);
                     ny = fmaf(QPL(w4, sny), r.idy, -r.oody); fy = fmaf(QPL(w4, sfy), r.idy, -r.oody);
                     nz = fmaf(QPL(w5, snz), r.idz, -r.oodz); fz = fmaf(QPL(w5, sfz), r.idz, -r.oodz);
-                    t1 = fmaxf(fmax3(nx, ny, nz), 0.0f);
-                    h1 = t1 <= fminf(fmin3(fx, fy, fz), best_t);
+                    t1 = fmaxf(fmax3(nx, ny, nz) * SLAB_NEAR, 0.0f);
+                    h1 = t1 <= fminf(fmin3(fx, fy, fz) * SLAB_FAR, best_t);
 #undef QPL
                     c0 = (int)w6; c1 = (int)w7;
                 } else {
@@ -388,12 +434,20 @@ k_trace5(const TraceArgs A)
                     if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
                         const float tt = __fdiv_rn(h.T, h.absDen);
                         const uint32_t pg = __float_as_uint(p1.w);
-                        bool dup = false;
+                        int at = -1;
                         for (int q = 0; q < cnt; ++q)
-                            dup = dup || (tset[q * TR_BLOCK] == tt && (!A.multi_geom || gset[q * TR_BLOCK] == pg));
-                        if (!dup) {
-                            if (cnt < CNT_SET) { tset[cnt * TR_BLOCK] = tt; if (A.multi_geom) gset[cnt * TR_BLOCK] = pg; ++cnt; }
+                            if (tset[q * TR_BLOCK] == tt && (!A.multi_geom || gset[q * TR_BLOCK] == pg)) at = q;
+                        if (at < 0) {
+                            if (cnt < CNT_SET) { tset[cnt * TR_BLOCK] = tt; if (A.multi_geom) gset[cnt * TR_BLOCK] = pg; at = cnt; ++cnt; }
                             else { overflow = true; cur = TR_SENTINEL; tri_i = tri_end; }   // the fix-up kernel recounts this ray
+                            if (MODE == 6 && !overflow) A.l_prim[lbase + at] = QSMRT_INVALID;   // so the first record always wins below
+                        }
+                        if (MODE == 6 && at >= 0) {
+                            const uint32_t pp = __float_as_uint(p0.w);
+                            if (pp < A.l_prim[lbase + at]) {            // survivor of equal (geometry, t): the lowest primitive id
+                                A.l_t[lbase + at] = tt; A.l_geom[lbase + at] = pg; A.l_prim[lbase + at] = pp;
+                                A.l_uv[lbase + at] = make_float2(__fdiv_rn(h.U, h.absDen), __fdiv_rn(h.V, h.absDen));
+                            }
                         }
                     }
                     if (!overflow) {

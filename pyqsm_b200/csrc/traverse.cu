@@ -115,8 +115,8 @@ __device__ __forceinline__ bool slab_fma(float lox, float hix, float loy, float 
     float x0 = fmaf(lox, r.idx, -r.oodx), x1 = fmaf(hix, r.idx, -r.oodx);
     float y0 = fmaf(loy, r.idy, -r.oody), y1 = fmaf(hiy, r.idy, -r.oody);
     float z0 = fmaf(loz, r.idz, -r.oodz), z1 = fmaf(hiz, r.idz, -r.oodz);
-    float tmin = fmaxf(fmax3(fminf(x0, x1), fminf(y0, y1), fminf(z0, z1)), 0.0f);
-    float tfar = fminf(fmin3(fmaxf(x0, x1), fmaxf(y0, y1), fmaxf(z0, z1)), tmax);
+    float tmin = fmaxf(fmax3(fminf(x0, x1), fminf(y0, y1), fminf(z0, z1)) * 0.99999905f, 0.0f);      // see SLAB_NEAR / SLAB_FAR
+    float tfar = fminf(fmin3(fmaxf(x0, x1), fmaxf(y0, y1), fmaxf(z0, z1)) * 1.00000095f, tmax);
     tn = tmin;
     return tmin <= tfar;
 }
@@ -201,16 +201,17 @@ k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t r
 // Evidence for its shape (profiles/README.md): the per-thread loop below spends half
 // its issue slots in leaf code with ~2.3 of 32 lanes active, and idle lanes of
 // finished rays wait for the slowest ray of the warp.
-__device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uint32_t row_len, uint64_t &i)
+__device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uint32_t row_len, uint64_t &i, uint32_t &x, uint64_t &y)
 {
     if (row_len == 0) { i = slot; return slot < N; }
     const uint32_t lane = (uint32_t)(slot & 31u);
     const uint64_t tile = slot >> 5;
     const uint32_t tiles_x = (row_len + 7u) >> 3;
-    const uint64_t ty = tile / tiles_x;
+    // 32-bit division whenever the tile number fits (batches below 2^37 rays): the 64-bit one is ~100 instructions
+    const uint64_t ty = (tile >> 32) == 0 ? (uint64_t)((uint32_t)tile / tiles_x) : tile / tiles_x;
     const uint32_t tx = (uint32_t)(tile - ty * tiles_x);
-    const uint32_t x = tx * 8u + (lane & 7u);
-    const uint64_t y = ty * 4u + (lane >> 3);
+    x = tx * 8u + (lane & 7u);
+    y = ty * 4u + (lane >> 3);
     i = y * row_len + x;
     return x < row_len && i < N;
 }
@@ -360,111 +361,74 @@ k_count_fix(SceneView sc, const float *__restrict__ rays, uint64_t N, int32_t *_
     }
 }
 
-// list_intersections, phase 1a: raw (un-deduplicated) hit count per ray
-struct RawCountVis {
-    const SceneView &sc; const Ray &r; int n;
-    __device__ __forceinline__ float tmax() const { return INFINITY; }
-    __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
-        for (uint32_t k = 0; k < count; ++k) {
-            float4 p0, p1, p2;
-            load_tri(sc.tris, first + k, p0, p1, p2);
-            MtHit h;
-            n += mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h) ? 1 : 0;
-        }
-        return false;
-    }
-};
-
-__global__ void __launch_bounds__(TR_BLOCK)
-k_raw_count(SceneView sc, const float *__restrict__ rays, uint64_t N, int32_t *__restrict__ out)
-{
-    __shared__ int sstack[TR_SSTACK * TR_BLOCK];
-    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
-    if (i >= N) return;
-    Ray r = load_ray(rays, i);
-    int spill[TR_LSTACK];
-    Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
-    RawCountVis vis{ sc, r, 0 };
-    if (sc.ntris) traverse<false>(sc, r, st, vis);
-    out[i] = vis.n;
-}
-
-// phase 1b: write every raw hit of ray i at raw[raw_off[i] ...]
-struct RawFillVis {
-    const SceneView &sc; const Ray &r; HitRec *dst;
-    __device__ __forceinline__ float tmax() const { return INFINITY; }
+// ---- list_intersections, throughput path -------------------------------------------------------------------
+// (1) count_intersections (persistent MODE 2 + exact fix-up) -> exclusive scan = ray_splits;
+// (2) persistent MODE 6 writes the distinct hits of every ray with 1 .. CNT_SET of them straight into the caller's
+//     arrays at ray_splits[i] (rays without hits -- most of a sparse canopy -- are not traversed again);
+// (3) k_list_finish: one thread per ray sorts its (short) segment by (t, geometry, primitive) and fills ray_ids;
+//     rays with more than CNT_SET hits enumerate them in increasing order instead, one traversal per hit.
+struct NextFullVis {      // smallest (t, geom) strictly after (pt, pg); among equal (t, geom) the lowest primitive
+    const SceneView &sc; const Ray &r;
+    float pt; uint32_t pg; bool have_prev;
+    float bt; uint32_t bg, bp; float bu, bv; bool found;
+    __device__ __forceinline__ float tmax() const { return bt; }
     __device__ __forceinline__ bool leaf(uint32_t first, uint32_t count) {
         for (uint32_t k = 0; k < count; ++k) {
             float4 p0, p1, p2;
             load_tri(sc.tris, first + k, p0, p1, p2);
             MtHit h;
             if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
-                HitRec hr;
-                hr.t = __fdiv_rn(h.T, h.absDen); hr.u = __fdiv_rn(h.U, h.absDen); hr.v = __fdiv_rn(h.V, h.absDen);
-                hr.geom = __float_as_uint(p1.w); hr.prim = __float_as_uint(p0.w);
-                *dst++ = hr;
+                const float tt = __fdiv_rn(h.T, h.absDen);
+                const uint32_t g = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
+                const bool after = !have_prev || (tt > pt) || (tt == pt && g > pg);
+                const bool better = !found || (tt < bt) || (tt == bt && (g < bg || (g == bg && pp < bp)));
+                if (after && better) {
+                    bt = tt; bg = g; bp = pp; found = true;
+                    bu = __fdiv_rn(h.U, h.absDen); bv = __fdiv_rn(h.V, h.absDen);
+                }
             }
         }
         return false;
     }
 };
 
-__device__ __forceinline__ bool hit_less(const HitRec &a, const HitRec &b)
-{
-    if (a.t != b.t) return a.t < b.t;
-    if (a.geom != b.geom) return a.geom < b.geom;
-    return a.prim < b.prim;
-}
-
-// phase 1b+1c fused: fill, then per ray shell-sort by (t, geom, prim) and drop
-// hits repeating the previous (t, geom); deduplicated count -> cnt[i]
 __global__ void __launch_bounds__(TR_BLOCK)
-k_raw_fill_sort(SceneView sc, const float *__restrict__ rays, uint64_t N,
-                const int64_t *__restrict__ raw_off, HitRec *__restrict__ raw, int32_t *__restrict__ cnt)
+k_list_finish(SceneView sc, const float *__restrict__ rays, uint64_t N, const int64_t *__restrict__ splits, int max_fast,
+              int64_t *__restrict__ ray_ids, float *__restrict__ t_hit, uint32_t *__restrict__ geom, uint32_t *__restrict__ prim,
+              float2 *__restrict__ uv)
 {
     __shared__ int sstack[TR_SSTACK * TR_BLOCK];
-    uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
+    const uint64_t i = blockIdx.x * (uint64_t)TR_BLOCK + threadIdx.x;
     if (i >= N) return;
-    Ray r = load_ray(rays, i);
+    const int64_t o = splits[i];
+    const int n = (int)(splits[i + 1] - o);
+    if (n == 0) return;
+    if (ray_ids) for (int k = 0; k < n; ++k) ray_ids[o + k] = (int64_t)i;
+    if (n <= max_fast) {
+        // insertion sort of the segment the persistent kernel filled (a handful of hits; keys (t, geom, prim))
+        for (int a = 1; a < n; ++a) {
+            const float xt = t_hit[o + a]; const uint32_t xg = geom[o + a], xp = prim[o + a]; const float2 xu = uv[o + a];
+            int b = a;
+            for (; b > 0; --b) {
+                const float yt = t_hit[o + b - 1]; const uint32_t yg = geom[o + b - 1], yp = prim[o + b - 1];
+                const bool less = xt < yt || (xt == yt && (xg < yg || (xg == yg && xp < yp)));
+                if (!less) break;
+                t_hit[o + b] = yt; geom[o + b] = yg; prim[o + b] = yp; uv[o + b] = uv[o + b - 1];
+            }
+            if (b != a) { t_hit[o + b] = xt; geom[o + b] = xg; prim[o + b] = xp; uv[o + b] = xu; }
+        }
+        return;
+    }
+    const Ray r = load_ray(rays, i);
     int spill[TR_LSTACK];
     Stack st; st.s = sstack + threadIdx.x; st.loc = spill;
-    HitRec *seg = raw + raw_off[i];
-    int n = (int)(raw_off[i + 1] - raw_off[i]);
-    RawFillVis vis{ sc, r, seg };
-    if (sc.ntris && n) traverse<false>(sc, r, st, vis);
-    for (int gap = n / 2; gap > 0; gap /= 2)
-        for (int a = gap; a < n; ++a) {
-            HitRec x = seg[a];
-            int b = a;
-            for (; b >= gap && hit_less(x, seg[b - gap]); b -= gap) seg[b] = seg[b - gap];
-            seg[b] = x;
-        }
-    int m = 0;
-    for (int a = 0; a < n; ++a) {
-        HitRec x = seg[a];
-        if (m > 0 && seg[m - 1].t == x.t && seg[m - 1].geom == x.geom) continue;
-        seg[m++] = x;
-    }
-    cnt[i] = m;
-}
-
-__global__ void __launch_bounds__(256)
-k_list_compact(uint64_t N, const int64_t *__restrict__ raw_off, const HitRec *__restrict__ raw,
-               const int64_t *__restrict__ splits, int64_t *__restrict__ ray_ids, float *__restrict__ t_hit,
-               uint32_t *__restrict__ geom, uint32_t *__restrict__ prim, float2 *__restrict__ uv)
-{
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int64_t o = splits[i];
-    int m = (int)(splits[i + 1] - o);
-    const HitRec *seg = raw + raw_off[i];
-    for (int k = 0; k < m; ++k) {
-        HitRec x = seg[k];
-        if (ray_ids) ray_ids[o + k] = (int64_t)i;
-        if (t_hit) t_hit[o + k] = x.t;
-        if (geom) geom[o + k] = x.geom;
-        if (prim) prim[o + k] = x.prim;
-        if (uv) uv[o + k] = make_float2(x.u, x.v);
+    NextFullVis nv{ sc, r, 0.0f, 0u, false, INFINITY, 0u, 0u, 0.0f, 0.0f, false };
+    for (int k = 0; k < n; ++k) {
+        nv.bt = INFINITY; nv.bg = 0u; nv.bp = 0u; nv.found = false;
+        traverse<true>(sc, r, st, nv);
+        if (!nv.found) break;                       // cannot happen: n came from the exact count
+        t_hit[o + k] = nv.bt; geom[o + k] = nv.bg; prim[o + k] = nv.bp; uv[o + k] = make_float2(nv.bu, nv.bv);
+        nv.pt = nv.bt; nv.pg = nv.bg; nv.have_prev = true;
     }
 }
 
@@ -1006,29 +970,24 @@ int trv_occluded(TrvState &ts, const SceneView &sc, const float *rays, uint64_t 
     return 0;
 }
 
-int trv_raw_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st)
+// list_intersections second pass: fill the CSR arrays at the scanned offsets, then sort each ray's segment
+int trv_list_fill(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, const int64_t *splits, uint32_t ngeoms,
+                  int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st)
 {
-    if (N == 0) return 0;
-    k_raw_count<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, out);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-int trv_raw_fill_sort(const SceneView &sc, const float *rays, uint64_t N, const int64_t *raw_off,
-                      HitRec *raw, int32_t *cnt, cudaStream_t st)
-{
-    if (N == 0) return 0;
-    k_raw_fill_sort<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, raw_off, raw, cnt);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-int trv_list_compact(uint64_t N, const int64_t *raw_off, const HitRec *raw, const int64_t *splits,
-                     int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st)
-{
-    if (N == 0) return 0;
-    k_list_compact<<<grid_for(N, 256), 256, 0, st>>>(N, raw_off, raw, splits, ray_ids, t_hit, geom, prim,
-                                                     reinterpret_cast<float2 *>(uv));
+    if (N == 0 || sc.ntris == 0) return 0;
+    const int depth = (int)sc.height + 2;
+    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * CNT_SET) * TR_BLOCK * sizeof(int);
+    int max_fast = 0;
+    if (use_v5(ts, sc, smem)) {
+        TraceArgs a{};
+        a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
+        a.depth = depth; a.multi_geom = ngeoms > 1;
+        a.splits = splits; a.l_t = t_hit; a.l_geom = geom; a.l_prim = prim; a.l_uv = reinterpret_cast<float2 *>(uv);
+        if (launch_trace5<6, false>(ts, a, smem, st)) return 1;
+        max_fast = CNT_SET;
+    }
+    k_list_finish<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, splits, max_fast, ray_ids, t_hit, geom, prim,
+                                                            reinterpret_cast<float2 *>(uv));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -3,8 +3,6 @@
 #include <vector>
 #include "common.cuh"
 
-struct HitRec { float t, u, v; uint32_t geom, prim; };   // 20-byte raw hit (list_intersections scratch)
-
 // Per-scene traversal options (qsmrt_scene_set_option), read at every launch.
 struct TrvOptions {
     int variant = 2;        // 1 = one independent loop per thread, 2 = persistent warp-uniform kernel (ships)
@@ -32,11 +30,8 @@ int trv_cast_rays(TrvState &ts, const SceneView &sc, const float *rays, uint64_t
                   uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
 int trv_count(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st);
 int trv_occluded(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st);
-int trv_raw_count(const SceneView &sc, const float *rays, uint64_t N, int32_t *out, cudaStream_t st);
-int trv_raw_fill_sort(const SceneView &sc, const float *rays, uint64_t N, const int64_t *raw_off,
-                      HitRec *raw, int32_t *cnt, cudaStream_t st);
-int trv_list_compact(uint64_t N, const int64_t *raw_off, const HitRec *raw, const int64_t *splits,
-                     int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st);
+int trv_list_fill(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, const int64_t *splits, uint32_t ngeoms,
+                  int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st);
 size_t trv_scan_scratch_bytes(uint64_t n);
 int trv_exclusive_scan(const int32_t *in, uint64_t n, int64_t *out, void *scratch, cudaStream_t st);
 int trv_gen_parallel(float *rays, uint64_t nu, uint64_t nv, const float o0[3], const float du[3],

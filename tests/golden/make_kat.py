@@ -78,6 +78,38 @@ kats.append(dict(name="kat10_box_distance_occupancy", mesh=dict(v=bv.tolist(), t
                  distance=[0.5, math.sqrt(0.75), 0.25, math.sqrt(0.5)], occupancy=[1.0, 0.0, 1.0, 0.0],
                  signed_distance=[-0.5, math.sqrt(0.75), -0.25, math.sqrt(0.5)]))
 
+# KAT-11: Open3D test_raycasting_scene.py::test_test_occlusions (as recalled): the KAT-1 rays with the interval moved
+# around the hit at t = 1.  tnear is exclusive, tfar inclusive (Embree: tnear < t <= tfar).
+kats.append(dict(name="kat11_occlusion_interval", mesh=dict(v=tri_v, t=tri_t),
+                 rays=[[0.2, 0.1, 1, 0, 0, -1], [10, 10, 10, 1, 0, 0]],
+                 occlusion_cases=[dict(tnear=0.0, tfar=INF, expect=[True, False]), dict(tnear=0.0, tfar=0.99, expect=[False, False]),
+                                  dict(tnear=1.01, tfar=INF, expect=[False, False]), dict(tnear=0.0, tfar=1.0, expect=[True, False]),
+                                  dict(tnear=1.0, tfar=INF, expect=[False, False]), dict(tnear=0.5, tfar=2.0, expect=[True, False])]))
+# KAT-12: Open3D test_output_shapes (as recalled): results keep the leading shape of the rays, plus 2 / 3 for uv / normals
+kats.append(dict(name="kat12_leading_shape", mesh=dict(v=tri_v, t=tri_t), shape=[2, 3],
+                 rays=[[0.2, 0.1, 1, 0, 0, -1], [10, 10, 10, 1, 0, 0], [0.9, 0.5, 2, 0, 0, -1],
+                       [0.2, 0.1, -3, 0, 0, 1], [0.5, 0.9, 1, 0, 0, -1], [0.6, 0.3, 1, 0, 0, -4]],
+                 cast=dict(t_hit=[1.0, INF, 2.0, 3.0, INF, 0.25], primitive_ids=[0, INV, 0, 0, INV, 0], geometry_ids=[0, INV, 0, 0, INV, 0]),
+                 count=[1, 0, 1, 1, 0, 1], occluded=[True, False, True, True, False, True]))
+# KAT-13: two geometries (add_triangles returns 0 then 1; ray_casting.py:156 keeps that id): the KAT-1 triangle at z = 0
+# and a copy at z = -1.  geometry_ids / primitive_ids of closest hits from above and below, both in list_intersections.
+tri_v2 = [[0, 0, -1], [1, 0, -1], [1, 1, -1]]
+kats.append(dict(name="kat13_two_geometries", mesh=dict(v=tri_v, t=tri_t), mesh2=dict(v=tri_v2, t=tri_t),
+                 rays=[[0.2, 0.1, 1, 0, 0, -1], [0.2, 0.1, -3, 0, 0, 1], [0.2, 0.1, -0.5, 0, 0, 1], [0.2, 0.1, -0.5, 0, 0, -1]],
+                 cast=dict(t_hit=[1.0, 2.0, 0.5, 0.5], geometry_ids=[0, 1, 0, 1], primitive_ids=[0, 0, 0, 0],
+                           primitive_uvs=[[0.1, 0.1]] * 4, primitive_normals=[[0, 0, 1]] * 4),
+                 count=[2, 2, 1, 1], occluded=[True, True, True, True],
+                 list=dict(ray_splits=[0, 2, 4, 5, 6], t_hit=[1.0, 2.0, 2.0, 3.0, 0.5, 0.5], geometry_ids=[0, 1, 1, 0, 0, 1],
+                           primitive_ids=[0] * 6, primitive_uvs=[[0.1, 0.1]] * 6)))
+# KAT-14: list_intersections on the unit box with ids and uvs (ray_casting.py:168-180 reads primitive_ids / primitive_uvs):
+# the ray at (0.25, 0.6) crosses the z = 0 and z = 1 faces in their second triangles (a, c, d) = prims 1 and 3,
+# p = a + u (c - a) + v (d - a) = (u, u + v)  =>  u = 0.25, v = 0.35
+kats.append(dict(name="kat14_box_list_ids", mesh=dict(v=bv.tolist(), t=bt.tolist()),
+                 rays=[[0.25, 0.6, -1, 0, 0, 1], [0.25, 0.6, 0.5, 0, 0, -2]],
+                 list=dict(ray_splits=[0, 2, 3], t_hit=[1.0, 2.0, 0.25], geometry_ids=[0, 0, 0], primitive_ids=[1, 3, 1],
+                           primitive_uvs=[[0.25, 0.35]] * 3),
+                 cast=dict(t_hit=[1.0, 0.25], primitive_ids=[1, 1], primitive_uvs=[[0.25, 0.35]] * 2, primitive_normals=[[0, 0, 1]] * 2)))
+
 # KAT-8: pinhole camera (Open3D CreateRaysPinhole): fov 90, eye (0,0,-1) looking at the origin
 kats.append(dict(name="kat8_pinhole", pinhole=dict(fov_deg=90, center=[0, 0, 0], eye=[0, 0, -1], up=[0, 1, 0],
                                                      width_px=4, height_px=2),

@@ -31,6 +31,8 @@ def check_kat(kat, scene_factory):
     s = scene_factory()
     gid = s.add_triangles(np.asarray(kat["mesh"]["v"], np.float32), np.asarray(kat["mesh"]["t"], np.uint32))
     assert gid == 0
+    if "mesh2" in kat:
+        assert s.add_triangles(np.asarray(kat["mesh2"]["v"], np.float32), np.asarray(kat["mesh2"]["t"], np.uint32)) == 1
     if "points" in kat:
         q = np.asarray(kat["points"], np.float32)
         if "closest" in kat:
@@ -48,6 +50,22 @@ def check_kat(kat, scene_factory):
             np.testing.assert_allclose(_np(s.compute_signed_distance(q)), np.asarray(kat["signed_distance"]), rtol=RTOL, err_msg=kat["name"])
         return
     rays = np.asarray(kat["rays"], np.float32)
+    if "shape" in kat:
+        # leading-shape preservation: the same rays shaped [..., 6] give results shaped [...] (+ 2 / 3)
+        lead = tuple(kat["shape"])
+        shaped = rays.reshape(lead + (6,))
+        a = s.cast_rays(shaped)
+        assert tuple(_np(a["t_hit"]).shape) == lead and tuple(_np(a["geometry_ids"]).shape) == lead
+        assert tuple(_np(a["primitive_ids"]).shape) == lead and tuple(_np(a["primitive_uvs"]).shape) == lead + (2,)
+        assert tuple(_np(a["primitive_normals"]).shape) == lead + (3,)
+        assert tuple(_np(s.count_intersections(shaped)).shape) == lead and tuple(_np(s.test_occlusions(shaped)).shape) == lead
+        flat = s.cast_rays(rays)
+        for key in ("t_hit", "geometry_ids", "primitive_ids", "primitive_uvs", "primitive_normals"):
+            assert np.array_equal(_np(a[key]).reshape(_np(flat[key]).shape), _np(flat[key])), (kat["name"], key)
+    for case in kat.get("occlusion_cases", []):
+        tfar = math.inf if case["tfar"] == "inf" else case["tfar"]
+        o = _np(s.test_occlusions(rays, tnear=case["tnear"], tfar=tfar))
+        assert o.tolist() == case["expect"], (kat["name"], case, o.tolist())
     if "cast" in kat:
         ans = s.cast_rays(rays)
         exp = kat["cast"]
@@ -84,3 +102,8 @@ def check_kat(kat, scene_factory):
         assert _np(l["ray_ids"]).shape == (k,) and _np(l["primitive_uvs"]).shape == (k, 2)
         splits = _np(l["ray_splits"])
         assert np.array_equal(_np(l["ray_ids"]), np.repeat(np.arange(len(rays)), np.diff(splits)))
+        for key in ("geometry_ids", "primitive_ids"):
+            if key in kat["list"]:
+                assert np.array_equal(_np(l[key]).astype(np.int64), np.asarray(kat["list"][key], np.int64)), (kat["name"], key)
+        if "primitive_uvs" in kat["list"]:
+            np.testing.assert_allclose(_np(l["primitive_uvs"]), np.asarray(kat["list"]["primitive_uvs"]), rtol=RTOL, atol=1e-6, err_msg=kat["name"])

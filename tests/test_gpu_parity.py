@@ -629,11 +629,11 @@ def test_property_gpu_equals_brute_force(case):
 
 
 def test_far_origins_and_offset_scenes(RS, oracle_mod):
-    """The conservative-box argument (leaf padding 2^-17, 3-cell widening of quantised nodes) is stated for ray
-    origins within a few tens of scene sizes and scenes near the coordinate origin; check it holds with margin:
-    origins 20 scene diagonals away, and the same tree translated 300 m from the origin (LiDAR plot offsets)."""
-    from pyqsm_b200 import _lib
-    L = _lib.load()
+    """Conservative boxes at any distance: the leaf padding (2^-17 of the scene, 3 cells for the quantised nodes)
+    covers origins within a few tens of scene sizes; beyond that every slab interval is widened by 2^-20 of its own
+    t (trace_persistent.cuh SLAB_NEAR / SLAB_FAR), which grows with the distance like the rounding of the slab
+    constants does.  Origins 20, 1000 and 10000 scene diagonals away, a tree translated 300 m from the coordinate
+    origin (LiDAR plot offsets), both node formats, both traversal kernels: every hit brute force finds is found."""
     v, t = syn.qsm_tree_mesh(seed=11, n_cylinders=40)
     diag = float(np.linalg.norm(v.max(0) - v.min(0)))
     for shift in (np.zeros(3, np.float32), np.array([300.0, -250.0, 40.0], np.float32)):
@@ -641,17 +641,23 @@ def test_far_origins_and_offset_scenes(RS, oracle_mod):
         o = oracle_mod.OracleScene()
         o.add_triangles(vs, t)
         near = syn.random_rays(vs.min(0), vs.max(0), 6000, seed=3)
-        far = near.copy()
-        far[:, :3] -= far[:, 3:] * np.float32(20.0 * diag)             # same lines, origins 20 diagonals back
-        rays = np.concatenate([near, far])
+        sets = [near]
+        for k in (20.0, 1.0e3, 1.0e4):
+            far = near.copy()
+            far[:, :3] -= far[:, 3:] * np.float32(k * diag)            # same lines, origins k diagonals back
+            sets.append(far)
+        rays = np.concatenate(sets)
         ref = o.cast_rays(rays, 0)                                     # brute force
-        assert np.isfinite(ref["t_hit"][6000:]).sum() > 300
-        for quant in (1, 0):
+        for k in range(1, 4):
+            assert np.isfinite(ref["t_hit"][6000 * k: 6000 * (k + 1)]).sum() > 300
+        cnt = o.count_intersections(rays, 0)
+        for quant, variant in ((1, 2), (0, 2), (1, 1)):
             g = RS()
             g.set_option("quantised_nodes", quant)
+            g.set_option("traversal_variant", variant)
             g.add_triangles(vs, t)
-            assert_cast_equal(g.cast_rays(rays), ref, None, f"far/shift{shift[0]}/q{quant}")
-            assert np.array_equal(g.count_intersections(rays).numpy(), o.count_intersections(rays, 0))
+            assert_cast_equal(g.cast_rays(rays), ref, None, f"far/shift{shift[0]}/q{quant}/v{variant}")
+            assert np.array_equal(g.count_intersections(rays).numpy(), cnt)
 
 
 @pytest.mark.parametrize("cap", [1, 7, 100])

@@ -30,8 +30,8 @@ class _ModeScene:
     def count_intersections(self, r):
         return self.s.count_intersections(r, self.mode)
 
-    def test_occlusions(self, r):
-        return self.s.test_occlusions(r, mode=self.mode)
+    def test_occlusions(self, r, tnear=0.0, tfar=float("inf")):
+        return self.s.test_occlusions(r, tnear, tfar, mode=self.mode)
 
     def list_intersections(self, r):
         return self.s.list_intersections(r, self.mode)
@@ -49,7 +49,7 @@ class _ModeScene:
         return self.s.compute_signed_distance(q, self.mode)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("kat", [k for k in KATS if "mesh" in k], ids=lambda k: k["name"])
 def test_golden_vectors(orc, kat, mode):
     check_kat(kat, lambda: _ModeScene(orc, mode))
@@ -177,6 +177,13 @@ def test_brute_equals_bvh(orc, seed):
     for k in a:
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(s.count_intersections(rays, 0), s.count_intersections(rays, 1))
+    # mode 2: the binned-SAH tree of the tree-quality measurement answers identically (and visits no more nodes)
+    lb_nodes = (s.cast_rays(rays, 1), s.last_counters)[1][0]
+    c = s.cast_rays(rays, 2)
+    assert s.last_counters[0] <= 1.1 * lb_nodes
+    for k in a:
+        assert np.array_equal(a[k], c[k]), k
+    assert np.array_equal(s.count_intersections(rays, 0), s.count_intersections(rays, 2))
     assert np.array_equal(s.test_occlusions(rays, mode=0), s.test_occlusions(rays, mode=1))
     assert np.array_equal(s.test_occlusions(rays, 0.5, 2.0, mode=0), s.test_occlusions(rays, 0.5, 2.0, mode=1))
     la, lb = s.list_intersections(rays, 0), s.list_intersections(rays, 1)

@@ -4,9 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from pyqsm_b200 import RaycastingScene, synthetic as syn, _lib
 ap = argparse.ArgumentParser(); ap.add_argument("--grid", type=int, default=4000); ap.add_argument("--angles", type=int, default=2)
+ap.add_argument("--mesh", default="c2", choices=["c1", "c2"])
 ap.add_argument("--combos", default="2:12,12,1,2,0,1;2:12,12,1,2,0,0;2:12,12,1,4,0,1;2:8,8,1,2,0,1;2:16,16,1,2,0,1")
 a = ap.parse_args()
-v, t = syn.canopy_mesh(2, 1_000_000)
+v, t = syn.canopy_mesh(2, 1_000_000) if a.mesh == "c2" else syn.qsm_tree_mesh(1)
 s = RaycastingScene(output_device="cuda"); s.add_triangles(v, t); s.commit(); print("stats", s.stats())
 L = _lib.load(); n = a.grid * a.grid
 rays = torch.empty(n, 6, dtype=torch.float32, device="cuda")
@@ -24,7 +25,7 @@ def timeit(reps=3):
     return best
 cur_lm = 2
 for k in range(a.angles):
-    el, az = sweep[(k * 27 + 5) % 64]
+    el, az = sweep[(k * 27 + 5) % 64] if a.mesh == "c2" else (45.0, 135.0 + 30.0 * k)
     g = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), a.grid, a.grid)
     _lib.check(L.qsmrt_gen_parallel_rays(P(rays), a.grid, a.grid, F3(g[0]), F3(g[1]), F3(g[2]), F3(g[3]), st))
     s.set_option("traversal_variant", 1); ms3 = timeit(); ref = (o[0].clone(), o[2].clone(), o[3].clone())
