@@ -22,10 +22,11 @@ struct LbvhBuildArgs {
     int             climb_capacity; // > 0: cap of the climb work list (test hook for its overflow path)
     float           quant_frac;     // 6 grid cells <= this share of the mean leaf diagonal -> 32-byte nodes
     // outputs / scratch (device)
-    uint32_t   *bounds_ord;         // [6]
-    BuildParams *params;
-    uint64_t   *keys, *keys_tmp;    // [T]
-    uint32_t   *order, *order_tmp;  // [T]
+    const BuildParams *params_host; // finished on the host (lbvh_finalize_params) from the geometries' bounds
+    BuildParams *params;            // device copy; the build adds leaf_diag_sum / use_q
+    uint64_t   *keys, *keys_tmp;    // [T]  the sorted arrays end up in (keys, order) or, when *result_in_tmp, in
+    uint32_t   *order, *order_tmp;  // [T]  (keys_tmp, order_tmp): the caller keeps that pair and recycles the other
+    int        *result_in_tmp;
     uint32_t   *sort_scratch;       // lbvh_sort_scratch_bytes(T)
     BNode      *bnodes;             // [2T-1] hand-over boxes of the global phase; the complete binary tree iff keep_bnodes
     int         keep_bnodes;
@@ -42,5 +43,9 @@ struct LbvhBuildArgs {
 size_t lbvh_sort_scratch_bytes(uint64_t n);
 size_t lbvh_climb_bytes(uint64_t n);
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
-                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant);
+                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant, bool hist_done,
+                    int *result_in_tmp);
+void lbvh_finalize_params(const float lo[3], const float hi[3], BuildParams *out);
+int lbvh_geometry_stats(const float *verts, uint64_t V, const uint32_t *idx, uint64_t T, uint32_t *out7_dev, float lo[3], float hi[3],
+                        uint32_t *max_index, cudaStream_t st);
 int lbvh_build(const LbvhBuildArgs &args, cudaStream_t st);

@@ -8,6 +8,8 @@
 // The key/ordering/topology arithmetic mirrors oracle/qsmrt_oracle.c
 // (orc_commit) so the builder can be checked bit-for-bit on the CPU.
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include "common.cuh"
 #include "build.h"
 
@@ -18,10 +20,6 @@ __device__ __forceinline__ uint32_t f2ord(float f) {
     uint32_t u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__device__ __forceinline__ float ord2f(uint32_t u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-}
-
 __device__ __forceinline__ void tri_bounds(const float *__restrict__ verts, const uint32_t *__restrict__ idx,
                                            uint64_t t, float lo[3], float hi[3])
 {
@@ -34,23 +32,27 @@ __device__ __forceinline__ void tri_bounds(const float *__restrict__ verts, cons
     }
 }
 
-__global__ void k_init_bounds(uint32_t *ob)
-{
-    if (threadIdx.x < 3) ob[threadIdx.x] = 0xFFFFFFFFu;        // running min
-    else if (threadIdx.x < 6) ob[threadIdx.x] = 0u;            // running max
-}
-
+// Registration-time statistics of one geometry (qsmrt_add_triangles): the largest vertex index (Embree would read
+// out of bounds; we reject) and the bounds over the vertices its triangles reference, in one pass over the index
+// array.  out[0..2] running min, out[3..5] running max (ordered-uint encoding), out[6] largest index.  The commit
+// then only combines the geometries' bounds on the host: no bounds kernels in the build.
 __global__ void __launch_bounds__(256)
-k_scene_bounds(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n, uint32_t *ob)
+k_geometry_stats(const float *__restrict__ verts, uint64_t nverts, const uint32_t *__restrict__ idx, uint64_t n, uint32_t *out)
 {
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-    // unrolled: the index -> vertex gathers of four triangles are in flight together (the loop is latency bound)
+    uint32_t mx = 0;
 #pragma unroll 4
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
-        float l[3], h[3];
-        tri_bounds(verts, idx, t, l, h);
+        const uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
+        mx = max(mx, max(i0, max(i1, i2)));
+        if (i0 < nverts && i1 < nverts && i2 < nverts) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], l[a]); hi[a] = fmaxf(hi[a], h[a]); }
+            for (int a = 0; a < 3; ++a) {
+                const float p0 = verts[3ull * i0 + a], p1 = verts[3ull * i1 + a], p2 = verts[3ull * i2 + a];
+                lo[a] = fminf(lo[a], fminf(p0, fminf(p1, p2)));
+                hi[a] = fmaxf(hi[a], fmaxf(p0, fmaxf(p1, p2)));
+            }
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -58,44 +60,18 @@ k_scene_bounds(const float *__restrict__ verts, const uint32_t *__restrict__ idx
             lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
         }
-    // one set of global atomics per block, not per warp (9472 warps x 6 atomics on six addresses at 2M triangles)
-    __shared__ uint32_t sb[6];
-    if (threadIdx.x < 3) sb[threadIdx.x] = 0xFFFFFFFFu; else if (threadIdx.x < 6) sb[threadIdx.x] = 0u;
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    __shared__ uint32_t sb[7];
+    if (threadIdx.x < 3) sb[threadIdx.x] = 0xFFFFFFFFu; else if (threadIdx.x < 7) sb[threadIdx.x] = 0u;
     __syncthreads();
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            atomicMin(&sb[a], f2ord(lo[a]));
-            atomicMax(&sb[3 + a], f2ord(hi[a]));
-        }
+        for (int a = 0; a < 3; ++a) { atomicMin(&sb[a], f2ord(lo[a])); atomicMax(&sb[3 + a], f2ord(hi[a])); }
+        atomicMax(&sb[6], mx);
     }
     __syncthreads();
-    if (threadIdx.x < 3) atomicMin(&ob[threadIdx.x], sb[threadIdx.x]);
-    else if (threadIdx.x < 6) atomicMax(&ob[threadIdx.x], sb[threadIdx.x]);
-}
-
-__global__ void k_finalize_bounds(const uint32_t *ob, BuildParams *bp)
-{
-    if (threadIdx.x != 0) return;
-    float m = 0.0f;
-    for (int a = 0; a < 3; ++a) {
-        float lo = ord2f(ob[a]), hi = ord2f(ob[3 + a]);
-        float ext = __fsub_rn(hi, lo);
-        bp->slo[a] = lo; bp->shi[a] = hi;
-        bp->scale[a] = ext > 0.0f ? __fdiv_rn(2097152.0f, ext) : 0.0f;
-        m = fmaxf(m, fabsf(lo)); m = fmaxf(m, fabsf(hi)); m = fmaxf(m, ext);
-    }
-    float pad = __fmul_rn(m, 7.62939453125e-06f);   // 2^-17, see DESIGN.md "box padding"
-    bp->pad = pad > 0.0f ? pad : 1e-30f;
-    // quantisation grid: padded bounds plus a 32-cell margin so the +-3-cell widening never clamps
-    for (int a = 0; a < 3; ++a) {
-        float ext = bp->shi[a] - bp->slo[a];
-        float e = bp->pad + ext * 4.8828125e-04f;       // 2^-11
-        bp->glo[a] = bp->slo[a] - e;
-        bp->cell[a] = (ext + 2.0f * e) / 65535.0f;
-        bp->inv_cell[a] = 1.0f / bp->cell[a];
-    }
-    bp->leaf_diag_sum = 0.0f;
+    if (threadIdx.x < 3) atomicMin(&out[threadIdx.x], sb[threadIdx.x]);
+    else if (threadIdx.x < 7) atomicMax(&out[threadIdx.x], sb[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------- Morton
@@ -110,11 +86,16 @@ __device__ __forceinline__ uint64_t spread21(uint32_t x)
     return v;
 }
 
+// Morton keys + (fused) the digit histograms of all radix passes: the key is histogrammed as it is produced, which
+// saves the separate histogram kernel and its re-read of the keys (shift0 / npass as in the sort; ghist zeroed).
 __global__ void __launch_bounds__(256)
 k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n,
-         BuildParams *__restrict__ bp, uint64_t *__restrict__ keys, uint32_t *__restrict__ order)
+         BuildParams *__restrict__ bp, uint64_t *__restrict__ keys, uint32_t *__restrict__ order,
+         uint32_t *__restrict__ ghist /* [npass][256], may be null */, int shift0, int npass)
 {
     __shared__ float wsum[8];
+    __shared__ uint32_t h[8][256];
+    if (ghist) { for (int i = threadIdx.x; i < npass * 256; i += 256) (&h[0][0])[i] = 0; __syncthreads(); }
     const float pad = bp->pad;
     float diag = 0.0f;
 #pragma unroll 2
@@ -129,8 +110,14 @@ k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint
             f = fminf(fmaxf(f, 0.0f), 2097151.0f);
             q[a] = (uint32_t)f;
         }
-        keys[t] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+        const uint64_t key = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+        keys[t] = key;
         order[t] = (uint32_t)t;
+        if (ghist) {
+            const uint64_t k = key >> shift0;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) if (p < npass) atomicAdd(&h[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
+        }
         // diagonal of the padded leaf box, as k_leaves_refit_emit will write it
         float dx = __fadd_rn(hi[0], pad) - __fsub_rn(lo[0], pad), dy = __fadd_rn(hi[1], pad) - __fsub_rn(lo[1], pad),
               dz = __fadd_rn(hi[2], pad) - __fsub_rn(lo[2], pad);
@@ -146,6 +133,8 @@ k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint
         for (int k = 0; k < 8; ++k) s += wsum[k];
         atomicAdd(&bp->leaf_diag_sum, s);
     }
+    if (ghist)      // wsum's barrier above ordered the shared-memory atomics of all warps
+        for (int i = threadIdx.x; i < npass * 256; i += 256) { const uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
 }
 
 // ------------------------------------------------------------ radix sort
@@ -294,31 +283,20 @@ constexpr int OS_ITEMS = 12;                         // keys per thread
 constexpr int OS_CTAS = 5;                           // resident CTAs per SM the kernel is shaped for (registers <= 51, shared <= 45.6 KB)
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;       // 3072 keys: 36 KB staged + 8 KB counters -> 4 CTAs / SM
 
-__global__ void __launch_bounds__(256)
-k_os_histogram(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ ghist /* [8][256] */, int shift0, int npass)
-{
-    __shared__ uint32_t h[8][256];
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
-    __syncthreads();
-    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
-        uint64_t k = keys[i] >> shift0;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) if (p < npass) atomicAdd(&h[p][(uint32_t)(k >> (8 * p)) & 0xFFu], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npass * 256; i += 256) { uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
-}
-
-// After the passes over the top 40 bits: order every run of keys that agree in those bits by (whole key, index) --
+// After the passes over the top 32 / 40 bits: order every run of keys that agree in those bits by (whole key, index) --
 // exactly what the three skipped low passes of the stable sort would have produced -- while copying to the
 // final buffers.  Runs are short (two triangles of one leaf, duplicates); a run longer than SORT_MAX_RUN raises
 // *overflow and the host repeats the build with all eight passes.
-constexpr int SORT_TOP_SHIFT = 23;          // 63-bit keys: passes at bits 23, 31, 39, 47, 55
 constexpr int SORT_MAX_RUN = 64;
+// passes over the top bits of the 63-bit keys: 5 (bits 23 .. 62) in general, 4 (bits 31 .. 62) for scenes of up to
+// 4M triangles, whose keys are almost all distinct in their top 32 bits already -- the fix-up orders what is left
+// either way, and a run of more than SORT_MAX_RUN keys falls back to the full 8-pass sort
+inline int sort_passes(uint64_t n) { return n <= (4ull << 20) ? 4 : 5; }
+inline int sort_shift0(uint64_t n) { return 63 - 8 * sort_passes(n); }
 
 __global__ void __launch_bounds__(256)
 k_sort_fixup(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
-             uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, int64_t n, unsigned long long *overflow)
+             uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, int64_t n, unsigned long long *overflow, int SORT_TOP_SHIFT)
 {
     const int64_t i = blockIdx.x * 256ll + threadIdx.x;
     if (i >= n) return;
@@ -903,33 +881,42 @@ size_t lbvh_climb_items(uint64_t n) { return (size_t)(n / 4 + 1024); }
 size_t lbvh_climb_bytes(uint64_t n) { return lbvh_climb_items(n) * sizeof(ClimbItem); }
 
 
-int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
-                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant)
+size_t lbvh_sort_clear_bytes(uint64_t n)
 {
+    const uint64_t os_tiles = (n + OS_TILE - 1) / OS_TILE;
+    return (size_t)(8ull * os_tiles * 256 + 8 * 256 + 8) * sizeof(uint32_t);
+}
+
+// keys / vals sorted by key (stable).  `overflow` non-null: only the top bits are sorted (sort_passes(n) passes) and
+// k_sort_fixup orders the short runs that agree in them -- fewer trips of 12 B per key through HBM for the same final
+// order.  hist_done: the caller zeroed the scratch and k_morton already filled the digit histograms.
+int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
+                    uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant, bool hist_done,
+                    int *result_in_tmp)
+{
+    *result_in_tmp = 0;
     if (n == 0) return 0;
     uint32_t ntiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
     uint32_t *tile_hist = scratch, *digit_tot = scratch + (uint64_t)ntiles * 256;
     uint64_t *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     if (sort_variant == 1) {
+        if (!hist_done) { qsmrt_set_error("onesweep sort needs the histograms of k_morton"); return 1; }
         const uint32_t os_tiles = (uint32_t)((n + OS_TILE - 1) / OS_TILE);
         // OS_CTAS x 45 KB only fit with the largest shared-memory split (a per-device function attribute; setting it is idempotent)
         CUDA_TRY(cudaFuncSetAttribute(k_os_pass, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         uint32_t *status = scratch, *ghist = scratch + 8ull * os_tiles * 256, *counters = ghist + 8 * 256;
-        // With `overflow`: five passes over the top 40 bits, then k_sort_fixup orders the (short) runs of keys
-        // that agree in them -- three fewer trips of 12 B per key through HBM for the same final order.
-        const int shift0 = overflow ? SORT_TOP_SHIFT : 0, npass = overflow ? 5 : 8;
-        // one clear for the look-back status of all passes, the histograms and the tile counters
-        CUDA_TRY(cudaMemsetAsync(scratch, 0, (8ull * os_tiles * 256 + 8 * 256 + 8) * sizeof(uint32_t), st));
-        k_os_histogram<<<(unsigned)std::min<uint64_t>((n + 4095) / 4096, 148 * 8), 256, 0, st>>>(keys, n, ghist, shift0, npass);
+        const int shift0 = overflow ? sort_shift0(n) : 0, npass = overflow ? sort_passes(n) : 8;
         for (int pass = 0; pass < npass; ++pass) {
             k_os_pass<<<os_tiles, OS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift0 + pass * 8, ghist + pass * 256,
                                                        status + (uint64_t)pass * os_tiles * 256, counters + pass);
             uint64_t *tk = kin; kin = kout; kout = tk;
             uint32_t *tv = vin; vin = vout; vout = tv;
         }
-        if (overflow)       // five passes: the data sits in the tmp buffers, the fix-up brings it home
-            k_sort_fixup<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, vin, kout, vout, (int64_t)n, overflow);
+        if (overflow) {         // the fix-up copies while it orders: the result is in whichever buffer pair it wrote
+            k_sort_fixup<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, vin, kout, vout, (int64_t)n, overflow, shift0);
+            *result_in_tmp = kout == keys_tmp;
+        } else *result_in_tmp = kin == keys_tmp;
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -945,19 +932,79 @@ int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t
     return 0;   // 8 passes: sorted data is back in keys / vals
 }
 
+// Scene bounds -> Morton scale, box padding and the 16-bit grid of the quantised nodes.  Host code: the bounds come
+// from the geometries' registration-time statistics.  Plain IEEE single arithmetic, the same operations in the same
+// order as oracle/qsmrt_oracle.c::orc_commit (the builder parity tests compare keys and padding bit for bit).
+void lbvh_finalize_params(const float lo[3], const float hi[3], BuildParams *bp)
+{
+    memset(bp, 0, sizeof(*bp));
+    volatile float m = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+        volatile float ext = hi[a] - lo[a];
+        bp->slo[a] = lo[a]; bp->shi[a] = hi[a];
+        bp->scale[a] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
+        m = fmaxf(m, fabsf(lo[a])); m = fmaxf(m, fabsf(hi[a])); m = fmaxf(m, ext);
+    }
+    volatile float pad = m * 7.62939453125e-06f;    // 2^-17, see DESIGN.md "box padding"
+    bp->pad = pad > 0.0f ? pad : 1e-30f;
+    // quantisation grid: padded bounds plus a 32-cell margin so the +-3-cell widening never clamps
+    for (int a = 0; a < 3; ++a) {
+        volatile float ext = bp->shi[a] - bp->slo[a];
+        volatile float w = ext * 4.8828125e-04f;    // 2^-11 (volatile: no fused multiply-add on the host either)
+        volatile float e = bp->pad + w;
+        bp->glo[a] = bp->slo[a] - e;
+        volatile float two_e = 2.0f * e;
+        bp->cell[a] = (ext + two_e) / 65535.0f;
+        bp->inv_cell[a] = 1.0f / bp->cell[a];
+    }
+    bp->leaf_diag_sum = 0.0f;
+}
+
+// out7_dev: 7 words of device scratch; out_host[7] receives lo.xyz, hi.xyz (as floats) and the largest index
+int lbvh_geometry_stats(const float *verts, uint64_t V, const uint32_t *idx, uint64_t T, uint32_t *out7_dev, float lo[3], float hi[3],
+                        uint32_t *max_index, cudaStream_t st)
+{
+    const uint32_t init[7] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u };
+    uint32_t h[7];
+    CUDA_TRY(cudaMemcpyAsync(out7_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (T) k_geometry_stats<<<(unsigned)std::min<uint64_t>((T + 255) / 256, 148 * 8), 256, 0, st>>>(verts, V, idx, T, out7_dev);
+    CUDA_TRY(cudaMemcpyAsync(h, out7_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int a = 0; a < 3; ++a) {
+        const uint32_t ul = h[a], uh = h[3 + a];
+        const uint32_t bl = (ul & 0x80000000u) ? (ul & 0x7FFFFFFFu) : ~ul, bh = (uh & 0x80000000u) ? (uh & 0x7FFFFFFFu) : ~uh;
+        memcpy(&lo[a], &bl, 4); memcpy(&hi[a], &bh, 4);
+    }
+    *max_index = h[6];
+    return 0;
+}
+
 int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
 {
     const uint64_t n = A.ntris;
     const int B = 256;
     const unsigned gN = (unsigned)((n + B - 1) / B);
     CUDA_TRY(cudaMemsetAsync(A.counters, 0, 5 * sizeof(unsigned long long), st));
-    k_init_bounds<<<1, 32, 0, st>>>(A.bounds_ord);
-    k_scene_bounds<<<min(gN, 148u * 8u), B, 0, st>>>(A.verts, A.idx, n, A.bounds_ord);
-    k_finalize_bounds<<<1, 32, 0, st>>>(A.bounds_ord, A.params);
-    k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order);
+    // the scene bounds were combined on the host from the geometries' registration-time statistics: upload the
+    // finished parameters (72 bytes), clear the sort's look-back status / histograms, and go straight to the keys
+    CUDA_TRY(cudaMemcpyAsync(A.params, A.params_host, sizeof(BuildParams), cudaMemcpyHostToDevice, st));
+    const bool onesweep = A.sort_variant == 1;
+    const bool top_only = !A.full_sort;
+    uint32_t *ghist = nullptr;
+    if (onesweep) {
+        CUDA_TRY(cudaMemsetAsync(A.sort_scratch, 0, lbvh_sort_clear_bytes(n), st));
+        ghist = A.sort_scratch + 8ull * ((n + OS_TILE - 1) / OS_TILE) * 256;
+    }
+    k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order, ghist,
+                                                 top_only ? sort_shift0(n) : 0, top_only ? sort_passes(n) : 8);
     CUDA_TRY(cudaGetLastError());
     if (A.ev_sort0) CUDA_TRY(cudaEventRecord(A.ev_sort0, st));
-    if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st, A.full_sort ? nullptr : A.counters + 4, A.sort_variant)) return 1;
+    int in_tmp = 0;
+    if (lbvh_radix_sort(A.keys, A.keys_tmp, A.order, A.order_tmp, n, A.sort_scratch, st, top_only ? A.counters + 4 : nullptr,
+                        A.sort_variant, onesweep, &in_tmp)) return 1;
+    if (A.result_in_tmp) *A.result_in_tmp = in_tmp;
+    const uint64_t *keys = in_tmp ? A.keys_tmp : A.keys;        // the caller keeps whichever pair holds the sorted arrays
+    const uint32_t *order = in_tmp ? A.order_tmp : A.order;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
     if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
     const int keep = (A.keep_bnodes || n == 1) ? 1 : 0;
@@ -966,7 +1013,7 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     unsigned *work_count = reinterpret_cast<unsigned *>(A.counters + 3);
     ClimbItem *work = reinterpret_cast<ClimbItem *>(A.climb_work);
     k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(
-        A.verts, A.idx, (int64_t)n, A.keys, A.order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
+        A.verts, A.idx, (int64_t)n, keys, order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
         A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap, A.quant_frac);
     k_hierarchy_climb<<<std::min((work_cap + CL_BLOCK - 1) / CL_BLOCK, 148u * 32u), CL_BLOCK, 0, st>>>(
         (int64_t)n, A.params, A.bnodes, A.flags, A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap);

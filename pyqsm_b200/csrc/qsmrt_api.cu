@@ -35,6 +35,7 @@ void qsmrt_set_error(const char *fmt, ...)
 struct Geometry {
     float *verts = nullptr; uint32_t *idx = nullptr;
     uint64_t V = 0, T = 0;
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };   // over the vertices its triangles reference
 };
 
 struct HostPipe {            // device staging of the *_host entry points: rays in, up to 32 B/ray of results out
@@ -199,7 +200,7 @@ k_read_sweep(const uint4 *__restrict__ buf, uint64_t n32, uint32_t reps, uint32_
     for (uint32_t r = 0; r < reps; ++r)
         for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n32; i += (uint64_t)gridDim.x * 256ull) {
             uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
-            asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"        // .cg: L2 only, never an L1 hit
                          : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "l"(buf + 2 * i));
             acc ^= w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
         }
@@ -210,14 +211,6 @@ __global__ void k_rebase_idx(const uint32_t *__restrict__ in, uint32_t *__restri
 {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i < n3) out[i] = in[i] + add;
-}
-
-__global__ void k_max_index(const uint32_t *__restrict__ in, uint64_t n3, uint32_t *out)
-{
-    uint32_t m = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n3; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, in[i]);
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 // QSM cylinder records -> triangle mesh with Open3D's create_cylinder topology (axis z, centred, 2 cap centres +
@@ -322,12 +315,12 @@ SceneView view_of(qsmrt_scene *s)
 
 // Scratch of one commit; everything here goes back to the block cache on every exit path.
 struct CommitScratch {
-    uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr, *bounds = nullptr;
+    uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr;
     unsigned long long *flags = nullptr, *counters = nullptr; uint32_t *climb = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, es0 = nullptr, es1 = nullptr;
     ~CommitScratch()
     {
-        dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(bounds); dfree(flags); dfree(counters); dfree(climb);
+        dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(flags); dfree(counters); dfree(climb);
         if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (es0) cudaEventDestroy(es0); if (es1) cudaEventDestroy(es1);
     }
 };
@@ -346,7 +339,7 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
     CUDA_TRY(cudaStreamSynchronize(st));        // goff / voff are locals
     // allocate everything before the timed region
     if (dmalloc(&s->keys, T) || dmalloc(&cs.keys_tmp, T) || dmalloc(&s->order, T) || dmalloc(&cs.order_tmp, T) ||
-        dmalloc(&cs.sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) || dmalloc(&cs.bounds, 8) ||
+        dmalloc(&cs.sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) ||
         dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&cs.flags, T) || dmalloc(&s->tris, T) ||
         dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(T - 1, 1)) ||
         dmalloc(&cs.counters, 5) || dmalloc(&cs.climb, lbvh_climb_bytes(T) / sizeof(uint32_t)))
@@ -365,11 +358,19 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
             if (ge.T) k_rebase_idx<<<(unsigned)((3 * ge.T + 255) / 256), 256, 0, st>>>(ge.idx, s->idx + 3 * goff[g], 3 * ge.T, (uint32_t)voff[g]);
         }
     }
+    // scene bounds = union of the geometries' registration-time bounds (only geometries with triangles count)
+    float slo[3] = { INFINITY, INFINITY, INFINITY }, shi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (const Geometry &ge : s->geoms)
+        if (ge.T) for (int a = 0; a < 3; ++a) { slo[a] = fminf(slo[a], ge.lo[a]); shi[a] = fmaxf(shi[a], ge.hi[a]); }
+    BuildParams bp_host;
+    lbvh_finalize_params(slo, shi, &bp_host);
+    int in_tmp = 0;
     LbvhBuildArgs A{};
+    A.params_host = &bp_host; A.result_in_tmp = &in_tmp;
     A.leaf_max = s->bopt.leaf_max; A.sort_variant = s->bopt.sort_variant; A.climb_capacity = s->bopt.climb_capacity;
     A.quant_frac = s->bopt.quant_frac;
     A.verts = s->verts; A.idx = s->idx; A.ntris = T; A.geom_offsets = s->goff; A.ngeoms = G;
-    A.bounds_ord = cs.bounds; A.params = s->params; A.keys = s->keys; A.keys_tmp = cs.keys_tmp;
+    A.params = s->params; A.keys = s->keys; A.keys_tmp = cs.keys_tmp;
     A.order = s->order; A.order_tmp = cs.order_tmp; A.sort_scratch = cs.sort_scratch;
     A.bnodes = s->bnodes; A.flags = cs.flags; A.keep_bnodes = s->bopt.keep_bnodes ? 1 : 0; A.climb_work = cs.climb;
     A.qnodes = s->qnodes;
@@ -387,6 +388,7 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
         if (!cnt[4]) break;
     }
     s->stats.full_sort = (uint32_t)A.full_sort;
+    if (in_tmp) { std::swap(s->keys, cs.keys_tmp); std::swap(s->order, cs.order_tmp); }     // keep the pair that holds the sorted arrays
     CUDA_TRY(cudaEventElapsedTime(&s->stats.build_ms, cs.e0, cs.e1));
     CUDA_TRY(cudaEventElapsedTime(&s->stats.sort_ms, cs.es0, cs.es1));
     BuildParams bp;
@@ -556,11 +558,11 @@ int qsmrt_add_triangles(qsmrt_scene *s, const float *verts, uint64_t V, const ui
         const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         if (V) CUDA_TRY(cudaMemcpy(g.verts, verts, 3 * V * sizeof(float), kind));
         if (T) CUDA_TRY(cudaMemcpy(g.idx, idx, 3 * T * sizeof(uint32_t), kind));
-        if (T) {        // Embree would read out of bounds; reject instead
-            if (dmalloc(&d_max, 1)) return 1;
-            CUDA_TRY(cudaMemset(d_max, 0, sizeof(uint32_t)));
-            k_max_index<<<(unsigned)std::min<uint64_t>((3 * T + 255) / 256, 1184), 256>>>(g.idx, 3 * T, d_max);
-            CUDA_TRY(cudaMemcpy(&maxi, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (T) {
+            // one pass over the index array: the largest index (Embree would read out of bounds; reject instead,
+            // SURVEY.md 8b) and the bounds of the referenced vertices, which the commit only has to combine
+            if (dmalloc(&d_max, 8)) return 1;
+            if (lbvh_geometry_stats(g.verts, V, g.idx, T, d_max, g.lo, g.hi, &maxi, nullptr)) return 1;
             if (maxi >= V) { qsmrt_set_error("triangle index %u out of range (%llu vertices)", maxi, (unsigned long long)V); return 1; }
         }
         return 0;
@@ -599,6 +601,10 @@ int qsmrt_add_cylinders(qsmrt_scene *s, const float *records, uint64_t n, uint32
         k_cylinders<<<(unsigned)n, 128>>>(rec, n, resolution, split, g.verts, g.idx);
         cudaError_t e = cudaDeviceSynchronize();
         dfree(rec_dev);
+        uint32_t *d_stats = nullptr, maxi = 0;
+        if (e == cudaSuccess && (dmalloc(&d_stats, 8) || lbvh_geometry_stats(g.verts, g.V, g.idx, g.T, d_stats, g.lo, g.hi, &maxi, nullptr)))
+            e = cudaErrorUnknown;
+        dfree(d_stats);
         if (e != cudaSuccess) { dfree(g.verts); dfree(g.idx); FAIL("cylinder generation failed: %s", cudaGetErrorString(e)); }
     }
     if (s->committed || s->verts) free_build(s);
@@ -681,6 +687,7 @@ int qsmrt_scene_set_option(qsmrt_scene *s, int key, double value)
     case QSMRT_OPT_COUNTERS: t.counters = iv != 0; break;
     case QSMRT_OPT_NODE_PATH: if (iv < 0 || iv > 2) FAIL("node path must be 0, 1 or 2"); t.node_path = iv; break;
     case QSMRT_OPT_CP_WARP_MAX: t.cp_warp_max = std::max(iv, 0); break;
+    case QSMRT_OPT_CTAS_PER_SM: t.ctas_per_sm = std::max(iv, 0); break;
     default: FAIL("unknown option %d", key);
     }
     if (rebuild && s->committed) { SCENE_ENTER(s); free_build(s); }     // the next query builds with the new option
@@ -705,6 +712,7 @@ int qsmrt_scene_get_option(qsmrt_scene *s, int key, double *value)
     case QSMRT_OPT_COUNTERS: *value = t.counters; break;
     case QSMRT_OPT_NODE_PATH: *value = t.node_path; break;
     case QSMRT_OPT_CP_WARP_MAX: *value = t.cp_warp_max; break;
+    case QSMRT_OPT_CTAS_PER_SM: *value = t.ctas_per_sm; break;
     default: FAIL("unknown option %d", key);
     }
     return 0;
@@ -1147,6 +1155,12 @@ int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out)
             Geometry g; g.V = vt[0]; g.T = vt[1];
             if (dmalloc(&g.verts, 3 * g.V) || dmalloc(&g.idx, 3 * g.T) ||
                 io.get(g.verts, 3 * g.V * sizeof(float)) || io.get(g.idx, 3 * g.T * sizeof(uint32_t))) { dfree(g.verts); dfree(g.idx); return 1; }
+            uint32_t *d_stats = nullptr, maxi = 0;
+            if (g.T && (dmalloc(&d_stats, 8) || lbvh_geometry_stats(g.verts, g.V, g.idx, g.T, d_stats, g.lo, g.hi, &maxi, nullptr) || maxi >= g.V)) {
+                dfree(d_stats); dfree(g.verts); dfree(g.idx);
+                FAIL("corrupt scene file (geometry %llu)", (unsigned long long)gi);
+            }
+            dfree(d_stats);
             s->geoms.push_back(g);
             T += g.T; V += g.V;
         }

@@ -215,7 +215,10 @@ k_trace5(const TraceArgs A)
     bool have_ray = false, exhausted = false;
     int cur = TR_SENTINEL;
     int *sptr = sbase;                              // next free stack slot (register; stride TR_BLOCK ints)
-    uint32_t tri_i = 0, tri_end = 0;
+    // the leaf a lane has parked for the next triangle phase, as its (negative) child reference ~(first << 2 | left - 1);
+    // 0 = none (node 0 is the root, never a leaf).  One register and a two-instruction park: the node step used to
+    // decode it into a first / end pair with four more ALU-pipe instructions per step, the pipe this loop is bound by.
+    int lcur = 0;
     unsigned n_node = 0, n_tri = 0;
     float *const tset = reinterpret_cast<float *>(sstack + A.depth * TR_BLOCK) + threadIdx.x;      // MODE 2
     uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + CNT_SET) * TR_BLOCK) + threadIdx.x;
@@ -223,12 +226,13 @@ k_trace5(const TraceArgs A)
     long long lbase = 0;                                        // MODE 6: first output slot of this lane's ray
     uint32_t snx = 0x7610u, sny = 0x7610u, snz = 0x7610u;       // QUANT: per-axis "near plane" byte selectors
 
-#define PARK_LEAF5() do { uint32_t ref_ = (uint32_t)~cur; tri_i = ref_ >> 2; tri_end = tri_i + (ref_ & 3u) + 1u; \
-                          sptr -= TR_BLOCK; cur = *sptr; } while (0)
+#define PARK_LEAF5() do { lcur = cur; sptr -= TR_BLOCK; cur = *sptr; } while (0)
+    // after a triangle of the parked leaf has been tested: the next one (reference - 3: first + 1, left - 1), or done
+#define NEXT_TRI5() do { if (((uint32_t)~lcur & 3u) != 0u) lcur -= 3; else { lcur = 0; if (cur < 0) PARK_LEAF5(); } } while (0)
 
     for (;;) {
         // ---- retire finished rays, refill idle lanes
-        const bool idle = (cur == TR_SENTINEL) && (tri_i >= tri_end);
+        const bool idle = (cur == TR_SENTINEL) && (lcur == 0);
         const unsigned im = __ballot_sync(FULL, idle);
         if (im == FULL || (!exhausted && __popc(im) >= A.refill)) {
             if (MODE == 3 || MODE == 4) {
@@ -317,7 +321,7 @@ k_trace5(const TraceArgs A)
                         best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
                         sbase[0] = TR_SENTINEL; sptr = sbase + TR_BLOCK;
                         cur = A.sc.ntris ? 0 : TR_SENTINEL;
-                        tri_i = tri_end = 0;
+                        lcur = 0;
                     }
                 }
                 continue;
@@ -326,7 +330,7 @@ k_trace5(const TraceArgs A)
         // ---- node phase
         for (;;) {
             const bool inner = (unsigned)cur < (unsigned)TR_SENTINEL;
-            const bool parked = tri_i < tri_end;
+            const bool parked = lcur != 0;
             const unsigned mw = __ballot_sync(FULL, inner && !parked);
             if (mw == 0u) break;
             if (__popc(mw) < A.want && __popc(__ballot_sync(FULL, parked)) >= A.tri_min) break;
@@ -348,7 +352,7 @@ k_trace5(const TraceArgs A)
 #pragma unroll
             for (int rep = 0; rep < NodeSteps<MODE>::value; ++rep) {
             const bool in_ = (unsigned)cur < (unsigned)TR_SENTINEL;
-            const bool pk_ = tri_i < tri_end;
+            const bool pk_ = lcur != 0;
             if (in_) {
                 int c0, c1;
                 float t0, t1;
@@ -402,14 +406,15 @@ k_trace5(const TraceArgs A)
         }
         // ---- triangle phase
         for (;;) {
-            const bool has = tri_i < tri_end;
+            const bool has = lcur != 0;
             const unsigned mh = __ballot_sync(FULL, has);
             if (mh == 0u) break;
             if (__popc(mh) < A.tri_min && __any_sync(FULL, (unsigned)cur < (unsigned)TR_SENTINEL && !has)) break;
             if (COUNTERS && lane == 0) { atomicAdd(&A.stats[7], 1ull); atomicAdd(&A.stats[8], (unsigned long long)__popc(mh)); }
 #pragma unroll
             for (int rep = 0; rep < TR_TRI_STEPS; ++rep)        // most leaves hold two triangles: one vote per leaf
-            if (tri_i < tri_end) {
+            if (lcur != 0) {
+                const uint32_t tri_i = (uint32_t)~lcur >> 2;
                 float4 p0, p1, p2;
                 load_tri(tris, tri_i, p0, p1, p2);
                 MtHit h;
@@ -421,14 +426,12 @@ k_trace5(const TraceArgs A)
                         bool better = (tt < best_t) | ((tt == best_t) & ((pg < best_geom) | ((pg == best_geom) & (pp < best_prim))));
                         if (better) { best_t = tt; best_geom = pg; best_prim = pp; best_tri = tri_i; }
                     }
-                    ++tri_i;
-                    if (tri_i == tri_end && cur < 0) PARK_LEAF5();
+                    NEXT_TRI5();
                 } else if (ANYHIT) {
                     if (mt_test(p0, p1, p2, r.O, r.D, A.tnear, A.tfar, h)) {
-                        best_prim = 0u; cur = TR_SENTINEL; tri_i = tri_end;       // occluded: drop the rest
+                        best_prim = 0u; cur = TR_SENTINEL; lcur = 0;              // occluded: drop the rest
                     } else {
-                        ++tri_i;
-                        if (tri_i == tri_end && cur < 0) PARK_LEAF5();
+                        NEXT_TRI5();
                     }
                 } else {
                     if (mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
@@ -439,7 +442,7 @@ k_trace5(const TraceArgs A)
                             if (tset[q * TR_BLOCK] == tt && (!A.multi_geom || gset[q * TR_BLOCK] == pg)) at = q;
                         if (at < 0) {
                             if (cnt < CNT_SET) { tset[cnt * TR_BLOCK] = tt; if (A.multi_geom) gset[cnt * TR_BLOCK] = pg; at = cnt; ++cnt; }
-                            else { overflow = true; cur = TR_SENTINEL; tri_i = tri_end; }   // the fix-up kernel recounts this ray
+                            else { overflow = true; cur = TR_SENTINEL; lcur = 0; }          // the fix-up kernel recounts this ray
                             if (MODE == 6 && !overflow) A.l_prim[lbase + at] = QSMRT_INVALID;   // so the first record always wins below
                         }
                         if (MODE == 6 && at >= 0) {
@@ -451,8 +454,7 @@ k_trace5(const TraceArgs A)
                         }
                     }
                     if (!overflow) {
-                        ++tri_i;
-                        if (tri_i == tri_end && cur < 0) PARK_LEAF5();
+                        NEXT_TRI5();
                     }
                 }
             }
@@ -463,6 +465,7 @@ k_trace5(const TraceArgs A)
         if (lane == 0) { atomicAdd(&A.stats[0], (unsigned long long)n_node); atomicAdd(&A.stats[1], (unsigned long long)n_tri); }
     }
 #undef PARK_LEAF5
+#undef NEXT_TRI5
 }
 
 // materialise the hemisphere rays of SRC 2 (tests and small batches): rays[n_points * n_dirs][6]

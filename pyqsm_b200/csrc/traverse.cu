@@ -135,8 +135,12 @@ __device__ __forceinline__ bool ray_index(uint64_t N, uint32_t row_len, uint64_t
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = blockIdx.x * (uint64_t)(TR_BLOCK / 32) + (threadIdx.x >> 5);
     const uint32_t tiles_x = (row_len + 7u) >> 3;
-    const uint64_t ty = warp / tiles_x;
+    uint64_t ty = warp / tiles_x;
     const uint32_t tx = (uint32_t)(warp - ty * tiles_x);
+    const uint64_t tile_rows = (N / row_len + 3u) >> 2;
+    if (ty >= tile_rows) return false;
+    // blocks are scheduled in index order: the middle rows of the grid first, the (cheap) edge rows last -- see centre_out
+    ty = (ty & 1u) ? (tile_rows >> 1) - 1u - (ty >> 1) : (tile_rows >> 1) + (ty >> 1);
     const uint32_t x = tx * 8u + (lane & 7u);
     const uint64_t y = ty * 4u + (lane >> 3);
     i = y * row_len + x;
@@ -201,6 +205,17 @@ k_cast_rays(SceneView sc, const float *__restrict__ rays, uint64_t N, uint32_t r
 // Evidence for its shape (profiles/README.md): the per-thread loop below spends half
 // its issue slots in leaf code with ~2.3 of 32 lanes active, and idle lanes of
 // finished rays wait for the slowest ray of the warp.
+// Rows of tiles are handed out from the middle of the grid outwards (mid, mid - 1, mid + 1, ...): ray grids are laid
+// over the scene's bounding box, so the long rays -- through the crown of a tree, the bulk of a canopy -- sit in
+// the middle rows and the cheap ones (misses near the box edge) at the top and bottom.  Row-major order left the
+// heaviest rays to start late and finish alone: on the C1 tree (1M rays) the average SM was busy 56 % of the
+// launch (ncu sm__cycles_active avg / max, profiles/r02_c1_tail.txt).  tile_rows = number of tile rows.
+__device__ __forceinline__ uint64_t centre_out(uint64_t k, uint64_t tile_rows)
+{
+    const uint64_t mid = tile_rows >> 1;
+    return (k & 1u) ? mid - 1u - (k >> 1) : mid + (k >> 1);
+}
+
 __device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uint32_t row_len, uint64_t &i, uint32_t &x, uint64_t &y)
 {
     if (row_len == 0) { i = slot; return slot < N; }
@@ -208,8 +223,10 @@ __device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uin
     const uint64_t tile = slot >> 5;
     const uint32_t tiles_x = (row_len + 7u) >> 3;
     // 32-bit division whenever the tile number fits (batches below 2^37 rays): the 64-bit one is ~100 instructions
-    const uint64_t ty = (tile >> 32) == 0 ? (uint64_t)((uint32_t)tile / tiles_x) : tile / tiles_x;
+    uint64_t ty = (tile >> 32) == 0 ? (uint64_t)((uint32_t)tile / tiles_x) : tile / tiles_x;
     const uint32_t tx = (uint32_t)(tile - ty * tiles_x);
+    const uint64_t rows = (N >> 32) == 0 ? (uint64_t)((uint32_t)N / row_len) : N / row_len;
+    ty = centre_out(ty, (rows + 3u) >> 2);
     x = tx * 8u + (lane & 7u);
     y = ty * 4u + (lane >> 3);
     i = y * row_len + x;
@@ -866,6 +883,7 @@ int launch_trace5_q(TrvState &ts, TraceArgs &a, size_t smem, cudaStream_t st)
         ts.occ.push_back(TrvState::Occ{ fn, smem, per_sm });
     }
     if (ts.sms == 0) CUDA_TRY(cudaDeviceGetAttribute(&ts.sms, cudaDevAttrMultiProcessorCount, ts.device));
+    if (ts.opt.ctas_per_sm > 0) per_sm = std::min(per_sm, ts.opt.ctas_per_sm);
     unsigned g = (unsigned)std::min<uint64_t>((uint64_t)per_sm * ts.sms, (a.nslots + TR_BLOCK - 1) / TR_BLOCK);
     k_trace5<MODE, COUNTERS, QUANT><<<g, TR_BLOCK, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());

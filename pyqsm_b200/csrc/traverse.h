@@ -12,6 +12,7 @@ struct TrvOptions {
     int counters = 0;       // 1: cast_rays launches count the node records / triangles they fetch
     int node_path = 0;      // 0 LSU 256-bit loads, 1 TEX, 2 half/half (L1 data-pipe experiment)
     int cp_warp_max = 16384;// closest-point batches up to this size run one warp per query
+    int ctas_per_sm = 0;    // persistent kernel: resident CTAs per SM (0 = as many as fit)
 };
 
 // Per-scene launch state: options, the ring of work cursors of the persistent kernels, the counter buffer and

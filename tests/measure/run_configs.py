@@ -2,7 +2,10 @@
 BASELINE.md section 7 (Mrays/s, canonical bytes per ray, roofline, build ms, CPU oracle Mrays/s, parity).
 Test / measurement infrastructure: uses the oracle as checker and CPU baseline.
 
-    python tests/measure/run_configs.py [c1 c2 c3 c4 c5] > profiles/r01_configs.json
+    python tests/measure/run_configs.py [c1 c2 c3 c4 c5] > profiles/r02_configs.json
+
+Run it under `ncu --metrics ... -k regex:k_trace5` as well to see which resource each configuration's launches
+load (issue slots, ALU pipe, L2, DRAM): profiles/r02_configs_ncu.txt.
 """
 import ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -57,8 +60,8 @@ if "c1" in want:
     t0 = time.perf_counter(); refc = o.count_intersections(rh, 1); cpu_c = time.perf_counter() - t0; cn, ct = o.last_counters
     same = bool(np.array_equal(out[2].cpu().numpy(), ref["primitive_ids"]) and np.array_equal(out[0].cpu().numpy(), ref["t_hit"]) and np.array_equal(cnt.cpu().numpy(), refc))
     b = 24 + 32 + 32 * nn / n + 48 * nt / n; bc = 24 + 4 + 32 * cn / n + 48 * ct / n
-    report(config="C1 cast_rays", triangles=int(t.shape[0]), rays=n, mrays_s=n / ms / 1e3, b_ray=b, roofline_mrays_s=HBM * 1e3 / b, frac=(n / ms / 1e3) / (HBM * 1e3 / b), build_ms=bms, cpu_mrays_s=n / cpu_s / 1e6, cpu_threads=o.num_threads, cpu_build_ms=obms, parity="bit-identical (all 1M rays)" if same else "MISMATCH")
-    report(config="C1 count_intersections", triangles=int(t.shape[0]), rays=n, mrays_s=n / cms / 1e3, b_ray=bc, roofline_mrays_s=HBM * 1e3 / bc, frac=(n / cms / 1e3) / (HBM * 1e3 / bc), cpu_mrays_s=n / cpu_c / 1e6, parity="bit-identical (all 1M rays)" if same else "MISMATCH")
+    report(config="C1 cast_rays", triangles=int(t.shape[0]), rays=n, mrays_s=n / ms / 1e3, b_ray=b, roofline_mrays_s=HBM * 1e3 / b, frac_canonical_hbm=(n / ms / 1e3) / (HBM * 1e3 / b), build_ms=bms, cpu_mrays_s=n / cpu_s / 1e6, cpu_threads=o.num_threads, cpu_build_ms=obms, parity="bit-identical (all 1M rays)" if same else "MISMATCH")
+    report(config="C1 count_intersections", triangles=int(t.shape[0]), rays=n, mrays_s=n / cms / 1e3, b_ray=bc, roofline_mrays_s=HBM * 1e3 / bc, frac_canonical_hbm=(n / cms / 1e3) / (HBM * 1e3 / bc), cpu_mrays_s=n / cpu_c / 1e6, parity="bit-identical (all 1M rays)" if same else "MISMATCH")
     del s, o
 
 if "c2" in want or "c5" in want:
@@ -72,8 +75,8 @@ if "c2" in want:
     ms = gpu_time(lambda: _lib.check(L.qsmrt_cast_rays_2d(s2._h, P(rays), 4000, 4000, *[P(x) for x in out], None)))
     sub = rays[::16].cpu().numpy(); t0 = time.perf_counter(); ref = o2.cast_rays(sub, 1); cpu_s = time.perf_counter() - t0
     same = bool(np.array_equal(out[2][::16].cpu().numpy(), ref["primitive_ids"]) and np.array_equal(out[0][::16].cpu().numpy(), ref["t_hit"]))
-    report(config="C2 cast_rays (one angle, API)", triangles=int(t2.shape[0]), rays=n, mrays_s=n / ms / 1e3, b_ray=cc["b_ray"], roofline_mrays_s=HBM * 1e3 / cc["b_ray"], frac=(n / ms / 1e3) / (HBM * 1e3 / cc["b_ray"]), build_ms=bms2, cpu_mrays_s=len(sub) / cpu_s / 1e6, cpu_threads=o2.num_threads, cpu_build_ms=obms2, parity="bit-identical (1M-ray subsample)" if same else "MISMATCH")
-    report(config="C2 fused sun sweep, 64 angles x 16M rays (wall clock incl. host loop)", rays=r["rays"], mrays_s=r["rays"] / dt / 1e6, seconds=dt, sunlit_rays=int(r["counts"].sum()))
+    report(config="C2 cast_rays (one angle, API)", triangles=int(t2.shape[0]), rays=n, mrays_s=n / ms / 1e3, b_ray=cc["b_ray"], roofline_mrays_s=HBM * 1e3 / cc["b_ray"], frac_canonical_hbm=(n / ms / 1e3) / (HBM * 1e3 / cc["b_ray"]), build_ms=bms2, cpu_mrays_s=len(sub) / cpu_s / 1e6, cpu_threads=o2.num_threads, cpu_build_ms=obms2, parity="bit-identical (1M-ray subsample)" if same else "MISMATCH")
+    report(config="C2 fused sun sweep, 64 angles x 16M rays (one launch, wall clock)", rays=r["rays"], mrays_s=r["rays"] / dt / 1e6, seconds=dt, sunlit_rays=int(r["counts"].sum()))
     del rays, out
 
 if "c5" in want:
@@ -82,13 +85,11 @@ if "c5" in want:
     pts, nd = torch.from_numpy(p0).cuda(), torch.from_numpy(nrm.astype(np.float32)).cuda()
     env.sky_gap_fraction(s2, pts[:1000], nd[:1000], n_dirs=10); torch.cuda.synchronize()
     t0 = time.perf_counter(); gap = env.sky_gap_fraction(s2, pts, nd, n_dirs=1000, seed=5); torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    idx = torch.arange(0, pts.shape[0], 1000, device="cuda")
-    rays = env.hemisphere_rays(pts[idx], nd[idx], n_dirs=1000, seed=5)           # NB: same hash needs the same point index
-    # the hash uses the point index, so regenerate the subsample's rays from the full index space instead
-    sub_gap = env.sky_gap_fraction(s2, pts[idx], nd[idx], n_dirs=1000, seed=5)
+    base = 517_000                                   # a block of 1000 points OF THE FULL LAUNCH: same place in the sample via point_base
+    rays = env.hemisphere_rays(pts[base:base + 1000], nd[base:base + 1000], n_dirs=1000, seed=5, point_base=base)
     rh = rays.cpu().numpy(); t0 = time.perf_counter(); occ = o2.test_occlusions(rh, mode=1); cpu_s = time.perf_counter() - t0
-    same = bool(np.allclose(sub_gap.cpu().numpy(), 1.0 - occ.reshape(-1, 1000).mean(1), atol=1e-7))
-    report(config="C5 sky Monte-Carlo gap fraction (1M points x 1000 directions, rays never materialised)", rays=int(pts.shape[0]) * 1000, mrays_s=pts.shape[0] * 1000 / dt / 1e6, seconds=dt, mean_gap=float(gap.mean()), cpu_mrays_s=len(rh) / cpu_s / 1e6, parity="identical to oracle occlusion on a 1000-point subsample (1M rays)" if same else "MISMATCH")
+    same = bool(np.array_equal(np.rint(gap[base:base + 1000].cpu().numpy() * 1000).astype(np.int64), 1000 - occ.reshape(1000, 1000).sum(1)))
+    report(config="C5 sky Monte-Carlo gap fraction (1M points x 1000 directions, rays never materialised)", rays=int(pts.shape[0]) * 1000, mrays_s=pts.shape[0] * 1000 / dt / 1e6, seconds=dt, mean_gap=float(gap.mean()), cpu_mrays_s=len(rh) / cpu_s / 1e6, parity="identical to oracle occlusion on a 1000-point block of the same launch (1M rays)" if same else "MISMATCH")
 if "c2" in want or "c5" in want:
     del s2, o2
 
@@ -104,7 +105,7 @@ if "c3" in want:
     sub = np.concatenate(sub_rays); subc = np.concatenate(sub_cnt)
     t0 = time.perf_counter(); refc = o.count_intersections(sub, 1); cpu_s = time.perf_counter() - t0; cn, ct = o.last_counters
     bc = 24 + 4 + 32 * cn / len(sub) + 48 * ct / len(sub); n = nu * nv
-    report(config="C3 rain count_intersections (10M triangles, 100M rays 20 deg off vertical)", triangles=int(t.shape[0]), rays=n, mrays_s=n / total_ms / 1e3, b_ray=bc, roofline_mrays_s=HBM * 1e3 / bc, frac=(n / total_ms / 1e3) / (HBM * 1e3 / bc), build_ms=bms, cpu_mrays_s=len(sub) / cpu_s / 1e6, cpu_threads=o.num_threads, cpu_build_ms=obms, intercepted=float(1 - hist[0].item() / n), parity="bit-identical (1M-ray subsample)" if np.array_equal(subc, refc) else "MISMATCH")
+    report(config="C3 rain count_intersections (10M triangles, 100M rays 20 deg off vertical)", triangles=int(t.shape[0]), rays=n, mrays_s=n / total_ms / 1e3, b_ray=bc, roofline_mrays_s=HBM * 1e3 / bc, frac_canonical_hbm=(n / total_ms / 1e3) / (HBM * 1e3 / bc), build_ms=bms, cpu_mrays_s=len(sub) / cpu_s / 1e6, cpu_threads=o.num_threads, cpu_build_ms=obms, intercepted=float(1 - hist[0].item() / n), parity="bit-identical (1M-ray subsample)" if np.array_equal(subc, refc) else "MISMATCH")
     del s, o
 
 if "c4" in want:
@@ -115,4 +116,4 @@ if "c4" in want:
     o, obms = oracle_scene(v, t); sub = rays[::64].cpu().numpy(); t0 = time.perf_counter(); ref = o.cast_rays(sub, 1); cpu_s = time.perf_counter() - t0; nn, nt = o.last_counters
     b = 24 + 32 + 32 * nn / len(sub) + 48 * nt / len(sub)
     same = bool(np.array_equal(out[2][::64].cpu().numpy(), ref["primitive_ids"]) and np.array_equal(out[0][::64].cpu().numpy(), ref["t_hit"]))
-    report(config="C4 plot (50M triangles) build + cast_rays 16M rays", triangles=int(t.shape[0]), rays=n, mrays_s=n / ms / 1e3, b_ray=b, roofline_mrays_s=HBM * 1e3 / b, frac=(n / ms / 1e3) / (HBM * 1e3 / b), build_ms=bms, sort_ms=st["sort_ms"], build_gbs=460.0 * t.shape[0] / bms / 1e6, bvh_height=st["bvh_height"], quantised_nodes=st["quantised_nodes"], cpu_mrays_s=len(sub) / cpu_s / 1e6, cpu_threads=o.num_threads, cpu_build_ms=obms, parity="bit-identical (250k-ray subsample)" if same else "MISMATCH")
+    report(config="C4 plot (50M triangles) build + cast_rays 16M rays", triangles=int(t.shape[0]), rays=n, mrays_s=n / ms / 1e3, b_ray=b, roofline_mrays_s=HBM * 1e3 / b, frac_canonical_hbm=(n / ms / 1e3) / (HBM * 1e3 / b), build_ms=bms, sort_ms=st["sort_ms"], build_gbs=460.0 * t.shape[0] / bms / 1e6, bvh_height=st["bvh_height"], quantised_nodes=st["quantised_nodes"], cpu_mrays_s=len(sub) / cpu_s / 1e6, cpu_threads=o.num_threads, cpu_build_ms=obms, parity="bit-identical (250k-ray subsample)" if same else "MISMATCH")
