@@ -48,7 +48,8 @@ typedef struct qsmrt_stats {
     uint32_t leaf_max;           /* triangles per collapsed leaf */
     uint32_t bvh_height;         /* binary LBVH height (bounds the traversal stack) */
     uint32_t quantised_nodes;    /* 1: the persistent kernel reads the 32-byte 16-bit-grid nodes */
-    uint32_t full_sort;          /* 1: the last commit fell back to all eight radix passes (a run of > 64 keys equal in their top 40 bits) */
+    uint32_t full_sort;          /* 1: the last commit fell back to all eight radix passes (a run of > 64 keys equal in their top bits) */
+    uint64_t num_references;     /* leaves of the LBVH before collapsing: num_triangles, more when sliver triangles were split */
 } qsmrt_stats;
 
 const char *qsmrt_last_error(void);
@@ -75,6 +76,8 @@ enum qsmrt_option {
     QSMRT_OPT_QUANT_THRESHOLD = 3,     /* 32-byte quantised nodes when 6 grid cells <= value x mean leaf-box diagonal (default 0.15; <= 0 restores it) */
     QSMRT_OPT_CLIMB_CAPACITY = 4,      /* cap of the hierarchy kernel's hand-over list (0 = default); test hook for its overflow path */
     QSMRT_OPT_SORT_VARIANT = 5,        /* 0 = histogram / scan / scatter per radix pass, 1 = one kernel per pass with decoupled look-back (default) */
+    QSMRT_OPT_SPLIT_MAX = 6,           /* sliver splitting: a long thin triangle enters the build as up to this many references with tight slab boxes (default 8; 1 = off) */
+    QSMRT_OPT_SPLIT_ASPECT = 7,        /* ... one reference per this many units of its aspect L^2 / 2A (default 2.0) */
     /* traversal (results are identical for every setting) */
     QSMRT_OPT_QUANTISED_NODES = 16,    /* 0 forces the 64-byte fp32 nodes even where the 32-byte nodes qualify */
     QSMRT_OPT_TRAVERSAL_VARIANT = 17,  /* 1 = one independent loop per thread (simple reference), 2 = persistent warp-uniform kernel (default) */

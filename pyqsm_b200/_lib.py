@@ -24,12 +24,13 @@ class Stats(C.Structure):
         ("build_ms", C.c_float), ("sort_ms", C.c_float), ("box_pad", C.c_float),
         ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3),
         ("leaf_max", C.c_uint32), ("bvh_height", C.c_uint32), ("quantised_nodes", C.c_uint32), ("full_sort", C.c_uint32),
+        ("num_references", C.c_uint64),
     ]
 
 
 # enum qsmrt_option (include/qsmrt.h)
 OPT = {
-    "leaf_max": 1, "keep_binary_nodes": 2, "quant_threshold": 3, "climb_capacity": 4, "sort_variant": 5,
+    "leaf_max": 1, "keep_binary_nodes": 2, "quant_threshold": 3, "climb_capacity": 4, "sort_variant": 5, "split_max": 6, "split_aspect": 7,
     "quantised_nodes": 16, "traversal_variant": 17, "refill": 18, "want": 19, "tri_min": 20, "counters": 21,
     "node_path": 22, "cp_warp_max": 23, "ctas_per_sm": 24,
 }

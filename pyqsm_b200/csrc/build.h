@@ -15,6 +15,8 @@ struct LbvhBuildArgs {
     const float    *verts;          // [V,3] concatenated
     const uint32_t *idx;            // [T,3] rebased into verts
     uint64_t        ntris;
+    const void     *refs;           // RefBox[nrefs] when slivers were split (lbvh_split_emit), else null: one leaf per triangle
+    uint64_t        nrefs;
     const uint64_t *geom_offsets;   // [ngeoms+1] first triangle of each geometry
     uint32_t        ngeoms;
     int             leaf_max;       // 1..QSMRT_LEAF_MAX triangles per collapsed leaf
@@ -24,7 +26,7 @@ struct LbvhBuildArgs {
     // outputs / scratch (device)
     const BuildParams *params_host; // finished on the host (lbvh_finalize_params) from the geometries' bounds
     BuildParams *params;            // device copy; the build adds leaf_diag_sum / use_q
-    uint64_t   *keys, *keys_tmp;    // [T]  the sorted arrays end up in (keys, order) or, when *result_in_tmp, in
+    uint64_t   *keys, *keys_tmp;    // [L]  (L = nrefs when refs, else ntris; likewise below) the sorted arrays end up in (keys, order) or, when *result_in_tmp, in
     uint32_t   *order, *order_tmp;  // [T]  (keys_tmp, order_tmp): the caller keeps that pair and recycles the other
     int        *result_in_tmp;
     uint32_t   *sort_scratch;       // lbvh_sort_scratch_bytes(T)
@@ -45,6 +47,11 @@ size_t lbvh_climb_bytes(uint64_t n);
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
                     uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant, bool hist_done,
                     int *result_in_tmp);
+size_t lbvh_ref_bytes(uint64_t nrefs);
+int lbvh_split_count(const float *verts, const uint32_t *idx, uint64_t T, int split_max, float split_aspect, int32_t *counts,
+                     unsigned long long *total_dev, cudaStream_t st);
+int lbvh_split_emit(const float *verts, const uint32_t *idx, uint64_t T, int split_max, float split_aspect, const int64_t *ref_off,
+                    void *refs, cudaStream_t st);
 void lbvh_finalize_params(const float lo[3], const float hi[3], BuildParams *out);
 int lbvh_geometry_stats(const float *verts, uint64_t V, const uint32_t *idx, uint64_t T, uint32_t *out7_dev, float lo[3], float hi[3],
                         uint32_t *max_index, cudaStream_t st);

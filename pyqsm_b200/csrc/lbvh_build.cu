@@ -74,6 +74,135 @@ k_geometry_stats(const float *__restrict__ verts, uint64_t nverts, const uint32_
     else if (threadIdx.x < 7) atomicMax(&out[threadIdx.x], sb[threadIdx.x]);
 }
 
+// ------------------------------------------------------- sliver splitting
+// An LBVH keys every primitive by the centre of its box, so long thin triangles at arbitrary tilt -- the 1.5 m x 8 cm
+// side triangles of create_cylinder trunks in a cylinder QSM -- get huge, mostly empty, heavily overlapping boxes:
+// on the C1 tree one ray through the trunk tested 813 boxes and 239 triangles (oracle counters), and a 1M-ray launch
+// spent most of its 0.37 ms waiting for a handful of such rays (profiles/r02_c1_tail.txt).  "Early split clipping"
+// (Ernst & Greiner 2007): a triangle whose aspect L^2 / 2A (longest edge L, area A) exceeds split_aspect is cut into
+// K = min(split_max, floor(aspect / split_aspect)) slabs across its longest edge and enters the build as K
+// REFERENCES, each with the tight box of its slab.  The triangle record is duplicated per reference, so traversal
+// is unchanged, and every query already treats two hits of one triangle as one (equal t, equal primitive).
+struct __align__(16) RefBox { float lo[3]; uint32_t tri; float hi[3]; uint32_t pad_; };
+
+__device__ __forceinline__ void load_corners(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t t,
+                                             float A[3], float B[3], float Cc[3])
+{
+    const uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { A[a] = verts[3ull * i0 + a]; B[a] = verts[3ull * i1 + a]; Cc[a] = verts[3ull * i2 + a]; }
+}
+
+// number of slabs for the triangle (A, B, C); on return the corners are rotated so that AB is the longest edge
+__device__ __forceinline__ int split_factor(float A[3], float B[3], float C[3], int split_max, float split_aspect)
+{
+    if (split_max <= 1) return 1;
+    float ab = 0.f, bc = 0.f, ca = 0.f, n[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { ab += (B[a] - A[a]) * (B[a] - A[a]); bc += (C[a] - B[a]) * (C[a] - B[a]); ca += (A[a] - C[a]) * (A[a] - C[a]); }
+    if (bc >= ab && bc >= ca) {            // rotate: (A, B, C) <- (B, C, A)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float t_ = A[a]; A[a] = B[a]; B[a] = C[a]; C[a] = t_; }
+        ab = bc;
+    } else if (ca >= ab && ca >= bc) {     // (A, B, C) <- (C, A, B)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float t_ = C[a]; C[a] = B[a]; B[a] = A[a]; A[a] = t_; }
+        ab = ca;
+    }
+    n[0] = (B[1] - A[1]) * (C[2] - A[2]) - (B[2] - A[2]) * (C[1] - A[1]);
+    n[1] = (B[2] - A[2]) * (C[0] - A[0]) - (B[0] - A[0]) * (C[2] - A[2]);
+    n[2] = (B[0] - A[0]) * (C[1] - A[1]) - (B[1] - A[1]) * (C[0] - A[0]);
+    const float area2 = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);        // 2 x area
+    if (!(area2 > 0.0f) || !(ab > 0.0f)) return 1;
+    const float k = floorf(ab / area2 / split_aspect);                          // L^2 / 2A / split_aspect
+    return k >= (float)split_max ? split_max : (k >= 2.0f ? (int)k : 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_split_count(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n, int split_max, float split_aspect,
+              int32_t *__restrict__ counts, unsigned long long *total)
+{
+    unsigned long long mine = 0;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        float A[3], B[3], C[3];
+        load_corners(verts, idx, t, A, B, C);
+        const int k = split_factor(A, B, C, split_max, split_aspect);
+        if (counts) counts[t] = k;
+        mine += (unsigned long long)k;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+    __shared__ unsigned long long ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long s_ = 0; for (int k = 0; k < 8; ++k) s_ += ws[k]; if (s_) atomicAdd(total, s_); }
+}
+
+// slab j of K across the longest edge AB (apex C projects to sc in [0, L]): the cross-section at parameter s joins
+// A + s u on AB with the point at s on AC (s <= sc) or CB (s >= sc); the slab is the hull of its two cross-sections
+// (plus C when sc lies inside), so its box is the min / max of at most five points
+__global__ void __launch_bounds__(256)
+k_split_emit(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n, int split_max, float split_aspect,
+             const int64_t *__restrict__ ref_off, RefBox *__restrict__ refs)
+{
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float A[3], B[3], C[3];
+    load_corners(verts, idx, t, A, B, C);
+    const int64_t o = ref_off[t];
+    const int K = (int)(ref_off[t + 1] - o);
+    if (K <= 1) {
+        RefBox r; r.tri = (uint32_t)t; r.pad_ = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { r.lo[a] = fminf(A[a], fminf(B[a], C[a])); r.hi[a] = fmaxf(A[a], fmaxf(B[a], C[a])); }
+        refs[o] = r;
+        return;
+    }
+    split_factor(A, B, C, split_max, split_aspect);         // rotates the corners: AB is the longest edge
+    float u[3], L = 0.f, sc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { u[a] = B[a] - A[a]; L += u[a] * u[a]; }
+    L = sqrtf(L);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { u[a] /= L; sc += (C[a] - A[a]) * u[a]; }
+    sc = fminf(fmaxf(sc, 0.0f), L);
+    for (int j = 0; j < K; ++j) {
+        const float s0 = L * (float)j / (float)K, s1 = L * (float)(j + 1) / (float)K;
+        RefBox r; r.tri = (uint32_t)t; r.pad_ = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { r.lo[a] = INFINITY; r.hi[a] = -INFINITY; }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float sv = e ? s1 : s0;
+            // the cross-section's end on the far boundary: on AC for sv <= sc, on CB beyond
+            float f, P0[3], P1[3];
+            if (sv <= sc) { f = sc > 0.0f ? sv / sc : 1.0f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { P0[a] = A[a]; P1[a] = C[a]; } }
+            else { f = (L - sc) > 0.0f ? (sv - sc) / (L - sc) : 0.0f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { P0[a] = C[a]; P1[a] = B[a]; } }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float onab = A[a] + sv * u[a], far = P0[a] + f * (P1[a] - P0[a]);
+                r.lo[a] = fminf(r.lo[a], fminf(onab, far)); r.hi[a] = fmaxf(r.hi[a], fmaxf(onab, far));
+            }
+        }
+        if (sc > s0 && sc < s1) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { r.lo[a] = fminf(r.lo[a], C[a]); r.hi[a] = fmaxf(r.hi[a], C[a]); }
+        }
+        // the slab lies inside the triangle: never let rounding push its box outside the triangle's own box, and
+        // widen by the slack of the interpolation (a few ulp of the coordinates; the leaf padding comes on top)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float tl = fminf(A[a], fminf(B[a], C[a])), th = fmaxf(A[a], fmaxf(B[a], C[a]));
+            const float e = 4.76837158e-07f * fmaxf(fabsf(tl), fabsf(th));      // 2^-21
+            r.lo[a] = fmaxf(r.lo[a] - e, tl); r.hi[a] = fminf(r.hi[a] + e, th);
+        }
+        refs[o + j] = r;
+    }
+}
+
 // ---------------------------------------------------------------- Morton
 __device__ __forceinline__ uint64_t spread21(uint32_t x)
 {
@@ -91,7 +220,8 @@ __device__ __forceinline__ uint64_t spread21(uint32_t x)
 __global__ void __launch_bounds__(256)
 k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n,
          BuildParams *__restrict__ bp, uint64_t *__restrict__ keys, uint32_t *__restrict__ order,
-         uint32_t *__restrict__ ghist /* [npass][256], may be null */, int shift0, int npass)
+         uint32_t *__restrict__ ghist /* [npass][256], may be null */, int shift0, int npass,
+         const RefBox *__restrict__ refs /* non-null: n references (split slivers) instead of n triangles */)
 {
     __shared__ float wsum[8];
     __shared__ uint32_t h[8][256];
@@ -101,7 +231,11 @@ k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint
 #pragma unroll 2
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
         float lo[3], hi[3];
-        tri_bounds(verts, idx, t, lo, hi);
+        if (refs) {
+            const RefBox r = refs[t];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo[a] = r.lo[a]; hi[a] = r.hi[a]; }
+        } else tri_bounds(verts, idx, t, lo, hi);
         uint32_t q[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -614,7 +748,7 @@ __device__ __forceinline__ void global_climb(const RefitOut &R, const RefitQueue
 
 __global__ void __launch_bounds__(RF_BLOCK, QSMRT_RF_MINB)
 k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restrict__ idx, int64_t n,
-                       const uint64_t *__restrict__ keys, const uint32_t *__restrict__ order,
+                       const uint64_t *__restrict__ keys, uint32_t *order, const RefBox *__restrict__ refs,
                        const uint64_t *__restrict__ goff, uint32_t ngeoms,
                        BuildParams *bp, BNode *bn, TriRec *__restrict__ tris,
                        unsigned long long *flags, TNode *__restrict__ tn, QNode *__restrict__ qn,
@@ -649,21 +783,29 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
     s_qi[1][threadIdx.x] = -1;
     s_flag[threadIdx.x] = 0u;
     if (i < n) {
-        const uint64_t t = order[i];
+        uint64_t t = order[i];
         const uint64_t k = keys[i];
         if (i > 0) dl = delta_adjacent(keys[i - 1], k, i - 1);
         if (i + 1 < n) dr = delta_adjacent(k, keys[i + 1], i);
+        float blo[3], bhi[3];
+        if (refs) {                 // a reference of a split triangle: its slab's box; `order` becomes sorted position -> triangle
+            const RefBox rb = refs[t];
+            t = rb.tri;
+            order[i] = rb.tri;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { blo[a] = rb.lo[a]; bhi[a] = rb.hi[a]; }
+        }
         uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
         float p0[3], p1[3], p2[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) { p0[a] = verts[3ull * i0 + a]; p1[a] = verts[3ull * i1 + a]; p2[a] = verts[3ull * i2 + a]; }
+        if (!refs) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { blo[a] = fminf(p0[a], fminf(p1[a], p2[a])); bhi[a] = fmaxf(p0[a], fmaxf(p1[a], p2[a])); }
+        }
         const float pad = bp->pad;
-        mlo.x = __fsub_rn(fminf(p0[0], fminf(p1[0], p2[0])), pad);
-        mlo.y = __fsub_rn(fminf(p0[1], fminf(p1[1], p2[1])), pad);
-        mlo.z = __fsub_rn(fminf(p0[2], fminf(p1[2], p2[2])), pad);
-        mhi.x = __fadd_rn(fmaxf(p0[0], fmaxf(p1[0], p2[0])), pad);
-        mhi.y = __fadd_rn(fmaxf(p0[1], fmaxf(p1[1], p2[1])), pad);
-        mhi.z = __fadd_rn(fmaxf(p0[2], fmaxf(p1[2], p2[2])), pad);
+        mlo.x = __fsub_rn(blo[0], pad); mlo.y = __fsub_rn(blo[1], pad); mlo.z = __fsub_rn(blo[2], pad);
+        mhi.x = __fadd_rn(bhi[0], pad); mhi.y = __fadd_rn(bhi[1], pad); mhi.z = __fadd_rn(bhi[2], pad);
         if (keep_bn) {
             mlo.w = __int_as_float(-1); mhi.w = __int_as_float(-1);
             float4 *leaf = reinterpret_cast<float4 *>(&bn[n - 1 + i]);
@@ -979,9 +1121,31 @@ int lbvh_geometry_stats(const float *verts, uint64_t V, const uint32_t *idx, uin
     return 0;
 }
 
+// Sliver splitting, host side: how many references the triangles want in total (*total_dev, zeroed by the caller;
+// counts may be null), and their boxes once the counts are scanned into ref_off[T + 1].
+size_t lbvh_ref_bytes(uint64_t nrefs) { return (size_t)nrefs * sizeof(RefBox); }
+
+int lbvh_split_count(const float *verts, const uint32_t *idx, uint64_t T, int split_max, float split_aspect, int32_t *counts,
+                     unsigned long long *total_dev, cudaStream_t st)
+{
+    if (T == 0) return 0;
+    k_split_count<<<(unsigned)std::min<uint64_t>((T + 255) / 256, 148 * 8), 256, 0, st>>>(verts, idx, T, split_max, split_aspect, counts, total_dev);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int lbvh_split_emit(const float *verts, const uint32_t *idx, uint64_t T, int split_max, float split_aspect, const int64_t *ref_off,
+                    void *refs, cudaStream_t st)
+{
+    if (T == 0) return 0;
+    k_split_emit<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(verts, idx, T, split_max, split_aspect, ref_off, static_cast<RefBox *>(refs));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
 {
-    const uint64_t n = A.ntris;
+    const uint64_t n = A.refs ? A.nrefs : A.ntris;          // leaves of the tree: references when slivers were split
     const int B = 256;
     const unsigned gN = (unsigned)((n + B - 1) / B);
     CUDA_TRY(cudaMemsetAsync(A.counters, 0, 5 * sizeof(unsigned long long), st));
@@ -996,7 +1160,8 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
         ghist = A.sort_scratch + 8ull * ((n + OS_TILE - 1) / OS_TILE) * 256;
     }
     k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order, ghist,
-                                                 top_only ? sort_shift0(n) : 0, top_only ? sort_passes(n) : 8);
+                                                 top_only ? sort_shift0(n) : 0, top_only ? sort_passes(n) : 8,
+                                                 static_cast<const RefBox *>(A.refs));
     CUDA_TRY(cudaGetLastError());
     if (A.ev_sort0) CUDA_TRY(cudaEventRecord(A.ev_sort0, st));
     int in_tmp = 0;
@@ -1004,7 +1169,7 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
                         A.sort_variant, onesweep, &in_tmp)) return 1;
     if (A.result_in_tmp) *A.result_in_tmp = in_tmp;
     const uint64_t *keys = in_tmp ? A.keys_tmp : A.keys;        // the caller keeps whichever pair holds the sorted arrays
-    const uint32_t *order = in_tmp ? A.order_tmp : A.order;
+    uint32_t *order = in_tmp ? A.order_tmp : A.order;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
     if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
     const int keep = (A.keep_bnodes || n == 1) ? 1 : 0;
@@ -1013,7 +1178,7 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     unsigned *work_count = reinterpret_cast<unsigned *>(A.counters + 3);
     ClimbItem *work = reinterpret_cast<ClimbItem *>(A.climb_work);
     k_hierarchy_refit_emit<<<(unsigned)((n + RF_BLOCK - 1) / RF_BLOCK), RF_BLOCK, 0, st>>>(
-        A.verts, A.idx, (int64_t)n, keys, order, A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
+        A.verts, A.idx, (int64_t)n, keys, order, static_cast<const RefBox *>(A.refs), A.geom_offsets, A.ngeoms, A.params, A.bnodes, A.tris, A.flags,
         A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap, A.quant_frac);
     k_hierarchy_climb<<<std::min((work_cap + CL_BLOCK - 1) / CL_BLOCK, 148u * 32u), CL_BLOCK, 0, st>>>(
         (int64_t)n, A.params, A.bnodes, A.flags, A.tnodes, A.qnodes, A.counters, A.leaf_max, keep, work, work_count, work_cap);

@@ -36,6 +36,8 @@ struct Geometry {
     float *verts = nullptr; uint32_t *idx = nullptr;
     uint64_t V = 0, T = 0;
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };   // over the vertices its triangles reference
+    uint64_t nrefs = 0;          // references its triangles want when slivers are split (>= T), counted at registration ...
+    int ref_max = 0; float ref_aspect = 0.0f;      // ... with these split options
 };
 
 struct HostPipe {            // device staging of the *_host entry points: rays in, up to 32 B/ray of results out
@@ -54,6 +56,8 @@ struct BuildOptions {
     int climb_capacity = 0;      // > 0: cap of the climb work list (test hook)
     int sort_variant = 1;        // 0 classic radix passes, 1 onesweep
     int allow_qnodes = 1;        // traversal may read the 32-byte nodes when the build made them
+    int split_max = 8;           // a sliver triangle enters the build as up to this many references (1 = no splitting)
+    float split_aspect = 2.0f;   // ... one per `split_aspect` units of its aspect L^2 / 2A
 };
 
 struct qsmrt_scene {
@@ -63,6 +67,7 @@ struct qsmrt_scene {
     // concatenated mesh (aliases geoms[0] when there is a single geometry)
     float *verts = nullptr; uint32_t *idx = nullptr; bool own_concat = false;
     uint64_t ntris = 0, nverts = 0;
+    uint64_t nleaves = 0;                            // leaves of the LBVH: ntris, or the number of references when slivers were split
     uint64_t *goff = nullptr, *voff = nullptr;       // device [ngeoms+1]
     // build products kept for traversal / introspection
     uint64_t *keys = nullptr; uint32_t *order = nullptr;
@@ -294,6 +299,22 @@ int check_rays(const float *rays, uint64_t N)
     return 0;
 }
 
+// references the triangles of a geometry want under the scene's current split options (registration-time statistic;
+// recounted by the commit only if the options were changed since)
+int count_refs(qsmrt_scene *s, Geometry &g)
+{
+    g.ref_max = s->bopt.split_max; g.ref_aspect = s->bopt.split_aspect; g.nrefs = g.T;
+    if (g.T == 0 || s->bopt.split_max <= 1) return 0;
+    unsigned long long *d = nullptr, h = 0;
+    if (dmalloc(&d, 1)) return 1;
+    int rc = cudaMemset(d, 0, sizeof(h)) != cudaSuccess || lbvh_split_count(g.verts, g.idx, g.T, g.ref_max, g.ref_aspect, nullptr, d, nullptr) ||
+             cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess;
+    dfree(d);
+    if (rc) { if (!g_err[0]) qsmrt_set_error("reference count failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    g.nrefs = h;
+    return 0;
+}
+
 SceneView view_of(qsmrt_scene *s)
 {
     if (s->trv.opt.node_path != 0 && !s->node_tex && s->tnodes) {
@@ -301,7 +322,7 @@ SceneView view_of(qsmrt_scene *s)
         // (QSMRT_OPT_NODE_PATH) reads it, and creating it cost every commit a driver call
         cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = s->tnodes;
         rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-        rd.res.linear.sizeInBytes = std::max<uint64_t>(s->ntris - 1, 1) * sizeof(TNode);
+        rd.res.linear.sizeInBytes = std::max<uint64_t>(s->nleaves - 1, 1) * sizeof(TNode);
         cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
         if (cudaCreateTextureObject(&s->node_tex, &rd, &td, nullptr) != cudaSuccess) { s->node_tex = 0; cudaGetLastError(); }
     }
@@ -317,10 +338,12 @@ SceneView view_of(qsmrt_scene *s)
 struct CommitScratch {
     uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr;
     unsigned long long *flags = nullptr, *counters = nullptr; uint32_t *climb = nullptr;
+    int32_t *split_cnt = nullptr; int64_t *ref_off = nullptr; char *scan_scratch = nullptr, *refs = nullptr;     // sliver splitting
     cudaEvent_t e0 = nullptr, e1 = nullptr, es0 = nullptr, es1 = nullptr;
     ~CommitScratch()
     {
         dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(flags); dfree(counters); dfree(climb);
+        dfree(split_cnt); dfree(ref_off); dfree(scan_scratch); dfree(refs);
         if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (es0) cudaEventDestroy(es0); if (es1) cudaEventDestroy(es1);
     }
 };
@@ -337,12 +360,24 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
     CUDA_TRY(cudaMemcpyAsync(s->goff, goff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->voff, voff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));        // goff / voff are locals
+    // sliver splitting: the geometries counted their references at registration, so the number of leaves is known here
+    uint64_t R = 0;
+    for (Geometry &ge : s->geoms) {
+        if (ge.ref_max != s->bopt.split_max || ge.ref_aspect != s->bopt.split_aspect) { if (count_refs(s, ge)) return 1; }
+        R += ge.nrefs;
+    }
+    const bool split = R > T && R < (1ull << 29);
+    const uint64_t Lv = split ? R : T;
+    s->nleaves = Lv;
     // allocate everything before the timed region
-    if (dmalloc(&s->keys, T) || dmalloc(&cs.keys_tmp, T) || dmalloc(&s->order, T) || dmalloc(&cs.order_tmp, T) ||
-        dmalloc(&cs.sort_scratch, lbvh_sort_scratch_bytes(T) / sizeof(uint32_t)) ||
-        dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * T - 1) || dmalloc(&cs.flags, T) || dmalloc(&s->tris, T) ||
-        dmalloc(&s->tnodes, std::max<uint64_t>(T - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(T - 1, 1)) ||
-        dmalloc(&cs.counters, 5) || dmalloc(&cs.climb, lbvh_climb_bytes(T) / sizeof(uint32_t)))
+    if (dmalloc(&s->keys, Lv) || dmalloc(&cs.keys_tmp, Lv) || dmalloc(&s->order, Lv) || dmalloc(&cs.order_tmp, Lv) ||
+        dmalloc(&cs.sort_scratch, lbvh_sort_scratch_bytes(Lv) / sizeof(uint32_t)) ||
+        dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * Lv - 1) || dmalloc(&cs.flags, Lv) || dmalloc(&s->tris, Lv) ||
+        dmalloc(&s->tnodes, std::max<uint64_t>(Lv - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(Lv - 1, 1)) ||
+        dmalloc(&cs.counters, 5) || dmalloc(&cs.climb, lbvh_climb_bytes(Lv) / sizeof(uint32_t)))
+        return 1;
+    if (split && (dmalloc(&cs.split_cnt, T) || dmalloc(&cs.ref_off, T + 1) || dmalloc(&cs.scan_scratch, trv_scan_scratch_bytes(T)) ||
+                  dmalloc(&cs.refs, lbvh_ref_bytes(R))))
         return 1;
     if (G == 1) { s->verts = s->geoms[0].verts; s->idx = s->geoms[0].idx; s->own_concat = false; }
     else {
@@ -364,8 +399,15 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
         if (ge.T) for (int a = 0; a < 3; ++a) { slo[a] = fminf(slo[a], ge.lo[a]); shi[a] = fmaxf(shi[a], ge.hi[a]); }
     BuildParams bp_host;
     lbvh_finalize_params(slo, shi, &bp_host);
+    if (split) {        // per-triangle slab counts -> offsets -> the references' boxes
+        if (lbvh_split_count(s->verts, s->idx, T, s->bopt.split_max, s->bopt.split_aspect, cs.split_cnt, cs.counters, st) ||
+            trv_exclusive_scan(cs.split_cnt, T, cs.ref_off, cs.scan_scratch, st) ||
+            lbvh_split_emit(s->verts, s->idx, T, s->bopt.split_max, s->bopt.split_aspect, cs.ref_off, cs.refs, st))
+            return 1;
+    }
     int in_tmp = 0;
     LbvhBuildArgs A{};
+    A.refs = split ? cs.refs : nullptr; A.nrefs = Lv;
     A.params_host = &bp_host; A.result_in_tmp = &in_tmp;
     A.leaf_max = s->bopt.leaf_max; A.sort_variant = s->bopt.sort_variant; A.climb_capacity = s->bopt.climb_capacity;
     A.quant_frac = s->bopt.quant_frac;
@@ -401,7 +443,8 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
     if (!s->bopt.keep_bnodes) dfree(s->bnodes);         // only the hand-over boxes of the build were in it
     for (int a = 0; a < 3; ++a) { s->glo[a] = bp.glo[a]; s->cell[a] = bp.cell[a]; }
     s->stats.quantised_nodes = s->use_qnodes ? 1u : 0u;
-    s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + T * sizeof(TriRec);
+    s->stats.bvh_bytes = cnt[0] * (s->use_qnodes ? sizeof(QNode) : sizeof(TNode)) + Lv * sizeof(TriRec);
+    s->stats.num_references = Lv;
     return 0;
 }
 
@@ -567,7 +610,7 @@ int qsmrt_add_triangles(qsmrt_scene *s, const float *verts, uint64_t V, const ui
         }
         return 0;
     };
-    const int rc = body();
+    const int rc = body() || count_refs(s, g);
     dfree(d_max);
     if (rc) { dfree(g.verts); dfree(g.idx); return 1; }
     if (s->committed || s->verts) free_build(s);
@@ -606,6 +649,7 @@ int qsmrt_add_cylinders(qsmrt_scene *s, const float *records, uint64_t n, uint32
             e = cudaErrorUnknown;
         dfree(d_stats);
         if (e != cudaSuccess) { dfree(g.verts); dfree(g.idx); FAIL("cylinder generation failed: %s", cudaGetErrorString(e)); }
+        if (count_refs(s, g)) { dfree(g.verts); dfree(g.idx); return 1; }
     }
     if (s->committed || s->verts) free_build(s);
     s->geoms.push_back(g);
@@ -677,6 +721,10 @@ int qsmrt_scene_set_option(qsmrt_scene *s, int key, double value)
     case QSMRT_OPT_SORT_VARIANT:
         if (iv != 0 && iv != 1) FAIL("sort variant must be 0 (classic) or 1 (onesweep)");
         rebuild = b.sort_variant != iv; b.sort_variant = iv; break;
+    case QSMRT_OPT_SPLIT_MAX:
+        if (iv < 1 || iv > 64) FAIL("split_max must be in 1..64");
+        rebuild = b.split_max != iv; b.split_max = iv; break;
+    case QSMRT_OPT_SPLIT_ASPECT: { const float f = value > 0.0 ? (float)value : 2.0f; rebuild = b.split_aspect != f; b.split_aspect = f; break; }
     case QSMRT_OPT_QUANTISED_NODES: b.allow_qnodes = iv != 0; break;
     case QSMRT_OPT_TRAVERSAL_VARIANT:
         if (iv != 1 && iv != 2) FAIL("unknown traversal variant %d (1 = per-thread loop, 2 = persistent kernel)", iv);
@@ -704,6 +752,8 @@ int qsmrt_scene_get_option(qsmrt_scene *s, int key, double *value)
     case QSMRT_OPT_QUANT_THRESHOLD: *value = b.quant_frac; break;
     case QSMRT_OPT_CLIMB_CAPACITY: *value = b.climb_capacity; break;
     case QSMRT_OPT_SORT_VARIANT: *value = b.sort_variant; break;
+    case QSMRT_OPT_SPLIT_MAX: *value = b.split_max; break;
+    case QSMRT_OPT_SPLIT_ASPECT: *value = b.split_aspect; break;
     case QSMRT_OPT_QUANTISED_NODES: *value = b.allow_qnodes; break;
     case QSMRT_OPT_TRAVERSAL_VARIANT: *value = t.variant; break;
     case QSMRT_OPT_REFILL: *value = t.refill; break;
@@ -1038,8 +1088,8 @@ int qsmrt_peel_projection(qsmrt_scene *s, uint64_t nu, uint64_t nv, const float 
     for (int layer = 0; !rc && layer < max_layers; ++layer) {
         double h[3] = { 0, 0, 0 };
         if (cudaMemsetAsync(sums, 0, 3 * sizeof(double), st) != cudaSuccess) { rc = 1; break; }
-        rc = trv_peel_cast(s->trv, sv, nu, nv, o0, du, dv, dir, alive, hit, st) ||
-             trv_peel_update(sv, s->order, alive, hit, layer_of, layer, dir, sums, st);
+        rc = trv_peel_cast(s->trv, sv, nu, nv, o0, du, dv, dir, s->order, alive, hit, st) ||
+             trv_peel_update(s->verts, s->idx, T, alive, hit, layer_of, layer, dir, sums, st);
         if (!rc && (cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                     cudaStreamSynchronize(st) != cudaSuccess)) rc = 1;
         if (rc || h[0] == 0.0) break;                       // nothing left that the rays can see
@@ -1060,8 +1110,8 @@ namespace {
 struct SceneFileHeader {
     char     magic[8];           // "QSMRTSC1"
     uint32_t version, flags;
-    uint64_t ngeoms, ntris, nverts;
-    int32_t  leaf_max, use_q;
+    uint64_t ngeoms, ntris, nverts, nleaves;
+    int32_t  leaf_max, use_q, split_max; float split_aspect;
     float    quant_frac, glo[3], cell[3];
     qsmrt_stats stats;
 };
@@ -1113,6 +1163,7 @@ int qsmrt_scene_save(qsmrt_scene *s, const char *path, uint32_t flags)
     h.ngeoms = s->geoms.size();
     for (const Geometry &g : s->geoms) { h.ntris += g.T; h.nverts += g.V; }
     h.leaf_max = s->bopt.leaf_max; h.quant_frac = s->bopt.quant_frac;
+    h.split_max = s->bopt.split_max; h.split_aspect = s->bopt.split_aspect; h.nleaves = h.flags ? s->nleaves : 0;
     if (h.flags) {
         h.use_q = s->use_qnodes ? 1 : 0; h.stats = s->stats;
         for (int a = 0; a < 3; ++a) { h.glo[a] = s->glo[a]; h.cell[a] = s->cell[a]; }
@@ -1124,7 +1175,7 @@ int qsmrt_scene_save(qsmrt_scene *s, const char *path, uint32_t flags)
         if (io.put(g.verts, 3 * g.V * sizeof(float)) || io.put(g.idx, 3 * g.T * sizeof(uint32_t))) return 1;
     }
     if (h.flags) {
-        const uint64_t T = s->ntris, NN = std::max<uint64_t>(T - 1, 1);
+        const uint64_t T = s->nleaves, NN = std::max<uint64_t>(T - 1, 1);
         if (io.put(s->params, sizeof(BuildParams)) || io.put(s->tnodes, NN * sizeof(TNode)) ||
             (s->use_qnodes && io.put(s->qnodes, NN * sizeof(QNode))) || io.put(s->tris, T * sizeof(TriRec)) ||
             io.put(s->order, T * sizeof(uint32_t)) || io.put(s->keys, T * sizeof(uint64_t)))
@@ -1146,7 +1197,9 @@ int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out)
         SceneFileHeader h;
         if (fread(&h, sizeof(h), 1, io.f) != 1 || memcmp(h.magic, "QSMRTSC1", 8) != 0 || h.version != 1)
             FAIL("%s is not a qsmrt scene file (version 1)", path);
-        if (h.ntris >= (1ull << 29) || h.nverts >= (1ull << 32) || h.leaf_max < 1 || h.leaf_max > QSMRT_LEAF_MAX) FAIL("corrupt scene file header");
+        if (h.ntris >= (1ull << 29) || h.nleaves >= (1ull << 29) || h.nverts >= (1ull << 32) || h.leaf_max < 1 || h.leaf_max > QSMRT_LEAF_MAX ||
+            h.split_max < 1 || h.split_max > 64 || !(h.split_aspect > 0.0f)) FAIL("corrupt scene file header");
+        s->bopt.split_max = h.split_max; s->bopt.split_aspect = h.split_aspect;      // before the geometries count their references
         uint64_t T = 0, V = 0;
         for (uint64_t gi = 0; gi < h.ngeoms; ++gi) {
             uint64_t vt[2];
@@ -1161,6 +1214,7 @@ int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out)
                 FAIL("corrupt scene file (geometry %llu)", (unsigned long long)gi);
             }
             dfree(d_stats);
+            if (count_refs(s, g)) { dfree(g.verts); dfree(g.idx); return 1; }
             s->geoms.push_back(g);
             T += g.T; V += g.V;
         }
@@ -1168,12 +1222,14 @@ int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out)
         s->bopt.leaf_max = h.leaf_max; s->bopt.quant_frac = h.quant_frac;
         if (!(h.flags & QSMRT_SAVE_BVH) || T == 0) return 0;        // geometry only: the first query builds
         const uint32_t G = (uint32_t)s->geoms.size();
-        const uint64_t NN = std::max<uint64_t>(T - 1, 1);
-        s->ntris = T; s->nverts = V;
+        const uint64_t Lv = h.nleaves;
+        if (Lv < T) FAIL("corrupt scene file (leaf count)");
+        const uint64_t NN = std::max<uint64_t>(Lv - 1, 1);
+        s->ntris = T; s->nverts = V; s->nleaves = Lv;
         std::vector<uint64_t> goff(G + 1, 0), voff(G + 1, 0);
         { uint64_t t = 0, v = 0; for (uint32_t g = 0; g < G; ++g) { goff[g] = t; voff[g] = v; t += s->geoms[g].T; v += s->geoms[g].V; } goff[G] = t; voff[G] = v; }
         if (dmalloc(&s->goff, G + 1) || dmalloc(&s->voff, G + 1) || dmalloc(&s->params, 1) || dmalloc(&s->tnodes, NN) ||
-            (h.use_q && dmalloc(&s->qnodes, NN)) || dmalloc(&s->tris, T) || dmalloc(&s->order, T) || dmalloc(&s->keys, T))
+            (h.use_q && dmalloc(&s->qnodes, NN)) || dmalloc(&s->tris, Lv) || dmalloc(&s->order, Lv) || dmalloc(&s->keys, Lv))
             return 1;
         CUDA_TRY(cudaMemcpy(s->goff, goff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(s->voff, voff.data(), (G + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
@@ -1188,8 +1244,8 @@ int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out)
             }
         }
         if (io.get(s->params, sizeof(BuildParams)) || io.get(s->tnodes, NN * sizeof(TNode)) ||
-            (h.use_q && io.get(s->qnodes, NN * sizeof(QNode))) || io.get(s->tris, T * sizeof(TriRec)) ||
-            io.get(s->order, T * sizeof(uint32_t)) || io.get(s->keys, T * sizeof(uint64_t)))
+            (h.use_q && io.get(s->qnodes, NN * sizeof(QNode))) || io.get(s->tris, Lv * sizeof(TriRec)) ||
+            io.get(s->order, Lv * sizeof(uint32_t)) || io.get(s->keys, Lv * sizeof(uint64_t)))
             return 1;
         CUDA_TRY(cudaDeviceSynchronize());
         s->use_qnodes = h.use_q != 0;
@@ -1230,8 +1286,8 @@ int qsmrt_debug_get_build(qsmrt_scene *s, uint64_t *keys, uint32_t *order, void 
 {
     SCENE_ENTER(s);
     if (do_commit(s, nullptr, nullptr)) return 1;
-    uint64_t T = s->ntris;
-    if (T == 0) return 0;
+    uint64_t T = s->nleaves;         // = triangles unless slivers were split (then: references, see qsmrt_stats.num_references)
+    if (s->ntris == 0) return 0;
     if (keys) CUDA_TRY(cudaMemcpy(keys, s->keys, T * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (order) CUDA_TRY(cudaMemcpy(order, s->order, T * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (nodes && !s->bnodes) FAIL("binary nodes were not kept: set QSMRT_OPT_KEEP_BINARY_NODES before the commit");

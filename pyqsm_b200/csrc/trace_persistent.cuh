@@ -134,7 +134,7 @@ struct TraceArgs {
     int32_t *counts;                                            // MODE 2
     const int64_t *splits; float *l_t; uint32_t *l_geom, *l_prim; float2 *l_uv;      // MODE 6
     uint32_t *accum; const uint64_t *goff; uint64_t accum_stride;   // MODE 3 / 4 (stride: one row of counts per grid of a sweep, 0 = one row)
-    const uint8_t *alive; uint8_t *hitflag;                     // MODE 5 (both indexed by sorted triangle)
+    const uint8_t *alive; uint8_t *hitflag; const uint32_t *order;  // MODE 5: flags per triangle (scene order) = order[sorted record]
     unsigned long long *cursor, *stats;
     int refill, want, tri_min, node_path;
     int depth;          // stack entries per thread; the MODE 2 hit set starts behind the stack in shared memory
@@ -276,7 +276,7 @@ k_trace5(const TraceArgs A)
                 } else if (MODE == 2) {
                     A.counts[ray_i] = overflow ? -1 : cnt;           // -1: k_count_fix recounts this ray exactly
                 } else if (MODE == 5) {
-                    if (best_prim != QSMRT_INVALID) A.hitflag[best_tri] = 1;
+                    if (best_prim != QSMRT_INVALID) A.hitflag[A.order[best_tri]] = 1;
                 }
             }
             if (exhausted) {
@@ -420,7 +420,7 @@ k_trace5(const TraceArgs A)
                 MtHit h;
                 if (COUNTERS) ++n_tri;
                 if (CLOSEST) {
-                    if ((MODE != 5 || A.alive[tri_i]) && mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
+                    if ((MODE != 5 || A.alive[A.order[tri_i]]) && mt_test(p0, p1, p2, r.O, r.D, 0.0f, INFINITY, h)) {
                         float tt = __fdiv_rn(h.T, h.absDen);
                         uint32_t pg = __float_as_uint(p1.w), pp = __float_as_uint(p0.w);
                         bool better = (tt < best_t) | ((tt == best_t) & ((pg < best_geom) | ((pg == best_geom) & (pp < best_prim))));

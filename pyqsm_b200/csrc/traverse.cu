@@ -718,20 +718,24 @@ k_points_to_rays(const float *__restrict__ pts, float *__restrict__ rays, uint64
 }
 
 // peel projection bookkeeping: triangles hit in this layer leave the scene; their 3-D and projected areas
-// are summed (ray_casting.py:285-301: hit-triangle surface area, 3-D and flattened along the view direction)
+// are summed (ray_casting.py:285-301: hit-triangle surface area, 3-D and flattened along the view direction).
+// Flags are per TRIANGLE (scene order), not per sorted record: a split sliver has several records.
 __global__ void __launch_bounds__(256)
-k_peel_update(const TriRec *__restrict__ tris, uint32_t n, const uint32_t *__restrict__ order, uint8_t *__restrict__ alive,
+k_peel_update(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n, uint8_t *__restrict__ alive,
               uint8_t *__restrict__ hitflag, int32_t *__restrict__ layer_of, int layer, f3 dir, double *__restrict__ sums)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     double cnt = 0.0, a3 = 0.0, ap = 0.0;
-    if (i < n && hitflag[i]) {
-        hitflag[i] = 0;
-        if (alive[i]) {
-            alive[i] = 0;
-            if (layer_of) layer_of[order[i]] = layer;
-            const float4 p1 = tris[i].p1, p2 = tris[i].p2;
-            f3 Ng = f3cross(f3{ p2.x, p2.y, p2.z }, f3{ p1.x, p1.y, p1.z });
+    if (t < n && hitflag[t]) {
+        hitflag[t] = 0;
+        if (alive[t]) {
+            alive[t] = 0;
+            if (layer_of) layer_of[t] = layer;
+            const uint32_t i0 = idx[3 * t], i1 = idx[3 * t + 1], i2 = idx[3 * t + 2];
+            const f3 v0 = { verts[3ull * i0], verts[3ull * i0 + 1], verts[3ull * i0 + 2] };
+            const f3 e1 = { __fsub_rn(v0.x, verts[3ull * i1]), __fsub_rn(v0.y, verts[3ull * i1 + 1]), __fsub_rn(v0.z, verts[3ull * i1 + 2]) };
+            const f3 e2 = { __fsub_rn(verts[3ull * i2], v0.x), __fsub_rn(verts[3ull * i2 + 1], v0.y), __fsub_rn(verts[3ull * i2 + 2], v0.z) };
+            f3 Ng = f3cross(e2, e1);          // the triangle record's e2 x e1
             cnt = 1.0;
             a3 = 0.5 * sqrt((double)Ng.x * Ng.x + (double)Ng.y * Ng.y + (double)Ng.z * Ng.z);
             ap = 0.5 * fabs((double)Ng.x * dir.x + (double)Ng.y * dir.y + (double)Ng.z * dir.z);
@@ -1167,7 +1171,7 @@ int trv_apply_sign(float *dist, const int32_t *counts, uint64_t N, cudaStream_t 
 
 // one layer of the peel projection: cast the grid against the triangles still alive, flag the owners of the closest hits
 int trv_peel_cast(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3], const float dv[3],
-                  const float dir[3], const uint8_t *alive, uint8_t *hitflag, cudaStream_t st)
+                  const float dir[3], const uint32_t *order, const uint8_t *alive, uint8_t *hitflag, cudaStream_t st)
 {
     if (nu * nv == 0 || sc.ntris == 0) return 0;
     if (!use_v5(ts, sc, stack_bytes(sc))) { qsmrt_set_error("peel projection needs the persistent kernel"); return 1; }
@@ -1176,17 +1180,17 @@ int trv_peel_cast(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv, c
     a.src.o0 = f3{ o0[0], o0[1], o0[2] }; a.src.du = f3{ du[0], du[1], du[2] };
     a.src.dv = f3{ dv[0], dv[1], dv[2] }; a.src.dir = f3{ dir[0], dir[1], dir[2] };
     a.N = nu * nv; a.row_len = nu >= 8 && nu < (1ull << 32) ? (uint32_t)nu : 0; a.nslots = slots_for(a.N, a.row_len);
-    a.alive = alive; a.hitflag = hitflag; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
+    a.alive = alive; a.hitflag = hitflag; a.order = order; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
     return launch_trace5<5, false>(ts, a, stack_bytes(sc), st);
 }
 
-int trv_peel_update(const SceneView &sc, const uint32_t *order, uint8_t *alive, uint8_t *hitflag, int32_t *layer_of,
+int trv_peel_update(const float *verts, const uint32_t *idx, uint64_t ntris, uint8_t *alive, uint8_t *hitflag, int32_t *layer_of,
                     int layer, const float dir[3], double *sums, cudaStream_t st)
 {
-    if (sc.ntris == 0) return 0;
+    if (ntris == 0) return 0;
     float len = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
     f3 d = len > 0.0f ? f3{ dir[0] / len, dir[1] / len, dir[2] / len } : f3{ 0.0f, 0.0f, 0.0f };
-    k_peel_update<<<grid_for(sc.ntris, 256), 256, 0, st>>>(sc.tris, sc.ntris, order, alive, hitflag, layer_of, layer, d, sums);
+    k_peel_update<<<grid_for(ntris, 256), 256, 0, st>>>(verts, idx, ntris, alive, hitflag, layer_of, layer, d, sums);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

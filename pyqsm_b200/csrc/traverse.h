@@ -57,6 +57,6 @@ int trv_closest_points(TrvState &ts, const SceneView &sc, const float *pts, uint
 int trv_points_to_rays(const float *pts, float *rays, uint64_t N, cudaStream_t st);
 int trv_apply_sign(float *dist, const int32_t *counts, uint64_t N, cudaStream_t st);
 int trv_peel_cast(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv, const float o0[3], const float du[3], const float dv[3],
-                  const float dir[3], const uint8_t *alive, uint8_t *hitflag, cudaStream_t st);
-int trv_peel_update(const SceneView &sc, const uint32_t *order, uint8_t *alive, uint8_t *hitflag, int32_t *layer_of,
+                  const float dir[3], const uint32_t *order, const uint8_t *alive, uint8_t *hitflag, cudaStream_t st);
+int trv_peel_update(const float *verts, const uint32_t *idx, uint64_t ntris, uint8_t *alive, uint8_t *hitflag, int32_t *layer_of,
                     int layer, const float dir[3], double *sums, cudaStream_t st);

@@ -201,3 +201,60 @@ def test_current_device_is_left_alone(RS, tree):
     a = s.cast_rays(rays[:1000])
     del s
     assert torch.cuda.current_device() == 0 and a["t_hit"].shape == (1000,)
+
+
+def test_sliver_splitting_changes_the_tree_not_the_answers(RS, oracle_mod):
+    """Long thin triangles (create_cylinder sides) enter the LBVH as several references with tight slab boxes
+    (QSMRT_OPT_SPLIT_MAX / _ASPECT).  Every query answers exactly as without splitting -- duplicates of a triangle
+    are one hit -- and meshes without slivers are left alone."""
+    from pyqsm_b200 import environment as env
+    v, t = syn.qsm_tree_mesh(seed=5, n_cylinders=60)
+    o = oracle_mod.OracleScene()
+    o.add_triangles(v, t)
+    rays = np.concatenate([syn.materialize_grid(*syn.parallel_ray_grid(v.min(0), v.max(0), syn.sun_direction(45, 135), 400, 300), 400, 300),
+                           syn.random_rays(v.min(0), v.max(0), 20000, seed=2)])
+    ref = o.cast_rays(rays, 0)                                      # brute force: no tree at all
+    refc = o.count_intersections(rays, 0)
+    refl = o.list_intersections(rays, 0)
+    q = syn.random_rays(v.min(0), v.max(0), 3000, seed=4)[:, :3].copy()
+    refq = o.compute_closest_points(q, 0)
+    seen = {}
+    for split_max, leaf_max in ((8, 2), (1, 2), (16, 4), (3, 1)):
+        s = RS()
+        s.set_option("split_max", split_max)
+        s.set_option("leaf_max", leaf_max)
+        s.add_triangles(v, t)
+        a = s.cast_rays(rays, outputs="all")
+        for k in ref:
+            assert np.array_equal(a[k].numpy(), ref[k]), (split_max, k)
+        assert np.array_equal(s.count_intersections(rays).numpy(), refc)
+        assert np.array_equal(s.test_occlusions(rays, 0.25, 7.0).numpy(), o.test_occlusions(rays, 0.25, 7.0, 0))
+        l = s.list_intersections(rays)
+        for k in refl:
+            assert np.array_equal(l[k].numpy(), refl[k]), (split_max, k)
+        c = s.compute_closest_points(q)
+        for k in ("points", "geometry_ids", "primitive_ids", "primitive_uvs", "primitive_normals"):
+            assert np.array_equal(c[k].numpy(), refq[k]), (split_max, k)
+        st = s.stats()
+        seen[split_max] = st["num_references"]
+        assert st["num_triangles"] == t.shape[0] and (st["num_references"] > t.shape[0]) == (split_max > 1)
+        if split_max == 8:                                          # the peel driver keeps its flags per triangle, not per reference
+            sd = RS(output_device="cuda")
+            sd.add_triangles(v, t)
+            sp = RS(output_device="cuda")
+            sp.set_option("split_max", 1)
+            sp.add_triangles(v, t)
+            p1, p2 = env.peel_projection(sd, grid=(300, 300), max_layers=6), env.peel_projection(sp, grid=(300, 300), max_layers=6)
+            assert torch.equal(p1["layer_of"], p2["layer_of"]) and [x[0] for x in p1["layers"]] == [x[0] for x in p2["layers"]]
+            np.testing.assert_allclose(np.asarray(p1["layers"]), np.asarray(p2["layers"]), rtol=1e-12)    # areas: sums of double atomics
+            path = "/tmp/qsmrt_split_scene.bin"
+            s.save(path)
+            z = RS.load(path)
+            assert z.stats()["num_references"] == st["num_references"]
+            assert torch.equal(z.cast_rays(rays, outputs=("primitive_ids",))["primitive_ids"], a["primitive_ids"])
+    assert seen[16] >= seen[8] > seen[3] > seen[1] == t.shape[0]
+    vc, tc = syn.canopy_mesh(7, 20000)                              # compact leaf triangles: nothing to split
+    sc = RS()
+    sc.add_triangles(vc, tc)
+    sc.commit()
+    assert sc.stats()["num_references"] == tc.shape[0]

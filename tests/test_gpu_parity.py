@@ -140,6 +140,7 @@ def test_builder_matches_oracle(c1):
     v, t, o, _ = c1
     g = RaycastingScene()
     g.set_option("keep_binary_nodes", 1)                     # the product build keeps no binary node array
+    g.set_option("split_max", 1)                             # the canonical tree has one leaf per triangle: no sliver splitting
     g.add_triangles(v, t)
     g.commit()
     n = t.shape[0]
@@ -174,6 +175,7 @@ def _builder_topology(RS, oracle_mod, v, t, keep, opts=None):
     o.commit()
     g = RS()
     g.set_option("keep_binary_nodes", 1 if keep else 0)
+    g.set_option("split_max", 1)                             # compare with the oracle's one-leaf-per-triangle tree
     for name, value in (opts or {}).items():
         g.set_option(name, value)
     g.add_triangles(v, t)

@@ -59,13 +59,15 @@ if "cnt" in want:
     del r, sl
 if "c1" in want:
     v1, t1 = syn.qsm_tree_mesh(1)
-    for lm in (2, 4):
-        c = RaycastingScene(output_device="cuda"); c.set_option("leaf_max", lm); c.add_triangles(v1, t1); c.commit()
+    for sm, lm in ((8, 2), (1, 2), (8, 4), (1, 4), (4, 2), (16, 2)):
+        c = RaycastingScene(output_device="cuda"); c.set_option("leaf_max", lm); c.set_option("split_max", sm); c.add_triangles(v1, t1)
+        bms = min(c.commit() if k == 0 else (c.set_option("leaf_max", 1), c.set_option("leaf_max", lm), c.commit())[2] for k in range(3))
+        st = c.stats()
         for G in (1000, 4000):
             r = grid_rays(c, syn.sun_direction(45, 135), G, G); o = outs(G * G); cnt = torch.empty(G * G, dtype=torch.int32, device="cuda")
-            for var, rf in ((1, 12), (2, 12), (2, 6), (2, 20)):
-                c.set_option("traversal_variant", var); c.set_option("refill", rf)
+            for var in (1, 2):
+                c.set_option("traversal_variant", var)
                 ms = gtime(lambda: _lib.check(L.qsmrt_cast_rays_2d(c._h, P(r), G, G, *[P(x) for x in o], None)), 5)
                 mc = gtime(lambda: _lib.check(L.qsmrt_count_intersections(c._h, P(r), G * G, P(cnt), None)), 5)
-                print(f"{tag} C1 leaf_max {lm} grid {G} variant {var} refill {rf}: cast {G*G/ms/1e3:.0f} Mr/s ({ms:.3f} ms)  count {G*G/mc/1e3:.0f} Mr/s", flush=True)
+                print(f"{tag} C1 split_max {sm} leaf_max {lm} (refs {st['num_references']}, build {bms:.3f} ms) grid {G} variant {var}: cast {G*G/ms/1e3:.0f} Mr/s ({ms:.3f} ms)  count {G*G/mc/1e3:.0f} Mr/s ({mc:.3f} ms)", flush=True)
             del r, o, cnt
