@@ -8,12 +8,13 @@ hemisphere sweep) at 1/2/4/8 B200, plus the LBVH build time.
 A step = one solar angle: cast_rays over 16 777 216 rays (+ the per-triangle
 exposure accumulation the sweep keeps on the device).  N > 1 (torchrun, one
 rank per GPU): the mesh is broadcast once over NCCL, every rank builds the
-same LBVH; a step is then N solar angles, each dealt in blocks of 4 grid rows
-round-robin to the ranks, so every rank casts 16 777 216 rays per step and
-all ranks do the same work (weak scaling, no data-path collective); one
-all-reduce of the per-triangle exposure closes the timed region, and rank 0
-recomputes the whole sweep alone to check the all-reduced result
-(`multi_gpu_parity`).  Prints ONE JSON line (rank 0).
+same LBVH and casts one whole solar angle (16 777 216 rays) per step; the angle
+slots are dealt to the ranks longest-processing-time-first on the committed
+per-angle kernel times, so the ranks' totals agree although single angles
+differ by +-15 % (weak scaling, no data-path collective); one all-reduce of
+the per-triangle exposure closes the timed region, and rank 0 recomputes the
+whole timed sweep alone to check the all-reduced result (`multi_gpu_parity`).
+Prints ONE JSON line (rank 0).
 
 --impl reference times the CPU path instead: Open3D itself is not installable
 in this image (no network), so it is the repo's CPU oracle
@@ -112,20 +113,49 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
 
 
-def angles_for(rank, world, nsteps):
-    """Solar angles of one rank.  The 8 x 8 sweep is sharded by AZIMUTH: step s = 8 j + e casts elevation e at azimuth
-    index (rank * (8 / world) + j + e) mod 8.  The ranks of a step are 360 / world degrees apart -- for 2 and 4 ranks
-    the same view of the (x/y symmetric) canopy and its ray grid, i.e. equal work per step -- and every rank walks
-    through all azimuths as the elevation changes, so axis-aligned and diagonal views (a few per cent apart in cost)
-    are mixed evenly in any run of steps.  N in {1, 2, 4, 8} ranks partition the 64 angles exactly."""
+def angle_costs():
+    """Relative cost of every solar angle of the sweep (kernel ms, index = elevation * 8 + azimuth) from the committed
+    per-angle profile of the cast kernel (tools/profile_angles.py); None if the profile is not there."""
+    from pyqsm_b200 import synthetic as syn
+    path = os.path.join(ROOT, "profiles", "r02_cast_rays_profile.json")
+    try:
+        rows = json.load(open(path))["angles"]
+        key = {(round(r["elevation"], 3), round(r["azimuth"], 3)): float(r["kernel_ms"]) for r in rows}
+        return [key[(round(e, 3), round(a, 3))] for e, a in syn.hemisphere_sweep()]
+    except Exception:
+        return None
+
+
+def schedule(world, nsteps, warmup=0):
+    """Solar angles of every rank: [world][nsteps] (elevation, azimuth).  Whole angles per rank (one 16M-ray grid per
+    step and rank: weak scaling, no direction mixing inside a launch, which costs ~7 %: profiles/r02_mix.txt).  The
+    world x nsteps angle slots walk the 8 x 8 sweep with stride 27 (coprime with 64: every window of the walk mixes
+    elevations and azimuths evenly, and any 64 consecutive slots are the whole sweep).  The first `warmup` steps take
+    slots in walk order; the timed slots are dealt longest-processing-time-first on the committed per-angle kernel
+    times (angle_costs), every rank getting the same number, so the ranks' totals agree to a fraction of a per cent
+    although single angles differ by +-15 %.  Without the profile the deal is round-robin in walk order."""
     from pyqsm_b200 import synthetic as syn
     sweep = syn.hemisphere_sweep()                      # index = elevation * 8 + azimuth
-    stride = max(1, 8 // world)
-    out = []
-    for s in range(nsteps):
-        e, j = s % 8, s // 8
-        out.append(sweep[e * 8 + (rank * stride + j + e) % 8])
-    return out
+    walk = [(27 * g) % 64 for g in range(world * nsteps)]
+    per_rank = [[walk[s * world + r] for s in range(warmup)] for r in range(world)]
+    timed = walk[world * warmup:]
+    cost = angle_costs()
+    k = nsteps - warmup
+    if cost is None or world == 1:
+        for r in range(world):
+            per_rank[r] += timed[r::world]
+    else:
+        load, mine = [0.0] * world, [[] for _ in range(world)]
+        for idx in sorted(timed, key=lambda i: (-cost[i], i)):
+            r = min((x for x in range(world) if len(mine[x]) < k), key=lambda x: (load[x], x))
+            mine[r].append(idx); load[r] += cost[idx]
+        for r in range(world):
+            per_rank[r] += sorted(mine[r], key=lambda i: timed.index(i))
+    return [[sweep[i] for i in seq] for seq in per_rank]
+
+
+def angles_for(rank, world, nsteps, warmup=0):
+    return schedule(world, nsteps, warmup)[rank]
 
 
 # --------------------------------------------------------------- reference arm
@@ -144,7 +174,7 @@ def run_reference(args):
     build_ms = (time.perf_counter() - t0) * 1e3
     lo, hi = v.min(0), v.max(0)
     stride = 8                                      # 2M of the angle's 16M rays per step
-    angs = angles_for(0, 1, args.warmup + args.steps)
+    angs = angles_for(0, 1, args.warmup + args.steps, args.warmup)
     ray_sets = [syn.materialize_grid(*syn.parallel_ray_grid(lo, hi, syn.sun_direction(e, a), GRID, GRID), GRID, GRID)[::stride].copy()
                 for e, a in angs[: min(len(angs), 4)]]
     n = ray_sets[0].shape[0]
@@ -173,30 +203,13 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------- our arm
-ROW_BLOCK = 4                     # rows per interleave block = rows of one 8 x 4 ray tile
-
-
-def step_angle_set(world, s, nsteps):
-    """The `world` solar angles cast in global step s (one per rank in the schedule of angles_for)."""
-    return [angles_for(k, world, nsteps)[s] for k in range(world)]
-
-
-def fill_step_rays(L, buf, tmp, lo, hi, angle_set, rank, world, stream):
-    """Rank `rank`'s 16M rays of one step.  The step's `world` angles are each cut into blocks of ROW_BLOCK grid rows
-    and dealt round-robin to the ranks (SURVEY 8e "tile interleaving"): every rank casts 1/world of EVERY angle of
-    the step, so all ranks do statistically identical work per step whatever the angles cost.  buf is
-    [world][GRID / world rows][GRID][6]; a block of 4 rows is exactly the rows of an 8 x 4 ray tile."""
+def fill_rays(L, buf, lo, hi, angle, stream):
+    """The 16M parallel rays of one solar angle, generated on the device into `buf`."""
     import ctypes as C
     from pyqsm_b200 import synthetic as syn, _lib
-    P = lambda x: C.c_void_p(x.data_ptr())
     F3 = lambda x: (C.c_float * 3)(*[float(y) for y in x])
-    nb = GRID // ROW_BLOCK // world
-    for k, (el, az) in enumerate(angle_set):
-        g = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), GRID, GRID)
-        dst = buf if world == 1 else tmp
-        _lib.check(L.qsmrt_gen_parallel_rays(P(dst), GRID, GRID, F3(g[0]), F3(g[1]), F3(g[2]), F3(g[3]), stream))
-        if world > 1:
-            buf.view(world, nb, ROW_BLOCK * GRID * 6)[k].copy_(tmp.view(nb, world, ROW_BLOCK * GRID * 6)[:, rank])
+    g = syn.parallel_ray_grid(lo, hi, syn.sun_direction(*angle), GRID, GRID)
+    _lib.check(L.qsmrt_gen_parallel_rays(C.c_void_p(buf.data_ptr()), GRID, GRID, F3(g[0]), F3(g[1]), F3(g[2]), F3(g[3]), stream))
 
 
 def measure_read_gbs(L, dev, mbytes, reps):
@@ -263,8 +276,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if GRID % (ROW_BLOCK * world):
-        raise SystemExit(f"--gpus {world}: the {GRID}-row grid does not split into blocks of {ROW_BLOCK} rows per rank")
 
     def gather_f64(vals):
         """[world][len(vals)] float64 on every rank."""
@@ -310,14 +321,13 @@ def run_ours(args):
     nsteps = args.warmup + args.steps
     P = lambda x: C.c_void_p(x.data_ptr())
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    # inputs resident in HBM before the timed region: one ray buffer per step (a ring of 16)
-    nbuf = min(nsteps, 16)
+    # inputs resident in HBM before the timed region: one 384 MB ray buffer per step (at most the 64 angles of the sweep)
+    plan = schedule(world, nsteps, args.warmup)
+    angs = plan[rank]
+    nbuf = min(nsteps, 64)
     rays = [torch.empty(n, 6, dtype=torch.float32, device=dev) for _ in range(nbuf)]
-    tmp = torch.empty(n, 6, dtype=torch.float32, device=dev) if world > 1 else None
-    buf_step = {}
-    for s in range(nsteps - nbuf, nsteps):              # the ring as it stands when the timed steps run
-        fill_step_rays(L, rays[s % nbuf], tmp, lo, hi, step_angle_set(world, s, nsteps), rank, world, stream)
-        buf_step[s % nbuf] = s
+    for s in range(max(0, nsteps - nbuf), nsteps):
+        fill_rays(L, rays[s % nbuf], lo, hi, angs[s], stream)
     t_hit = torch.empty(n, dtype=torch.float32, device=dev)
     gid = torch.empty(n, dtype=torch.uint32, device=dev)
     pid = torch.empty(n, dtype=torch.uint32, device=dev)
@@ -331,9 +341,6 @@ def run_ours(args):
     def accumulate(into):
         _lib.check(L.qsmrt_accumulate_hits(scene._h, P(gid), P(pid), n, P(into), stream))
 
-    # the step whose rays each timed step actually casts (with more steps than ring slots the early ones see the
-    # rays of a later step of the schedule: same work, and the parity check below follows the same list)
-    cast_steps = [buf_step[(args.warmup + s) % nbuf] for s in range(args.steps)]
     for s in range(args.warmup):
         cast(rays[s % nbuf]); accumulate(exposure)
     exposure.zero_()
@@ -375,17 +382,15 @@ def run_ours(args):
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         if rank == 0:
             ref = torch.zeros_like(exposure)
-            full = tmp
-            F3 = lambda x: (C.c_float * 3)(*[float(y) for y in x])
-            for s in cast_steps:
-                for el, az in step_angle_set(world, s, nsteps):
-                    g = syn.parallel_ray_grid(lo, hi, syn.sun_direction(el, az), GRID, GRID)
-                    _lib.check(L.qsmrt_gen_parallel_rays(P(full), GRID, GRID, F3(g[0]), F3(g[1]), F3(g[2]), F3(g[3]), stream))
+            full = torch.empty(n, 6, dtype=torch.float32, device=dev)
+            for r in range(world):
+                for s in range(args.warmup, nsteps):
+                    fill_rays(L, full, lo, hi, plan[r][s], stream)
                     cast(full); accumulate(ref)
             ok[0] = 1 if torch.equal(ref, exposure) else 0
+            del full
         dist.broadcast(ok, 0)
         parity = "bit-identical" if int(ok.item()) == 1 else "MISMATCH"
-        del tmp
 
     # ---- e2e: the public API with HOST buffers (pinned), copies inside the timed region
     e2e_steps = max(2, min(args.steps, 5))
@@ -456,7 +461,7 @@ def run_ours(args):
         peak_hbm, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak_hbm, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    timed_angles = [a for s in cast_steps for a in step_angle_set(world, s, nsteps)]
+    timed_angles = angs[args.warmup:]
     b_ray, nn, nt = b_ray_for(timed_angles)
     k_ms = float(np.mean(kern_ms))
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -537,8 +542,9 @@ def run_ours(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "triangles": ntri, "rays_per_step": n * world, "rays_per_step_per_gpu": n,
-                   "parallelism": f"replicated scene; a step = {world} solar angle(s), each cut into blocks of {ROW_BLOCK} grid rows dealt "
-                                  f"round-robin to the {world} rank(s) (every rank casts 1/{world} of every angle of the step)",
+                   "parallelism": f"replicated scene; one whole solar angle (16M rays) per step and rank over {world} rank(s); the timed "
+                                  "angle slots (a stride-27 walk of the 8 x 8 sweep) are dealt to the ranks longest-processing-time-"
+                                  "first on the committed per-angle kernel times",
                    "l2": "no explicit flush: each step reads 384 MB of rays and writes 512 MB of results (> 126 MB L2), "
                          "a different ray buffer every step; the BVH (scene) stays warm across the sweep by design",
                    "hit_fraction_last_step": hit_fraction},

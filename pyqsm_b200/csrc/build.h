@@ -29,7 +29,7 @@ struct LbvhBuildArgs {
     uint64_t   *keys, *keys_tmp;    // [L]  (L = nrefs when refs, else ntris; likewise below) the sorted arrays end up in (keys, order) or, when *result_in_tmp, in
     uint32_t   *order, *order_tmp;  // [T]  (keys_tmp, order_tmp): the caller keeps that pair and recycles the other
     int        *result_in_tmp;
-    uint32_t   *sort_scratch;       // lbvh_sort_scratch_bytes(T)
+    uint32_t   *sort_scratch;       // lbvh_sort_scratch_bytes(L); counters | flags | sort_scratch are ONE block (lbvh_zero_block_bytes), in that order
     BNode      *bnodes;             // [2T-1] hand-over boxes of the global phase; the complete binary tree iff keep_bnodes
     int         keep_bnodes;
     unsigned long long *flags;      // [T-1] hand-over slot of each split (k_hierarchy_refit_emit)
@@ -37,12 +37,13 @@ struct LbvhBuildArgs {
     TNode      *tnodes;             // [max(T-1,1)]
     QNode      *qnodes;             // [max(T-1,1)] quantised twin of tnodes
     void       *climb_work;         // lbvh_climb_bytes(T): subtrees handed to the climb kernel
-    unsigned long long *counters;   // [5] nodes emitted, leaves emitted, binary tree height, climb list length, sort overflow
+    unsigned long long *counters;   // [8] (the start of the zero block) nodes emitted, leaves emitted, binary tree height, climb list length, sort overflow
     int         full_sort;          // all eight radix passes (after a sort overflow: a run of > 64 keys equal in their top 40 bits)
     cudaEvent_t ev_sort0, ev_sort1; // optional
 };
 
 size_t lbvh_sort_scratch_bytes(uint64_t n);
+size_t lbvh_zero_block_bytes(uint64_t n);
 size_t lbvh_climb_bytes(uint64_t n);
 int lbvh_radix_sort(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp,
                     uint64_t n, uint32_t *scratch, cudaStream_t st, unsigned long long *overflow, int sort_variant, bool hist_done,

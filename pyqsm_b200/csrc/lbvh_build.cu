@@ -219,13 +219,17 @@ __device__ __forceinline__ uint64_t spread21(uint32_t x)
 // saves the separate histogram kernel and its re-read of the keys (shift0 / npass as in the sort; ghist zeroed).
 __global__ void __launch_bounds__(256)
 k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint64_t n,
-         BuildParams *__restrict__ bp, uint64_t *__restrict__ keys, uint32_t *__restrict__ order,
+         const BuildParams bpv /* by value: finished on the host */, BuildParams *__restrict__ bp_out, float *__restrict__ diag_sum,
+         uint64_t *__restrict__ keys, uint32_t *__restrict__ order,
          uint32_t *__restrict__ ghist /* [npass][256], may be null */, int shift0, int npass,
          const RefBox *__restrict__ refs /* non-null: n references (split slivers) instead of n triangles */)
 {
     __shared__ float wsum[8];
     __shared__ uint32_t h[8][256];
     if (ghist) { for (int i = threadIdx.x; i < npass * 256; i += 256) (&h[0][0])[i] = 0; __syncthreads(); }
+    // the device copy of the parameters the later kernels read: written here instead of by a separate upload
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bp_out = bpv;
+    const BuildParams *bp = &bpv;
     const float pad = bp->pad;
     float diag = 0.0f;
 #pragma unroll 2
@@ -265,7 +269,7 @@ k_morton(const float *__restrict__ verts, const uint32_t *__restrict__ idx, uint
     if (threadIdx.x == 0) {
         float s = 0.0f;
         for (int k = 0; k < 8; ++k) s += wsum[k];
-        atomicAdd(&bp->leaf_diag_sum, s);
+        atomicAdd(diag_sum, s);
     }
     if (ghist)      // wsum's barrier above ordered the shared-memory atomics of all warps
         for (int i = threadIdx.x; i < npass * 256; i += 256) { const uint32_t v = (&h[0][0])[i]; if (v) atomicAdd(&ghist[i], v); }
@@ -639,7 +643,7 @@ struct RefitOut {
 #define QSMRT_RF_BLOCK 256
 #endif
 #ifndef QSMRT_RF_MINB
-#define QSMRT_RF_MINB 1
+#define QSMRT_RF_MINB 5
 #endif
 constexpr int RF_BLOCK = QSMRT_RF_BLOCK;      // leaves per block (A/B: make EXTRA=-DQSMRT_RF_BLOCK=128)
 constexpr int RF_WARPS = RF_BLOCK / 32;
@@ -773,7 +777,8 @@ k_hierarchy_refit_emit(const float *__restrict__ verts, const uint32_t *__restri
     // The 32-byte nodes widen every box by 3 grid cells per side: use them when that is small against a leaf
     // (mean leaf diagonal from k_morton).  Every thread evaluates the same expression; thread 0 records it.
     const float max_cell = fmaxf(bp->cell[0], fmaxf(bp->cell[1], bp->cell[2]));
-    const bool use_q = 6.0f * max_cell <= quant_frac * (bp->leaf_diag_sum / (float)n);
+    // (mean leaf diagonal: k_morton's sum, kept in the zeroed counter block: counters[5] holds a float)
+    const bool use_q = 6.0f * max_cell <= quant_frac * (*reinterpret_cast<const float *>(counters + 5) / (float)n);
     if (i == 0) bp->use_q = use_q ? 1 : 0;
     const RefitOut R{ bn, tn, qn, bp, n, leaf_max, use_q, keep_bn != 0 };
     const RefitQueue Q{ s_qf, s_qi, bfirst, blast };
@@ -1023,6 +1028,9 @@ size_t lbvh_climb_items(uint64_t n) { return (size_t)(n / 4 + 1024); }
 size_t lbvh_climb_bytes(uint64_t n) { return lbvh_climb_items(n) * sizeof(ClimbItem); }
 
 
+// counters (64 B) | flags [n - 1] | sort scratch: one allocation, cleared by one memset at the start of the build
+size_t lbvh_zero_block_bytes(uint64_t n) { return 64 + (size_t)n * sizeof(unsigned long long) + lbvh_sort_scratch_bytes(n); }
+
 size_t lbvh_sort_clear_bytes(uint64_t n)
 {
     const uint64_t os_tiles = (n + OS_TILE - 1) / OS_TILE;
@@ -1148,18 +1156,15 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     const uint64_t n = A.refs ? A.nrefs : A.ntris;          // leaves of the tree: references when slivers were split
     const int B = 256;
     const unsigned gN = (unsigned)((n + B - 1) / B);
-    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 5 * sizeof(unsigned long long), st));
-    // the scene bounds were combined on the host from the geometries' registration-time statistics: upload the
-    // finished parameters (72 bytes), clear the sort's look-back status / histograms, and go straight to the keys
-    CUDA_TRY(cudaMemcpyAsync(A.params, A.params_host, sizeof(BuildParams), cudaMemcpyHostToDevice, st));
+    // ONE clear for everything the build accumulates into: the counters, the global-phase flags of the hierarchy and
+    // the sort's look-back status / histograms / tile counters sit in one block (lbvh_zero_block_bytes); the finished
+    // parameters travel to k_morton by value, which also stores the device copy the later kernels read
     const bool onesweep = A.sort_variant == 1;
     const bool top_only = !A.full_sort;
-    uint32_t *ghist = nullptr;
-    if (onesweep) {
-        CUDA_TRY(cudaMemsetAsync(A.sort_scratch, 0, lbvh_sort_clear_bytes(n), st));
-        ghist = A.sort_scratch + 8ull * ((n + OS_TILE - 1) / OS_TILE) * 256;
-    }
-    k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, A.params, A.keys, A.order, ghist,
+    CUDA_TRY(cudaMemsetAsync(A.counters, 0, 64 + (n > 1 ? n - 1 : 0) * sizeof(unsigned long long) + (onesweep ? lbvh_sort_clear_bytes(n) : 0), st));
+    uint32_t *ghist = onesweep ? A.sort_scratch + 8ull * ((n + OS_TILE - 1) / OS_TILE) * 256 : nullptr;
+    k_morton<<<min(gN, 148u * 16u), B, 0, st>>>(A.verts, A.idx, n, *A.params_host, A.params, reinterpret_cast<float *>(A.counters + 5),
+                                                 A.keys, A.order, ghist,
                                                  top_only ? sort_shift0(n) : 0, top_only ? sort_passes(n) : 8,
                                                  static_cast<const RefBox *>(A.refs));
     CUDA_TRY(cudaGetLastError());
@@ -1171,7 +1176,6 @@ int lbvh_build(const LbvhBuildArgs &A, cudaStream_t st)
     const uint64_t *keys = in_tmp ? A.keys_tmp : A.keys;        // the caller keeps whichever pair holds the sorted arrays
     uint32_t *order = in_tmp ? A.order_tmp : A.order;
     if (A.ev_sort1) CUDA_TRY(cudaEventRecord(A.ev_sort1, st));
-    if (n > 1) CUDA_TRY(cudaMemsetAsync(A.flags, 0, (n - 1) * sizeof(unsigned long long), st));
     const int keep = (A.keep_bnodes || n == 1) ? 1 : 0;
     const unsigned work_cap = A.climb_capacity > 0 ? std::min<unsigned>((unsigned)A.climb_capacity, (unsigned)lbvh_climb_items(n))
                                                        : (unsigned)lbvh_climb_items(n);

@@ -336,13 +336,14 @@ SceneView view_of(qsmrt_scene *s)
 
 // Scratch of one commit; everything here goes back to the block cache on every exit path.
 struct CommitScratch {
-    uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr, *sort_scratch = nullptr;
-    unsigned long long *flags = nullptr, *counters = nullptr; uint32_t *climb = nullptr;
+    uint64_t *keys_tmp = nullptr; uint32_t *order_tmp = nullptr;
+    char *zero_block = nullptr;         // counters | hierarchy flags | sort scratch: cleared by one memset (lbvh_zero_block_bytes)
+    uint32_t *climb = nullptr;
     int32_t *split_cnt = nullptr; int64_t *ref_off = nullptr; char *scan_scratch = nullptr, *refs = nullptr;     // sliver splitting
     cudaEvent_t e0 = nullptr, e1 = nullptr, es0 = nullptr, es1 = nullptr;
     ~CommitScratch()
     {
-        dfree(keys_tmp); dfree(order_tmp); dfree(sort_scratch); dfree(flags); dfree(counters); dfree(climb);
+        dfree(keys_tmp); dfree(order_tmp); dfree(zero_block); dfree(climb);
         dfree(split_cnt); dfree(ref_off); dfree(scan_scratch); dfree(refs);
         if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (es0) cudaEventDestroy(es0); if (es1) cudaEventDestroy(es1);
     }
@@ -371,11 +372,14 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
     s->nleaves = Lv;
     // allocate everything before the timed region
     if (dmalloc(&s->keys, Lv) || dmalloc(&cs.keys_tmp, Lv) || dmalloc(&s->order, Lv) || dmalloc(&cs.order_tmp, Lv) ||
-        dmalloc(&cs.sort_scratch, lbvh_sort_scratch_bytes(Lv) / sizeof(uint32_t)) ||
-        dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * Lv - 1) || dmalloc(&cs.flags, Lv) || dmalloc(&s->tris, Lv) ||
+        dmalloc(&cs.zero_block, lbvh_zero_block_bytes(Lv)) ||
+        dmalloc(&s->params, 1) || dmalloc(&s->bnodes, 2 * Lv - 1) || dmalloc(&s->tris, Lv) ||
         dmalloc(&s->tnodes, std::max<uint64_t>(Lv - 1, 1)) || dmalloc(&s->qnodes, std::max<uint64_t>(Lv - 1, 1)) ||
-        dmalloc(&cs.counters, 5) || dmalloc(&cs.climb, lbvh_climb_bytes(Lv) / sizeof(uint32_t)))
+        dmalloc(&cs.climb, lbvh_climb_bytes(Lv) / sizeof(uint32_t)))
         return 1;
+    unsigned long long *const counters = reinterpret_cast<unsigned long long *>(cs.zero_block);
+    unsigned long long *const flags = counters + 8;
+    uint32_t *const sort_scratch = reinterpret_cast<uint32_t *>(flags + (Lv > 1 ? Lv - 1 : 0));
     if (split && (dmalloc(&cs.split_cnt, T) || dmalloc(&cs.ref_off, T + 1) || dmalloc(&cs.scan_scratch, trv_scan_scratch_bytes(T)) ||
                   dmalloc(&cs.refs, lbvh_ref_bytes(R))))
         return 1;
@@ -400,7 +404,7 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
     BuildParams bp_host;
     lbvh_finalize_params(slo, shi, &bp_host);
     if (split) {        // per-triangle slab counts -> offsets -> the references' boxes
-        if (lbvh_split_count(s->verts, s->idx, T, s->bopt.split_max, s->bopt.split_aspect, cs.split_cnt, cs.counters, st) ||
+        if (lbvh_split_count(s->verts, s->idx, T, s->bopt.split_max, s->bopt.split_aspect, cs.split_cnt, counters + 6, st) ||
             trv_exclusive_scan(cs.split_cnt, T, cs.ref_off, cs.scan_scratch, st) ||
             lbvh_split_emit(s->verts, s->idx, T, s->bopt.split_max, s->bopt.split_aspect, cs.ref_off, cs.refs, st))
             return 1;
@@ -413,10 +417,10 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
     A.quant_frac = s->bopt.quant_frac;
     A.verts = s->verts; A.idx = s->idx; A.ntris = T; A.geom_offsets = s->goff; A.ngeoms = G;
     A.params = s->params; A.keys = s->keys; A.keys_tmp = cs.keys_tmp;
-    A.order = s->order; A.order_tmp = cs.order_tmp; A.sort_scratch = cs.sort_scratch;
-    A.bnodes = s->bnodes; A.flags = cs.flags; A.keep_bnodes = s->bopt.keep_bnodes ? 1 : 0; A.climb_work = cs.climb;
+    A.order = s->order; A.order_tmp = cs.order_tmp; A.sort_scratch = sort_scratch;
+    A.bnodes = s->bnodes; A.flags = flags; A.keep_bnodes = s->bopt.keep_bnodes ? 1 : 0; A.climb_work = cs.climb;
     A.qnodes = s->qnodes;
-    A.tris = s->tris; A.tnodes = s->tnodes; A.counters = cs.counters; A.ev_sort0 = cs.es0; A.ev_sort1 = cs.es1;
+    A.tris = s->tris; A.tnodes = s->tnodes; A.counters = counters; A.ev_sort0 = cs.es0; A.ev_sort1 = cs.es1;
     unsigned long long cnt[5] = {};
     // The sort normally runs over the top 40 key bits plus an exact fix-up of short runs; a scene with a run of more
     // than 64 triangles in one 2^-13 cell (thousands of coincident triangles) reports an overflow and is built again
@@ -426,7 +430,7 @@ int build_scene(qsmrt_scene *s, cudaStream_t st, CommitScratch &cs)
         if (lbvh_build(A, st)) return 1;
         CUDA_TRY(cudaEventRecord(cs.e1, st));
         CUDA_TRY(cudaEventSynchronize(cs.e1));
-        CUDA_TRY(cudaMemcpy(cnt, cs.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(cnt, counters, sizeof(cnt), cudaMemcpyDeviceToHost));
         if (!cnt[4]) break;
     }
     s->stats.full_sort = (uint32_t)A.full_sort;
@@ -736,6 +740,8 @@ int qsmrt_scene_set_option(qsmrt_scene *s, int key, double value)
     case QSMRT_OPT_NODE_PATH: if (iv < 0 || iv > 2) FAIL("node path must be 0, 1 or 2"); t.node_path = iv; break;
     case QSMRT_OPT_CP_WARP_MAX: t.cp_warp_max = std::max(iv, 0); break;
     case QSMRT_OPT_CTAS_PER_SM: t.ctas_per_sm = std::max(iv, 0); break;
+    case QSMRT_OPT_TILE_ORDER: t.tile_order = iv != 0; break;
+    case QSMRT_OPT_COUNT_SET: if (iv < 4 || iv > 32) FAIL("count_set must be in 4..32"); t.count_set = iv; break;
     default: FAIL("unknown option %d", key);
     }
     if (rebuild && s->committed) { SCENE_ENTER(s); free_build(s); }     // the next query builds with the new option
@@ -763,6 +769,8 @@ int qsmrt_scene_get_option(qsmrt_scene *s, int key, double *value)
     case QSMRT_OPT_NODE_PATH: *value = t.node_path; break;
     case QSMRT_OPT_CP_WARP_MAX: *value = t.cp_warp_max; break;
     case QSMRT_OPT_CTAS_PER_SM: *value = t.ctas_per_sm; break;
+    case QSMRT_OPT_TILE_ORDER: *value = t.tile_order; break;
+    case QSMRT_OPT_COUNT_SET: *value = t.count_set; break;
     default: FAIL("unknown option %d", key);
     }
     return 0;

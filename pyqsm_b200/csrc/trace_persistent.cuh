@@ -139,6 +139,8 @@ struct TraceArgs {
     int refill, want, tri_min, node_path;
     int depth;          // stack entries per thread; the MODE 2 hit set starts behind the stack in shared memory
     int multi_geom;     // > 1 geometry: the set also keeps geometry ids
+    int row_major;      // 2-D batches: tile rows in memory order instead of from the middle outwards
+    int set_cap;        // MODE 2 / 6: entries of the per-lane hit set (shared memory: fewer entries, more resident CTAs)
 };
 
 #ifndef QSMRT_TRACE_MINB
@@ -172,7 +174,7 @@ constexpr int TR_TRI_STEPS = 2;      // triangle tests per phase vote (1: -1.5 %
 // Widening every slab interval by 2^-20 of its own t (8 ulp) keeps the test conservative at any distance; the two
 // multiplications per child are immediate-form FMULs on the FMA pipe, which this ALU-bound loop leaves idle.
 constexpr float SLAB_NEAR = 0.99999905f, SLAB_FAR = 1.00000095f;
-constexpr int CNT_SET = 32;     // distinct (geometry, t) pairs a lane can hold before it defers to the exact slow path
+constexpr int CNT_SET = 32;     // largest hit set: distinct (geometry, t) pairs a lane can hold before it defers to the exact slow path (TraceArgs.set_cap <= CNT_SET)
 
 __device__ __forceinline__ void ld256u(const void *p, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
                                        uint32_t &w4, uint32_t &w5, uint32_t &w6, uint32_t &w7)
@@ -221,7 +223,7 @@ k_trace5(const TraceArgs A)
     int lcur = 0;
     unsigned n_node = 0, n_tri = 0;
     float *const tset = reinterpret_cast<float *>(sstack + A.depth * TR_BLOCK) + threadIdx.x;      // MODE 2
-    uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + CNT_SET) * TR_BLOCK) + threadIdx.x;
+    uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + A.set_cap) * TR_BLOCK) + threadIdx.x;
     int cnt = 0; bool overflow = false;
     long long lbase = 0;                                        // MODE 6: first output slot of this lane's ray
     uint32_t snx = 0x7610u, sny = 0x7610u, snz = 0x7610u;       // QUANT: per-axis "near plane" byte selectors
@@ -294,13 +296,13 @@ k_trace5(const TraceArgs A)
                     bool ok = slot < A.nslots;
                     if (A.src.kind == 3) {          // sweep: slot -> (grid, slot inside the grid)
                         const uint64_t a = fast_div(slot, A.src.per_grid_slots);
-                        ok = ok && ray_index_of_slot(slot - a * A.src.per_grid_slots, A.src.per_grid_rays, A.row_len, i, gx, gy);
+                        ok = ok && ray_index_of_slot(slot - a * A.src.per_grid_slots, A.src.per_grid_rays, A.row_len, i, gx, gy, A.row_major != 0);
                         i += a * A.src.per_grid_rays;
-                    } else ok = ok && ray_index_of_slot(slot, A.N, A.row_len, i, gx, gy);
+                    } else ok = ok && ray_index_of_slot(slot, A.N, A.row_len, i, gx, gy, A.row_major != 0);
                     if (MODE == 6 && ok) {          // nothing to list (or too much for the on-chip set: k_list_slow does those)
                         lbase = A.splits[i];
                         const long long k = A.splits[i + 1] - lbase;
-                        ok = k > 0 && k <= CNT_SET;
+                        ok = k > 0 && k <= A.set_cap;
                     }
                     if (ok) {
                         r = source_ray(A.src, i, gx, gy, A.row_len != 0);
@@ -441,7 +443,7 @@ k_trace5(const TraceArgs A)
                         for (int q = 0; q < cnt; ++q)
                             if (tset[q * TR_BLOCK] == tt && (!A.multi_geom || gset[q * TR_BLOCK] == pg)) at = q;
                         if (at < 0) {
-                            if (cnt < CNT_SET) { tset[cnt * TR_BLOCK] = tt; if (A.multi_geom) gset[cnt * TR_BLOCK] = pg; at = cnt; ++cnt; }
+                            if (cnt < A.set_cap) { tset[cnt * TR_BLOCK] = tt; if (A.multi_geom) gset[cnt * TR_BLOCK] = pg; at = cnt; ++cnt; }
                             else { overflow = true; cur = TR_SENTINEL; lcur = 0; }          // the fix-up kernel recounts this ray
                             if (MODE == 6 && !overflow) A.l_prim[lbase + at] = QSMRT_INVALID;   // so the first record always wins below
                         }

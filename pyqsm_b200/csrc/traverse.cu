@@ -216,7 +216,8 @@ __device__ __forceinline__ uint64_t centre_out(uint64_t k, uint64_t tile_rows)
     return (k & 1u) ? mid - 1u - (k >> 1) : mid + (k >> 1);
 }
 
-__device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uint32_t row_len, uint64_t &i, uint32_t &x, uint64_t &y)
+__device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uint32_t row_len, uint64_t &i, uint32_t &x, uint64_t &y,
+                                                  bool row_major = false)
 {
     if (row_len == 0) { i = slot; return slot < N; }
     const uint32_t lane = (uint32_t)(slot & 31u);
@@ -226,7 +227,7 @@ __device__ __forceinline__ bool ray_index_of_slot(uint64_t slot, uint64_t N, uin
     uint64_t ty = (tile >> 32) == 0 ? (uint64_t)((uint32_t)tile / tiles_x) : tile / tiles_x;
     const uint32_t tx = (uint32_t)(tile - ty * tiles_x);
     const uint64_t rows = (N >> 32) == 0 ? (uint64_t)((uint32_t)N / row_len) : N / row_len;
-    ty = centre_out(ty, (rows + 3u) >> 2);
+    if (!row_major) ty = centre_out(ty, (rows + 3u) >> 2);
     x = tx * 8u + (lane & 7u);
     y = ty * 4u + (lane >> 3);
     i = y * row_len + x;
@@ -899,6 +900,7 @@ template <int MODE, bool COUNTERS>
 int launch_trace5(TrvState &ts, TraceArgs &a, size_t smem, cudaStream_t st)
 {
     a.refill = ts.opt.refill; a.want = std::max(1, ts.opt.want); a.tri_min = std::max(1, ts.opt.tri_min);
+    a.row_major = ts.opt.tile_order == 0;
     a.node_path = a.sc.node_tex ? ts.opt.node_path : 0;
     if (next_cursor(ts, &a.cursor, st)) return 1;
     if (a.sc.qnodes) return launch_trace5_q<MODE, COUNTERS, true>(ts, a, smem, st);
@@ -961,11 +963,12 @@ int trv_count(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, 
 {
     if (N == 0) return 0;
     const int depth = (int)sc.height + 2;
-    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * CNT_SET) * TR_BLOCK * sizeof(int);
+    const int set_cap = std::min(std::max(ts.opt.count_set, 4), CNT_SET);
+    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * set_cap) * TR_BLOCK * sizeof(int);
     if (use_v5(ts, sc, smem)) {
         TraceArgs a{};
         a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
-        a.counts = out; a.depth = depth; a.multi_geom = ngeoms > 1;
+        a.counts = out; a.depth = depth; a.multi_geom = ngeoms > 1; a.set_cap = set_cap;
         if (launch_trace5<2, false>(ts, a, smem, st)) return 1;
         const int sms = ts.sms ? ts.sms : 148;
         k_count_fix<<<(unsigned)std::min<uint64_t>(grid_for(N, TR_BLOCK), (uint64_t)sms * 8), TR_BLOCK, 0, st>>>(sc, rays, N, out);
@@ -998,15 +1001,16 @@ int trv_list_fill(TrvState &ts, const SceneView &sc, const float *rays, uint64_t
 {
     if (N == 0 || sc.ntris == 0) return 0;
     const int depth = (int)sc.height + 2;
-    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * CNT_SET) * TR_BLOCK * sizeof(int);
+    const int set_cap = std::min(std::max(ts.opt.count_set, 4), CNT_SET);
+    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * set_cap) * TR_BLOCK * sizeof(int);
     int max_fast = 0;
     if (use_v5(ts, sc, smem)) {
         TraceArgs a{};
         a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
-        a.depth = depth; a.multi_geom = ngeoms > 1;
+        a.depth = depth; a.multi_geom = ngeoms > 1; a.set_cap = set_cap;
         a.splits = splits; a.l_t = t_hit; a.l_geom = geom; a.l_prim = prim; a.l_uv = reinterpret_cast<float2 *>(uv);
         if (launch_trace5<6, false>(ts, a, smem, st)) return 1;
-        max_fast = CNT_SET;
+        max_fast = set_cap;
     }
     k_list_finish<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, splits, max_fast, ray_ids, t_hit, geom, prim,
                                                             reinterpret_cast<float2 *>(uv));

@@ -51,7 +51,12 @@ cast(mine, G, rows, out); torch.cuda.synchronize()
 if world > 1: dist.barrier()
 e0.record(); cast(mine, G, rows, out); e1.record(); torch.cuda.synchronize()
 cast_ms = e0.elapsed_time(e1)
-# gather per-ray results on rank 0 (NCCL has no uint32: ids travel as int32 bit patterns)
+# gather per-ray results on rank 0 (NCCL has no uint32: ids travel as int32 bit patterns); first a small warm-up
+# gather: NCCL sets up its point-to-point channels on the first call
+if world > 1:
+    w = torch.zeros(8, device=dev)
+    dist.gather(w, [torch.empty_like(w) for _ in range(world)] if rank == 0 else None, dst=0)
+    torch.cuda.synchronize(); dist.barrier()
 t0 = time.perf_counter()
 if world > 1:
     bt = [torch.empty_like(out[0]) for _ in range(world)] if rank == 0 else None

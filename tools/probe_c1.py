@@ -8,7 +8,8 @@ L = _lib.load()
 P = lambda x: C.c_void_p(x.data_ptr()); F3 = lambda x: (C.c_float * 3)(*[float(y) for y in x])
 v, t = syn.qsm_tree_mesh(1)
 lm = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-s = RaycastingScene(output_device="cuda"); s.set_option("leaf_max", lm); s.add_triangles(v, t); s.commit()
+sm = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+s = RaycastingScene(output_device="cuda"); s.set_option("leaf_max", lm); s.set_option("split_max", sm); s.add_triangles(v, t); s.commit()
 st = s.stats()
 for G in (1000, 4000):
     g = syn.parallel_ray_grid(np.asarray(st["scene_lo"], np.float64), np.asarray(st["scene_hi"], np.float64), syn.sun_direction(45, 135), G, G)
@@ -23,4 +24,4 @@ for G in (1000, 4000):
             _lib.check(L.qsmrt_cast_rays_2d(s._h, P(r), G, G, *[P(x) for x in o], None)); torch.cuda.synchronize()
     s.set_option("traversal_variant", 2)
     _lib.check(L.qsmrt_count_intersections(s._h, P(r), G * G, P(cnt), None)); torch.cuda.synchronize()
-    print(G, "hit fraction", float(torch.isfinite(o[0]).float().mean()), "mean count", float(cnt.float().mean()), "max count", int(cnt.max()))
+    print("split_max", sm, "references", st["num_references"], "grid", G, "hit fraction", float(torch.isfinite(o[0]).float().mean()), "mean count", float(cnt.float().mean()), "max count", int(cnt.max()))
