@@ -347,13 +347,12 @@ def run_ours(args):
     if world > 1:
         # warm the collective the timed region ends with: NCCL sets up an all-reduce's channels on its first call
         dist.all_reduce(torch.zeros_like(exposure))
+    clocks = ClockSampler(local)                        # every rank samples its own GPU (NVML start-up happens here, not
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 3)]     # between the barrier and the start)
     torch.cuda.synchronize()
     if world > 1:
-        dist.barrier()
-    clocks = ClockSampler(local)
-    clocks.start()                                      # every rank samples its own GPU
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 3)]
-    torch.cuda.synchronize()
+        dist.barrier()                                  # all ranks enter the timed region together: the closing all-reduce
+    clocks.start()                                      # would otherwise charge a late starter's delay to everyone else
     ev[0].record()
     for s in range(args.steps):
         ev[1 + 2 * s].record()
