@@ -143,15 +143,36 @@ struct TraceArgs {
     int set_cap;        // MODE 2 / 6: entries of the per-lane hit set (shared memory: fewer entries, more resident CTAs)
 };
 
+// Resident CTAs per SM the kernel is compiled for (register cap 51 at 10, 40 at 12).  Measured (profiles/r02_tuning.txt):
+// 12 helps cast_rays on the quantised nodes (+2.4 % on C2, +4 % on the C3 scene) and hurts the 64-byte-node path (C4 -4 %)
+// and the all-hits modes (-7 %), so it is chosen per instantiation.
 #ifndef QSMRT_TRACE_MINB
 #define QSMRT_TRACE_MINB 10
 #endif
+#ifndef QSMRT_TRACE_MINB_M0Q
+#define QSMRT_TRACE_MINB_M0Q 12
+#endif
+#ifndef QSMRT_TRACE_MINB_M3Q
+#define QSMRT_TRACE_MINB_M3Q QSMRT_TRACE_MINB
+#endif
+#ifndef QSMRT_TRACE_MINB_M4Q
+#define QSMRT_TRACE_MINB_M4Q QSMRT_TRACE_MINB
+#endif
+template <int MODE, bool QUANT> struct TraceMinB {
+    static constexpr int value = !QUANT ? QSMRT_TRACE_MINB : MODE == 0 ? QSMRT_TRACE_MINB_M0Q : MODE == 3 ? QSMRT_TRACE_MINB_M3Q
+                               : MODE == 4 ? QSMRT_TRACE_MINB_M4Q : QSMRT_TRACE_MINB;
+};
 // Node steps per phase vote (the vote only decides the phase, so voting less often saves the loop control all 32
 // lanes execute, but lanes that finish inside the block idle until its end).  Round 1 (before the sweep source and
 // the aggregated atomics): 1 -> 2 +8 %, 2 -> 4 +2 %, 4 -> 8 +2-3 % for cast_rays.  Re-measured in round 2
 // (profiles/r02_tuning.txt): cast_rays C2 4 = 8 (4568 vs 4583 Mrays/s) while the short rays of the C1 tree gain
 // 5-12 % with 4; the fused kernels, whose lanes retire cheaply and want prompt refills, prefer 2: sun sweep
 // 3511 / 3854 / 4086 and sky 2038 / 2184 / 2444 Mrays/s at 8 / 4 / 2.
+// MODE 2 / 6 hit set in local memory instead of shared memory (measured: C3 count 381 -> 474, canopy count 701 -> 781 Mrays/s:
+// shared memory then holds only the stack, 10 CTAs per SM instead of 7).  0 = the shared-memory set (A/B reference).
+#ifndef QSMRT_SET_LOCAL
+#define QSMRT_SET_LOCAL 1
+#endif
 #ifndef QSMRT_STEPS_M0
 #define QSMRT_STEPS_M0 4
 #endif
@@ -198,7 +219,7 @@ __device__ __forceinline__ float qhi(uint32_t w) { return __uint_as_float(__byte
 // is the binding resource, profiles/README.md).  The ray's slab constants are folded with the grid:
 // t = (2^23 + q) * (cell/d) - (2^23 * cell/d - (glo - o)/d), so the slab code is unchanged.
 template <int MODE, bool COUNTERS, bool QUANT>
-__global__ void __launch_bounds__(TR_BLOCK, QSMRT_TRACE_MINB)
+__global__ void __launch_bounds__(TR_BLOCK, (TraceMinB<MODE, QUANT>::value))
 k_trace5(const TraceArgs A)
 {
     constexpr bool CLOSEST = MODE == 0 || MODE == 3 || MODE == 5;
@@ -222,8 +243,19 @@ k_trace5(const TraceArgs A)
     // decode it into a first / end pair with four more ALU-pipe instructions per step, the pipe this loop is bound by.
     int lcur = 0;
     unsigned n_node = 0, n_tri = 0;
+#if QSMRT_SET_LOCAL
+    // MODE 2 / 6 hit set in LOCAL memory (L1-cached, thread-interleaved like the shared layout): shared memory then
+    // holds only the stack and 10 CTAs fit per SM instead of 7; the set is touched once per accepted hit
+    float tset_l[(MODE == 2 || MODE == 6) ? CNT_SET : 1];
+    uint32_t gset_l[(MODE == 2 || MODE == 6) ? CNT_SET : 1];
+#define TSET(q) tset_l[q]
+#define GSET(q) gset_l[q]
+#else
     float *const tset = reinterpret_cast<float *>(sstack + A.depth * TR_BLOCK) + threadIdx.x;      // MODE 2
     uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + A.set_cap) * TR_BLOCK) + threadIdx.x;
+#define TSET(q) tset[(q) * TR_BLOCK]
+#define GSET(q) gset[(q) * TR_BLOCK]
+#endif
     int cnt = 0; bool overflow = false;
     long long lbase = 0;                                        // MODE 6: first output slot of this lane's ray
     uint32_t snx = 0x7610u, sny = 0x7610u, snz = 0x7610u;       // QUANT: per-axis "near plane" byte selectors
@@ -441,9 +473,9 @@ k_trace5(const TraceArgs A)
                         const uint32_t pg = __float_as_uint(p1.w);
                         int at = -1;
                         for (int q = 0; q < cnt; ++q)
-                            if (tset[q * TR_BLOCK] == tt && (!A.multi_geom || gset[q * TR_BLOCK] == pg)) at = q;
+                            if (TSET(q) == tt && (!A.multi_geom || GSET(q) == pg)) at = q;
                         if (at < 0) {
-                            if (cnt < A.set_cap) { tset[cnt * TR_BLOCK] = tt; if (A.multi_geom) gset[cnt * TR_BLOCK] = pg; at = cnt; ++cnt; }
+                            if (cnt < A.set_cap) { TSET(cnt) = tt; if (A.multi_geom) GSET(cnt) = pg; at = cnt; ++cnt; }
                             else { overflow = true; cur = TR_SENTINEL; lcur = 0; }          // the fix-up kernel recounts this ray
                             if (MODE == 6 && !overflow) A.l_prim[lbase + at] = QSMRT_INVALID;   // so the first record always wins below
                         }
@@ -468,6 +500,8 @@ k_trace5(const TraceArgs A)
     }
 #undef PARK_LEAF5
 #undef NEXT_TRI5
+#undef TSET
+#undef GSET
 }
 
 // materialise the hemisphere rays of SRC 2 (tests and small batches): rays[n_points * n_dirs][6]

@@ -964,7 +964,7 @@ int trv_count(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, 
     if (N == 0) return 0;
     const int depth = (int)sc.height + 2;
     const int set_cap = std::min(std::max(ts.opt.count_set, 4), CNT_SET);
-    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * set_cap) * TR_BLOCK * sizeof(int);
+    const size_t smem = (size_t)(depth + (QSMRT_SET_LOCAL ? 0 : (ngeoms > 1 ? 2 : 1) * set_cap)) * TR_BLOCK * sizeof(int);
     if (use_v5(ts, sc, smem)) {
         TraceArgs a{};
         a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
@@ -1002,7 +1002,7 @@ int trv_list_fill(TrvState &ts, const SceneView &sc, const float *rays, uint64_t
     if (N == 0 || sc.ntris == 0) return 0;
     const int depth = (int)sc.height + 2;
     const int set_cap = std::min(std::max(ts.opt.count_set, 4), CNT_SET);
-    const size_t smem = (size_t)(depth + (ngeoms > 1 ? 2 : 1) * set_cap) * TR_BLOCK * sizeof(int);
+    const size_t smem = (size_t)(depth + (QSMRT_SET_LOCAL ? 0 : (ngeoms > 1 ? 2 : 1) * set_cap)) * TR_BLOCK * sizeof(int);
     int max_fast = 0;
     if (use_v5(ts, sc, smem)) {
         TraceArgs a{};
