@@ -226,6 +226,9 @@ k_trace5(const TraceArgs A)
     constexpr bool ANYHIT = MODE == 1 || MODE == 4;
     extern __shared__ int sstack[];                 // [depth][TR_BLOCK] (+ MODE 2: [CNT_SET][TR_BLOCK] t, geometry)
     int *const sbase = sstack + threadIdx.x;
+#define STACK_PUSH(v) do { *sptr = (v); sptr += TR_BLOCK; } while (0)
+#define STACK_POP(dst) do { sptr -= TR_BLOCK; (dst) = *sptr; } while (0)
+#define STACK_RESET() do { sbase[0] = TR_SENTINEL; sptr = sbase + TR_BLOCK; } while (0)
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
@@ -260,7 +263,7 @@ k_trace5(const TraceArgs A)
     long long lbase = 0;                                        // MODE 6: first output slot of this lane's ray
     uint32_t snx = 0x7610u, sny = 0x7610u, snz = 0x7610u;       // QUANT: per-axis "near plane" byte selectors
 
-#define PARK_LEAF5() do { lcur = cur; sptr -= TR_BLOCK; cur = *sptr; } while (0)
+#define PARK_LEAF5() do { lcur = cur; STACK_POP(cur); } while (0)
     // after a triangle of the parked leaf has been tested: the next one (reference - 3: first + 1, left - 1), or done
 #define NEXT_TRI5() do { if (((uint32_t)~lcur & 3u) != 0u) lcur -= 3; else { lcur = 0; if (cur < 0) PARK_LEAF5(); } } while (0)
 
@@ -353,7 +356,7 @@ k_trace5(const TraceArgs A)
                         best_t = ANYHIT ? A.tfar : INFINITY;
                         cnt = 0; overflow = false;
                         best_geom = QSMRT_INVALID; best_prim = QSMRT_INVALID;
-                        sbase[0] = TR_SENTINEL; sptr = sbase + TR_BLOCK;
+                        STACK_RESET();
                         cur = A.sc.ntris ? 0 : TR_SENTINEL;
                         lcur = 0;
                     }
@@ -431,8 +434,8 @@ k_trace5(const TraceArgs A)
                 const bool take1 = !h0 || (CLOSEST && h1 && (t1 < t0));
                 int nxt = take1 ? c1 : c0;
                 const int other = c0 ^ c1 ^ nxt;        // the child not taken (one LOP3)
-                if (h0 && h1) { *sptr = other; sptr += TR_BLOCK; }
-                if (!h0 && !h1) { sptr -= TR_BLOCK; nxt = *sptr; }
+                if (h0 && h1) STACK_PUSH(other);
+                if (!h0 && !h1) STACK_POP(nxt);
                 cur = nxt;
                 if (cur < 0 && !pk_) PARK_LEAF5();
             }
@@ -502,6 +505,9 @@ k_trace5(const TraceArgs A)
 #undef NEXT_TRI5
 #undef TSET
 #undef GSET
+#undef STACK_PUSH
+#undef STACK_POP
+#undef STACK_RESET
 }
 
 // materialise the hemisphere rays of SRC 2 (tests and small batches): rays[n_points * n_dirs][6]
