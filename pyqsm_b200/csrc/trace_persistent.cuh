@@ -143,25 +143,14 @@ struct TraceArgs {
     int set_cap;        // MODE 2 / 6: entries of the per-lane hit set (shared memory: fewer entries, more resident CTAs)
 };
 
-// Resident CTAs per SM the kernel is compiled for (register cap 51 at 10, 40 at 12).  Measured (profiles/r02_tuning.txt):
-// 12 helps cast_rays on the quantised nodes (+2.4 % on C2, +4 % on the C3 scene) and hurts the 64-byte-node path (C4 -4 %)
-// and the all-hits modes (-7 %), so it is chosen per instantiation.
+// Resident CTAs per SM the kernel is compiled for (register cap 51 at 10, 40 at 12).  Measured (profiles/r02_tuning.txt,
+// profiles/r02_kernel_select.txt): 12 gains 1-2 % for cast_rays on the coherent 16M-ray grids of the canopy and loses
+// everywhere else -- 3-10 % on cylinder-QSM scenes, 37-75 % on incoherent rays through the 2M-triangle canopy (the
+// spills of the 40-register build sit in the refill path and incoherent rays leave them no L1) -- so it is 10 for all.
 #ifndef QSMRT_TRACE_MINB
 #define QSMRT_TRACE_MINB 10
 #endif
-#ifndef QSMRT_TRACE_MINB_M0Q
-#define QSMRT_TRACE_MINB_M0Q 12
-#endif
-#ifndef QSMRT_TRACE_MINB_M3Q
-#define QSMRT_TRACE_MINB_M3Q QSMRT_TRACE_MINB
-#endif
-#ifndef QSMRT_TRACE_MINB_M4Q
-#define QSMRT_TRACE_MINB_M4Q QSMRT_TRACE_MINB
-#endif
-template <int MODE, bool QUANT> struct TraceMinB {
-    static constexpr int value = !QUANT ? QSMRT_TRACE_MINB : MODE == 0 ? QSMRT_TRACE_MINB_M0Q : MODE == 3 ? QSMRT_TRACE_MINB_M3Q
-                               : MODE == 4 ? QSMRT_TRACE_MINB_M4Q : QSMRT_TRACE_MINB;
-};
+template <int MODE, bool QUANT> struct TraceMinB { static constexpr int value = QSMRT_TRACE_MINB; };
 // Node steps per phase vote (the vote only decides the phase, so voting less often saves the loop control all 32
 // lanes execute, but lanes that finish inside the block idle until its end).  Round 1 (before the sweep source and
 // the aggregated atomics): 1 -> 2 +8 %, 2 -> 4 +2 %, 4 -> 8 +2-3 % for cast_rays.  Re-measured in round 2
