@@ -103,7 +103,11 @@ int qsmrt_scene_get_counters(qsmrt_scene *scene, uint64_t out[16]);
  * geometries as added and, with QSMRT_SAVE_BVH, the committed LBVH (traversal
  * nodes, quantised twin, triangle records, order, keys, grid); load creates a
  * new scene from the file -- committed if the file holds the BVH, otherwise
- * built by the first query (the build is deterministic: same tree either way). */
+ * built by the first query (the build is deterministic: same tree either way).
+ * load range-checks the geometry indices and every reference of a stored BVH
+ * (children, leaf ranges, order, primitive ids), so a damaged or mismatched file
+ * is an error, not a device fault; it does not defend against a crafted file
+ * (e.g. cyclic child references) -- treat scene files like the pickles they replace. */
 #define QSMRT_SAVE_BVH 1u
 int qsmrt_scene_save(qsmrt_scene *scene, const char *path, uint32_t flags);
 int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out);

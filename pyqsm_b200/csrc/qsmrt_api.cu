@@ -218,6 +218,43 @@ __global__ void k_rebase_idx(const uint32_t *__restrict__ in, uint32_t *__restri
     if (i < n3) out[i] = in[i] + add;
 }
 
+// Scene files: everything a traversal kernel would follow from a loaded BVH must stay inside the loaded arrays.
+// The node array has unused slots (subtrees collapsed into leaves), so the nodes are checked by walking the tree
+// from the root one level per launch: child references and leaf ranges in range, the quantised twin naming the same
+// children; the host bounds the number of nodes visited (a cycle or a shared subtree exceeds it) and the depth.
+__global__ void __launch_bounds__(256)
+k_validate_level(const TNode *__restrict__ tn, const QNode *__restrict__ qn, uint64_t nn, uint64_t nleaves,
+                 const int *__restrict__ frontier, uint32_t count, int *__restrict__ next, uint32_t *next_count, uint32_t *bad)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= count) return;
+    const int node = frontier[i];
+    const int c[2] = { tn[node].d.x, tn[node].d.y };
+    bool ok = !qn || ((int)qn[node].w[6] == c[0] && (int)qn[node].w[7] == c[1]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (c[k] >= 0) {
+            ok = ok && c[k] != 0 && (uint64_t)c[k] < nn;               // the root is nobody's child
+            if (ok) { const uint32_t at = atomicAdd(next_count, 1u); if (at < nn) next[at] = c[k]; }
+        } else {
+            const uint32_t r = ~(uint32_t)c[k];
+            ok = ok && (uint64_t)(r >> 2) + (r & 3u) + 1u <= nleaves;
+        }
+    }
+    if (!ok) *bad = 1u;
+}
+
+// ... and the triangle records and the order array, which have no unused slots
+__global__ void __launch_bounds__(256)
+k_validate_leaves(const TriRec *__restrict__ tris, const uint32_t *__restrict__ order, uint64_t nleaves, uint64_t ntris,
+                  const uint64_t *__restrict__ goff, uint32_t ngeoms, uint32_t *bad)
+{
+    const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
+    if (i >= nleaves) return;
+    const uint32_t g = __float_as_uint(tris[i].p1.w), p = __float_as_uint(tris[i].p0.w);
+    if (!(order[i] < ntris && g < ngeoms && goff[g] + p < goff[g + 1])) *bad = 1u;
+}
+
 // QSM cylinder records -> triangle mesh with Open3D's create_cylinder topology (axis z, centred, 2 cap centres +
 // (split+1) rings of `res` vertices; 2*res cap + 2*res*split side triangles), rotated from +z onto the record's
 // axis (Rodrigues) and translated to its centre: what get_shape(..., shape="cylinder") builds on the CPU
@@ -511,17 +548,36 @@ struct HostOut { void *host; void *keep; size_t bytes; };
 template <int NOUT, class Launch>
 int run_host_pipe(qsmrt_scene *s, const float *rays, uint64_t N, const HostOut (&outs)[NOUT], Launch launch)
 {
-    uint64_t chunk_rays = 1ull << 20;                       // QSMRT_HOST_CHUNK overrides (rays per pipeline stage)
+    size_t stage_bytes = 0, back_bytes = 0, off_of[NOUT];
+    for (int k = 0; k < NOUT; ++k) {
+        off_of[k] = stage_bytes;
+        if (outs[k].host && !outs[k].keep) { stage_bytes += (outs[k].bytes + 15) & ~(size_t)15; back_bytes += outs[k].bytes; }
+    }
+    // rays per pipeline stage (QSMRT_HOST_CHUNK overrides): 1M when the results are the larger transfer, 2M when the
+    // rays are (measured on C2, profiles/r02_tuning.txt: 1.39 Grays/s with all five results, 1.96 -> 2.11 with t_hit + ids)
+    uint64_t chunk_rays = back_bytes > 24 ? 1ull << 20 : 2ull << 20;
     if (const char *e = getenv("QSMRT_HOST_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk_rays = (uint64_t)v; }
+    bool ramp = true;                                       // QSMRT_HOST_RAMP=0: equal stages (A/B)
+    if (const char *e = getenv("QSMRT_HOST_RAMP")) ramp = atoi(e) != 0;
     const uint64_t chunk = std::min<uint64_t>(N, chunk_rays);
-    size_t stage_bytes = 0, off_of[NOUT];
-    for (int k = 0; k < NOUT; ++k) { off_of[k] = stage_bytes; if (outs[k].host && !outs[k].keep) stage_bytes += (outs[k].bytes + 15) & ~(size_t)15; }
     if (ensure_pipe(s, chunk, std::max<size_t>(stage_bytes, 16))) return 1;
     HostPipe &hp = s->pipe;
-    const uint64_t nchunks = (N + chunk - 1) / chunk;
-    for (uint64_t c = 0; c < nchunks; ++c) {
+    // Stage sizes.  The first copy-in and the last copy-out are the only transfers nothing overlaps, so a long batch
+    // starts and ends with short stages (chunk/8, /4, /2) and runs full stages in between.
+    std::vector<uint64_t> sizes;
+    if (ramp && N >= 4 * chunk && chunk >= (1u << 16)) {
+        uint64_t used = 0;
+        for (uint64_t c = chunk / 8; c < chunk; c *= 2) { sizes.push_back(c); used += 2 * c; }
+        const size_t nramp = sizes.size();
+        for (uint64_t left = N - used; left; ) { const uint64_t n = std::min(chunk, left); sizes.push_back(n); left -= n; }
+        for (size_t k = nramp; k-- > 0; ) sizes.push_back(sizes[k]);
+    } else {
+        for (uint64_t left = N; left; ) { const uint64_t n = std::min(chunk, left); sizes.push_back(n); left -= n; }
+    }
+    uint64_t off = 0;
+    for (size_t c = 0; c < sizes.size(); off += sizes[c], ++c) {
         const int b = (int)(c % HostPipe::NBUF);
-        const uint64_t off = c * chunk, n = std::min(chunk, N - off);
+        const uint64_t n = sizes[c];
         if (c >= HostPipe::NBUF) CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.e_out[b], 0));   // buffer drained
         CUDA_TRY(cudaMemcpyAsync(hp.rays[b], rays + 6 * off, 6 * n * sizeof(float), cudaMemcpyHostToDevice, hp.s_in));
         CUDA_TRY(cudaEventRecord(hp.e_in[b], hp.s_in));
@@ -1255,6 +1311,32 @@ int qsmrt_scene_load(int cuda_device, const char *path, qsmrt_scene **out)
             (h.use_q && io.get(s->qnodes, NN * sizeof(QNode))) || io.get(s->tris, Lv * sizeof(TriRec)) ||
             io.get(s->order, Lv * sizeof(uint32_t)) || io.get(s->keys, Lv * sizeof(uint64_t)))
             return 1;
+        // range check of everything the traversal follows (a file cut short or belonging to other geometry fails here,
+        // not inside a kernel), one tree level per launch; the stored height sizes the traversal stack
+        if (h.stats.bvh_height > 4096u || h.stats.num_triangles != T) FAIL("corrupt scene file (statistics)");
+        {
+            int *front[2] = { nullptr, nullptr };
+            uint32_t *d_cnt = nullptr, h_cnt[3] = { 0, 0, 0 };                  // next level's size, bad flag, spare
+            const QNode *qn = h.use_q ? s->qnodes : nullptr;
+            int rc = dmalloc(&front[0], NN) || dmalloc(&front[1], NN) || dmalloc(&d_cnt, 4);
+            uint64_t visited = 1;
+            uint32_t count = 1, levels = 0;
+            if (!rc) rc = cudaMemset(front[0], 0, sizeof(int)) != cudaSuccess || cudaMemset(d_cnt, 0, 4 * sizeof(uint32_t)) != cudaSuccess;
+            if (!rc) {
+                k_validate_leaves<<<(unsigned)((Lv + 255) / 256), 256>>>(s->tris, s->order, Lv, T, s->goff, G, d_cnt + 1);
+                while (count && !h_cnt[1] && visited <= NN && levels <= h.stats.bvh_height + 1u) {
+                    k_validate_level<<<(count + 255) / 256, 256>>>(s->tnodes, qn, NN, Lv, front[levels & 1], count, front[(levels + 1) & 1], d_cnt, d_cnt + 1);
+                    if (cudaMemcpy(h_cnt, d_cnt, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                        cudaMemset(d_cnt, 0, sizeof(uint32_t)) != cudaSuccess) { rc = 2; break; }
+                    count = h_cnt[0]; visited += count; ++levels;
+                }
+            }
+            dfree(front[0]); dfree(front[1]); dfree(d_cnt);
+            if (rc == 1) return 1;
+            if (rc) FAIL("scene file validation: %s", cudaGetErrorString(cudaGetLastError()));
+            if (h_cnt[1]) FAIL("corrupt scene file (BVH references out of range)");
+            if (count || visited > NN) FAIL("corrupt scene file (BVH is not a tree of the stored height)");
+        }
         CUDA_TRY(cudaDeviceSynchronize());
         s->use_qnodes = h.use_q != 0;
         s->stats = h.stats;

@@ -133,6 +133,32 @@ def test_scene_file_round_trip(RS, tree, tmp_path, with_bvh):
         RS.load(bad)
 
 
+def test_scene_file_damage_is_an_error_not_a_fault(RS, tree, tmp_path):
+    """A scene file cut short, or whose BVH points outside its own arrays, raises RuntimeError at load (every
+    reference the traversal would follow is range-checked on the GPU); the process stays usable."""
+    v, t, o, rays = tree
+    s = RS()
+    s.add_triangles(v, t)
+    path = tmp_path / "scene.qsmrt"
+    s.save(path, with_bvh=True)
+    st = s.stats()
+    raw = bytearray(path.read_bytes())
+    lv, nn, q = st["num_references"], max(st["num_references"] - 1, 1), 1 if st["quantised_nodes"] else 0
+    tnodes_at = len(raw) - (lv * (8 + 4 + 48) + nn * 32 * q + nn * 64)       # keys, order, records, quantised twin, nodes
+    cut = tmp_path / "cut.qsmrt"
+    cut.write_bytes(bytes(raw[: len(raw) - 1000]))
+    with pytest.raises(RuntimeError, match="truncated"):
+        RS.load(cut)
+    wild = bytearray(raw)
+    wild[tnodes_at + 48: tnodes_at + 56] = np.asarray([0x7FFFFFF0, 0x7FFFFFF0], np.int32).tobytes()      # the root's child references
+    bad = tmp_path / "wild.qsmrt"
+    bad.write_bytes(bytes(wild))
+    with pytest.raises(RuntimeError, match="out of range"):
+        RS.load(bad)
+    z = RS.load(path)                                               # the undamaged file still loads and answers
+    assert torch.equal(z.cast_rays(rays)["t_hit"], s.cast_rays(rays)["t_hit"])
+
+
 def test_vertex_exposure_and_hit_vertices(RS, tree):
     """Per-vertex results as the reference derives them (ray_casting.py:287-292): hit_tris = triangles[prim_ids],
     hit_vert_ids = np.unique(hit_tris).  mark_hit_primitives(vertices=True) gives that set as a mask,
