@@ -192,7 +192,11 @@ int qsmrt_test_occlusions_host(qsmrt_scene *scene, const float *rays_host, uint6
  *           counts) and returns the total K in *total_out (synchronises);
  *   _fill   writes the K hits, per ray sorted by (t, geometry, primitive):
  *           ray_ids[K] int64, t_hit[K], geometry_ids[K], primitive_ids[K],
- *           primitive_uvs[K x 2]. */
+ *           primitive_uvs[K x 2] (synchronises).
+ * The rays are traversed ONCE, in _count, which also collects the hit records
+ * in device memory owned by the scene (20 bytes per hit + 8 per ray, returned
+ * by _fill); _fill only moves them into the caller's arrays and must follow
+ * _count on the same, unchanged rays. */
 int qsmrt_list_intersections_count(qsmrt_scene *scene, const float *rays_dev, uint64_t N,
                                    int64_t *ray_splits, int64_t *total_out, void *stream);
 int qsmrt_list_intersections_fill(qsmrt_scene *scene, const float *rays_dev, uint64_t N,

@@ -80,6 +80,7 @@ struct qsmrt_scene {
     cudaTextureObject_t node_tex = 0;
     // list_intersections cache between _count and _fill
     const float *list_rays = nullptr; uint64_t list_n = 0;
+    ListStash list_stash; int list_max_fast = 0;     // the hit records _count collected for _fill
     HostPipe pipe;
     float *sweep_dev = nullptr; uint32_t sweep_cap = 0;     // per-grid constants of qsmrt_sun_exposure_sweep
 };
@@ -167,8 +168,18 @@ template <class T> int dmalloc(T **p, uint64_t count)
 }
 template <class T> void dfree(T *&p) { dfree_bytes(p); p = nullptr; }
 
+void free_list_stash(qsmrt_scene *s)
+{
+    ListStash &ls = s->list_stash;
+    s->list_max_fast = 0; ls.cap = 0;
+    if (!ls.base && !ls.t && !ls.geom && !ls.prim && !ls.uv && !ls.count) return;
+    SyncedFrees batch;
+    dfree(ls.base); dfree(ls.t); dfree(ls.geom); dfree(ls.prim); dfree(ls.uv); dfree(ls.count);
+}
+
 void free_build(qsmrt_scene *s)
 {
+    free_list_stash(s);
     if (s->own_concat) { dfree(s->verts); dfree(s->idx); }
     s->verts = nullptr; s->idx = nullptr; s->own_concat = false;
     dfree(s->goff); dfree(s->voff); dfree(s->keys); dfree(s->order);
@@ -955,19 +966,36 @@ int qsmrt_list_intersections_count(qsmrt_scene *s, const float *rays, uint64_t N
         s->list_rays = rays; s->list_n = N;
         return 0;
     }
-    // first pass = count_intersections (the same distinct-(geometry, t) rule), scanned into the CSR offsets
+    // ONE all-hits traversal: the counts (count_intersections' distinct-(geometry, t) rule), scanned into the CSR
+    // offsets, and the hit records themselves in a stash that _fill moves to the caller's arrays.  The stash is sized
+    // for 4 hits per ray; a batch with more is traversed once more with exactly the room it needs.
+    free_list_stash(s);
     int32_t *cnt = nullptr; char *scratch = nullptr;
     auto body = [&]() -> int {
         if (dmalloc(&cnt, N) || dmalloc(&scratch, trv_scan_scratch_bytes(N))) return 1;
-        if (trv_count(s->trv, view_of(s), rays, N, cnt, (uint32_t)s->geoms.size(), st) ||
-            trv_exclusive_scan(cnt, N, ray_splits, scratch, st)) return 1;
-        CUDA_TRY(cudaMemcpyAsync(total_out, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        ListStash &ls = s->list_stash;
+        unsigned long long cap = 4 * N + 65536, needed = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            needed = 0;
+            if (dmalloc(&ls.base, N) || dmalloc(&ls.t, cap) || dmalloc(&ls.geom, cap) || dmalloc(&ls.prim, cap) ||
+                dmalloc(&ls.uv, 2 * cap) || dmalloc(&ls.count, 1)) {
+                free_list_stash(s);         // no room for a stash: count only, _fill enumerates the hits of every ray
+                g_err[0] = 0;
+            } else ls.cap = cap;
+            if (trv_list_collect(s->trv, view_of(s), rays, N, (uint32_t)s->geoms.size(), cnt, ls, &s->list_max_fast, st) ||
+                trv_exclusive_scan(cnt, N, ray_splits, scratch, st)) return 1;
+            CUDA_TRY(cudaMemcpyAsync(total_out, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            if (ls.count) CUDA_TRY(cudaMemcpyAsync(&needed, ls.count, sizeof(needed), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (needed <= ls.cap) break;
+            free_list_stash(s);
+            cap = needed;
+        }
         return 0;
     };
     const int rc = body();
     dfree(cnt); dfree(scratch);
-    if (rc) return 1;
+    if (rc) { free_list_stash(s); return 1; }
     s->list_rays = rays; s->list_n = N;
     return 0;
 }
@@ -982,24 +1010,25 @@ int qsmrt_list_intersections_fill(qsmrt_scene *s, const float *rays, uint64_t N,
     if (reinterpret_cast<uintptr_t>(uv) & 7u) FAIL("primitive_uvs must be 8-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     s->list_rays = nullptr; s->list_n = 0;
-    if (s->ntris == 0 || N == 0) return 0;
-    // the fill writes t / geometry / primitive / uv of every hit while it deduplicates: outputs the caller skipped
-    // are staged in scratch
+    if (s->ntris == 0 || N == 0) { free_list_stash(s); return 0; }
+    // the output pass sorts each ray's records in the caller's t / geometry / primitive / uv arrays: outputs the
+    // caller skipped are staged in scratch
     int64_t total = 0;
     CUDA_TRY(cudaMemcpyAsync(&total, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (total == 0) return 0;
+    if (total == 0) { free_list_stash(s); return 0; }
     float *t_tmp = nullptr, *uv_tmp = nullptr; uint32_t *g_tmp = nullptr, *p_tmp = nullptr;
     auto body = [&]() -> int {
         if ((!t_hit && dmalloc(&t_tmp, (uint64_t)total)) || (!geom && dmalloc(&g_tmp, (uint64_t)total)) ||
             (!prim && dmalloc(&p_tmp, (uint64_t)total)) || (!uv && dmalloc(&uv_tmp, 2 * (uint64_t)total))) return 1;
-        if (trv_list_fill(s->trv, view_of(s), rays, N, ray_splits, (uint32_t)s->geoms.size(), ray_ids, t_hit ? t_hit : t_tmp,
+        if (trv_list_emit(view_of(s), rays, N, ray_splits, s->list_stash, s->list_max_fast, ray_ids, t_hit ? t_hit : t_tmp,
                           geom ? geom : g_tmp, prim ? prim : p_tmp, uv ? uv : uv_tmp, st)) return 1;
-        if (t_tmp || g_tmp || p_tmp || uv_tmp) CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaStreamSynchronize(st));        // the stash (and any scratch) goes back to the block cache below
         return 0;
     };
     const int rc = body();
     dfree(t_tmp); dfree(g_tmp); dfree(p_tmp); dfree(uv_tmp);
+    free_list_stash(s);
     return rc;
 }
 

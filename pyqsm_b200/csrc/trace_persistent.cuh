@@ -25,9 +25,12 @@
 //   3  closest hit  -> atomicAdd(accum[triangle], 1)        (sun exposure: no 32 B/ray of results)
 //   4  any hit      -> atomicAdd(accum[ray / n_dirs], !hit) (sky visibility per query point)
 //   5  closest hit among the triangles still alive -> hitflag[sorted triangle] = 1   (peel projection)
-//   6  all hits     -> the distinct (geometry, t) hits of ray i written at list.* [splits[i] ...] (list_intersections,
-//                      second pass: the counts of MODE 2 are already scanned into splits); equal (geometry, t) keeps
-//                      the lowest primitive id.  Rays without hits, or with more than CNT_SET, are skipped here
+//   6  all hits     -> MODE 2's count AND the distinct hits themselves (list_intersections in ONE traversal): the
+//                      per-lane set also keeps primitive id and uv (equal (geometry, t) keeps the lowest primitive
+//                      id); a retiring warp reserves room for its rays' records in a stash with one atomicAdd
+//                      and writes them there; stash_base[ray] says where.  k_list_finish later moves them to
+//                      the caller's CSR arrays in (t, geometry, primitive) order.  Rays with more than CNT_SET
+//                      distinct hits are marked -1 like MODE 2 and enumerated by the slow path.
 // SRC (where rays come from; a uniform runtime switch, only touched at refill)
 //   0  rays[N][6] in memory
 //   1  parallel grid: origin0 + i*du + j*dv, direction dir  (same arithmetic as k_gen_parallel)
@@ -132,15 +135,16 @@ struct TraceArgs {
     uint64_t N; uint32_t row_len; uint64_t nslots;
     CastOut out; uint8_t *occluded; float tnear, tfar;          // MODE 0 / 1
     int32_t *counts;                                            // MODE 2
-    const int64_t *splits; float *l_t; uint32_t *l_geom, *l_prim; float2 *l_uv;      // MODE 6
+    long long *st_base; float *st_t; uint32_t *st_geom, *st_prim; float2 *st_uv;     // MODE 6: the stash of hit records,
+    unsigned long long *st_count, st_cap;                                            //         records reserved so far, capacity
     uint32_t *accum; const uint64_t *goff; uint64_t accum_stride;   // MODE 3 / 4 (stride: one row of counts per grid of a sweep, 0 = one row)
     const uint8_t *alive; uint8_t *hitflag; const uint32_t *order;  // MODE 5: flags per triangle (scene order) = order[sorted record]
     unsigned long long *cursor, *stats;
     int refill, want, tri_min, node_path;
-    int depth;          // stack entries per thread; the MODE 2 hit set starts behind the stack in shared memory
+    int depth;          // stack entries per thread
     int multi_geom;     // > 1 geometry: the set also keeps geometry ids
     int row_major;      // 2-D batches: tile rows in memory order instead of from the middle outwards
-    int set_cap;        // MODE 2 / 6: entries of the per-lane hit set (shared memory: fewer entries, more resident CTAs)
+    int set_cap;        // MODE 2 / 6: entries of the per-lane hit set in use (<= CNT_SET)
 };
 
 // Resident CTAs per SM the kernel is compiled for (register cap 51 at 10, 40 at 12).  Measured (profiles/r02_tuning.txt,
@@ -157,11 +161,6 @@ template <int MODE, bool QUANT> struct TraceMinB { static constexpr int value = 
 // (profiles/r02_tuning.txt): cast_rays C2 4 = 8 (4568 vs 4583 Mrays/s) while the short rays of the C1 tree gain
 // 5-12 % with 4; the fused kernels, whose lanes retire cheaply and want prompt refills, prefer 2: sun sweep
 // 3511 / 3854 / 4086 and sky 2038 / 2184 / 2444 Mrays/s at 8 / 4 / 2.
-// MODE 2 / 6 hit set in local memory instead of shared memory (measured: C3 count 381 -> 474, canopy count 701 -> 781 Mrays/s:
-// shared memory then holds only the stack, 10 CTAs per SM instead of 7).  0 = the shared-memory set (A/B reference).
-#ifndef QSMRT_SET_LOCAL
-#define QSMRT_SET_LOCAL 1
-#endif
 #ifndef QSMRT_STEPS_M0
 #define QSMRT_STEPS_M0 4
 #endif
@@ -213,7 +212,7 @@ k_trace5(const TraceArgs A)
 {
     constexpr bool CLOSEST = MODE == 0 || MODE == 3 || MODE == 5;
     constexpr bool ANYHIT = MODE == 1 || MODE == 4;
-    extern __shared__ int sstack[];                 // [depth][TR_BLOCK] (+ MODE 2: [CNT_SET][TR_BLOCK] t, geometry)
+    extern __shared__ int sstack[];                 // [depth][TR_BLOCK]
     int *const sbase = sstack + threadIdx.x;
 #define STACK_PUSH(v) do { *sptr = (v); sptr += TR_BLOCK; } while (0)
 #define STACK_POP(dst) do { sptr -= TR_BLOCK; (dst) = *sptr; } while (0)
@@ -235,21 +234,16 @@ k_trace5(const TraceArgs A)
     // decode it into a first / end pair with four more ALU-pipe instructions per step, the pipe this loop is bound by.
     int lcur = 0;
     unsigned n_node = 0, n_tri = 0;
-#if QSMRT_SET_LOCAL
-    // MODE 2 / 6 hit set in LOCAL memory (L1-cached, thread-interleaved like the shared layout): shared memory then
-    // holds only the stack and 10 CTAs fit per SM instead of 7; the set is touched once per accepted hit
+    // MODE 2 / 6 hit set in LOCAL memory (L1-cached, thread-interleaved): shared memory then holds only the stack and
+    // 10 CTAs fit per SM instead of the 7 a shared-memory set allowed (measured: C3 count 381 -> 474, canopy count
+    // 701 -> 781 Mrays/s); the set is touched once per accepted hit
     float tset_l[(MODE == 2 || MODE == 6) ? CNT_SET : 1];
     uint32_t gset_l[(MODE == 2 || MODE == 6) ? CNT_SET : 1];
+    uint32_t pset_l[MODE == 6 ? CNT_SET : 1];                   // MODE 6: primitive id and uv of each set entry
+    float uset_l[MODE == 6 ? CNT_SET : 1], vset_l[MODE == 6 ? CNT_SET : 1];
 #define TSET(q) tset_l[q]
 #define GSET(q) gset_l[q]
-#else
-    float *const tset = reinterpret_cast<float *>(sstack + A.depth * TR_BLOCK) + threadIdx.x;      // MODE 2
-    uint32_t *const gset = reinterpret_cast<uint32_t *>(sstack + (A.depth + A.set_cap) * TR_BLOCK) + threadIdx.x;
-#define TSET(q) tset[(q) * TR_BLOCK]
-#define GSET(q) gset[(q) * TR_BLOCK]
-#endif
     int cnt = 0; bool overflow = false;
-    long long lbase = 0;                                        // MODE 6: first output slot of this lane's ray
     uint32_t snx = 0x7610u, sny = 0x7610u, snz = 0x7610u;       // QUANT: per-axis "near plane" byte selectors
 
 #define PARK_LEAF5() do { lcur = cur; STACK_POP(cur); } while (0)
@@ -277,6 +271,28 @@ k_trace5(const TraceArgs A)
                 }
                 if (idle) have_ray = false;
             }
+            if (MODE == 6) {
+                // the rays retiring together reserve their stash records with one atomicAdd (prefix sum over the lanes)
+                const bool put = idle && have_ray && !overflow && cnt > 0;
+                const int mine = put ? cnt : 0;
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += y; }
+                const int total = __shfl_sync(FULL, incl, 31);
+                if (total) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(A.st_count, (unsigned long long)total);
+                    base = __shfl_sync(FULL, base, 0) + (unsigned long long)(incl - mine);
+                    if (put) {
+                        A.st_base[ray_i] = (long long)base;
+                        if (base + (unsigned long long)mine <= A.st_cap)        // else: the host sees st_count > st_cap and repeats with room
+                            for (int q = 0; q < cnt; ++q) {
+                                A.st_t[base + q] = TSET(q); A.st_geom[base + q] = GSET(q); A.st_prim[base + q] = pset_l[q];
+                                A.st_uv[base + q] = make_float2(uset_l[q], vset_l[q]);
+                            }
+                    }
+                }
+            }
             if (idle && have_ray) {
                 have_ray = false;
                 if (MODE == 0) {
@@ -299,7 +315,7 @@ k_trace5(const TraceArgs A)
                     }
                 } else if (MODE == 1) {
                     A.occluded[ray_i] = best_prim != QSMRT_INVALID ? 1 : 0;
-                } else if (MODE == 2) {
+                } else if (MODE == 2 || MODE == 6) {
                     A.counts[ray_i] = overflow ? -1 : cnt;           // -1: k_count_fix recounts this ray exactly
                 } else if (MODE == 5) {
                     if (best_prim != QSMRT_INVALID) A.hitflag[A.order[best_tri]] = 1;
@@ -323,11 +339,6 @@ k_trace5(const TraceArgs A)
                         ok = ok && ray_index_of_slot(slot - a * A.src.per_grid_slots, A.src.per_grid_rays, A.row_len, i, gx, gy, A.row_major != 0);
                         i += a * A.src.per_grid_rays;
                     } else ok = ok && ray_index_of_slot(slot, A.N, A.row_len, i, gx, gy, A.row_major != 0);
-                    if (MODE == 6 && ok) {          // nothing to list (or too much for the on-chip set: k_list_slow does those)
-                        lbase = A.splits[i];
-                        const long long k = A.splits[i + 1] - lbase;
-                        ok = k > 0 && k <= A.set_cap;
-                    }
                     if (ok) {
                         r = source_ray(A.src, i, gx, gy, A.row_len != 0);
                         if (QUANT) {
@@ -467,15 +478,16 @@ k_trace5(const TraceArgs A)
                         for (int q = 0; q < cnt; ++q)
                             if (TSET(q) == tt && (!A.multi_geom || GSET(q) == pg)) at = q;
                         if (at < 0) {
-                            if (cnt < A.set_cap) { TSET(cnt) = tt; if (A.multi_geom) GSET(cnt) = pg; at = cnt; ++cnt; }
-                            else { overflow = true; cur = TR_SENTINEL; lcur = 0; }          // the fix-up kernel recounts this ray
-                            if (MODE == 6 && !overflow) A.l_prim[lbase + at] = QSMRT_INVALID;   // so the first record always wins below
+                            if (cnt < A.set_cap) {
+                                TSET(cnt) = tt; if (A.multi_geom || MODE == 6) GSET(cnt) = pg;
+                                if (MODE == 6) pset_l[cnt] = QSMRT_INVALID;                  // so the first record always wins below
+                                at = cnt; ++cnt;
+                            } else { overflow = true; cur = TR_SENTINEL; lcur = 0; }          // the fix-up kernel recounts this ray
                         }
                         if (MODE == 6 && at >= 0) {
                             const uint32_t pp = __float_as_uint(p0.w);
-                            if (pp < A.l_prim[lbase + at]) {            // survivor of equal (geometry, t): the lowest primitive id
-                                A.l_t[lbase + at] = tt; A.l_geom[lbase + at] = pg; A.l_prim[lbase + at] = pp;
-                                A.l_uv[lbase + at] = make_float2(__fdiv_rn(h.U, h.absDen), __fdiv_rn(h.V, h.absDen));
+                            if (pp < pset_l[at]) {                      // survivor of equal (geometry, t): the lowest primitive id
+                                pset_l[at] = pp; uset_l[at] = __fdiv_rn(h.U, h.absDen); vset_l[at] = __fdiv_rn(h.V, h.absDen);
                             }
                         }
                     }

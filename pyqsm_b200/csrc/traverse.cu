@@ -380,11 +380,12 @@ k_count_fix(SceneView sc, const float *__restrict__ rays, uint64_t N, int32_t *_
 }
 
 // ---- list_intersections, throughput path -------------------------------------------------------------------
-// (1) count_intersections (persistent MODE 2 + exact fix-up) -> exclusive scan = ray_splits;
-// (2) persistent MODE 6 writes the distinct hits of every ray with 1 .. CNT_SET of them straight into the caller's
-//     arrays at ray_splits[i] (rays without hits -- most of a sparse canopy -- are not traversed again);
-// (3) k_list_finish: one thread per ray sorts its (short) segment by (t, geometry, primitive) and fills ray_ids;
-//     rays with more than CNT_SET hits enumerate them in increasing order instead, one traversal per hit.
+// (1) ONE all-hits traversal (persistent MODE 6 + exact fix-up of the rays with more than CNT_SET hits): the counts,
+//     and the distinct hits of every ray with 1 .. CNT_SET of them in a stash (records in retirement order);
+// (2) exclusive scan of the counts = ray_splits;
+// (3) k_list_finish: one thread per ray moves its records from the stash to the caller's arrays at ray_splits[i],
+//     ordered by (t, geometry, primitive), and fills ray_ids; rays with more than CNT_SET hits enumerate them in
+//     increasing order instead, one traversal per hit.
 struct NextFullVis {      // smallest (t, geom) strictly after (pt, pg); among equal (t, geom) the lowest primitive
     const SceneView &sc; const Ray &r;
     float pt; uint32_t pg; bool have_prev;
@@ -412,6 +413,8 @@ struct NextFullVis {      // smallest (t, geom) strictly after (pt, pg); among e
 
 __global__ void __launch_bounds__(TR_BLOCK)
 k_list_finish(SceneView sc, const float *__restrict__ rays, uint64_t N, const int64_t *__restrict__ splits, int max_fast,
+              const long long *__restrict__ st_base, const float *__restrict__ st_t, const uint32_t *__restrict__ st_geom,
+              const uint32_t *__restrict__ st_prim, const float2 *__restrict__ st_uv,
               int64_t *__restrict__ ray_ids, float *__restrict__ t_hit, uint32_t *__restrict__ geom, uint32_t *__restrict__ prim,
               float2 *__restrict__ uv)
 {
@@ -423,9 +426,10 @@ k_list_finish(SceneView sc, const float *__restrict__ rays, uint64_t N, const in
     if (n == 0) return;
     if (ray_ids) for (int k = 0; k < n; ++k) ray_ids[o + k] = (int64_t)i;
     if (n <= max_fast) {
-        // insertion sort of the segment the persistent kernel filled (a handful of hits; keys (t, geom, prim))
-        for (int a = 1; a < n; ++a) {
-            const float xt = t_hit[o + a]; const uint32_t xg = geom[o + a], xp = prim[o + a]; const float2 xu = uv[o + a];
+        // insertion sort of the records the persistent kernel stashed (a handful of hits; keys (t, geom, prim))
+        const long long sb = st_base[i];
+        for (int a = 0; a < n; ++a) {
+            const float xt = st_t[sb + a]; const uint32_t xg = st_geom[sb + a], xp = st_prim[sb + a]; const float2 xu = st_uv[sb + a];
             int b = a;
             for (; b > 0; --b) {
                 const float yt = t_hit[o + b - 1]; const uint32_t yg = geom[o + b - 1], yp = prim[o + b - 1];
@@ -433,7 +437,7 @@ k_list_finish(SceneView sc, const float *__restrict__ rays, uint64_t N, const in
                 if (!less) break;
                 t_hit[o + b] = yt; geom[o + b] = yg; prim[o + b] = yp; uv[o + b] = uv[o + b - 1];
             }
-            if (b != a) { t_hit[o + b] = xt; geom[o + b] = xg; prim[o + b] = xp; uv[o + b] = xu; }
+            t_hit[o + b] = xt; geom[o + b] = xg; prim[o + b] = xp; uv[o + b] = xu;
         }
         return;
     }
@@ -964,7 +968,7 @@ int trv_count(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, 
     if (N == 0) return 0;
     const int depth = (int)sc.height + 2;
     const int set_cap = std::min(std::max(ts.opt.count_set, 4), CNT_SET);
-    const size_t smem = (size_t)(depth + (QSMRT_SET_LOCAL ? 0 : (ngeoms > 1 ? 2 : 1) * set_cap)) * TR_BLOCK * sizeof(int);
+    const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
     if (use_v5(ts, sc, smem)) {
         TraceArgs a{};
         a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
@@ -995,24 +999,40 @@ int trv_occluded(TrvState &ts, const SceneView &sc, const float *rays, uint64_t 
     return 0;
 }
 
-// list_intersections second pass: fill the CSR arrays at the scanned offsets, then sort each ray's segment
-int trv_list_fill(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, const int64_t *splits, uint32_t ngeoms,
-                  int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st)
+// list_intersections, the traversal: counts[i] = distinct hits of ray i (exact), and the hit records of the rays with
+// 1 .. *max_fast_out of them in the stash (stash.cap records; *stash.count says afterwards how many the batch
+// wanted: more than the capacity means records were dropped and the caller repeats with room).  *max_fast_out = 0:
+// no stash (per-thread kernels; every ray takes k_list_finish's enumeration path).  Asynchronous.
+int trv_list_collect(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, uint32_t ngeoms, int32_t *counts,
+                     const ListStash &stash, int *max_fast_out, cudaStream_t st)
 {
+    *max_fast_out = 0;
     if (N == 0 || sc.ntris == 0) return 0;
     const int depth = (int)sc.height + 2;
     const int set_cap = std::min(std::max(ts.opt.count_set, 4), CNT_SET);
-    const size_t smem = (size_t)(depth + (QSMRT_SET_LOCAL ? 0 : (ngeoms > 1 ? 2 : 1) * set_cap)) * TR_BLOCK * sizeof(int);
-    int max_fast = 0;
-    if (use_v5(ts, sc, smem)) {
-        TraceArgs a{};
-        a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
-        a.depth = depth; a.multi_geom = ngeoms > 1; a.set_cap = set_cap;
-        a.splits = splits; a.l_t = t_hit; a.l_geom = geom; a.l_prim = prim; a.l_uv = reinterpret_cast<float2 *>(uv);
-        if (launch_trace5<6, false>(ts, a, smem, st)) return 1;
-        max_fast = set_cap;
-    }
-    k_list_finish<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, splits, max_fast, ray_ids, t_hit, geom, prim,
+    const size_t smem = (size_t)depth * TR_BLOCK * sizeof(int);
+    if (!use_v5(ts, sc, smem) || !stash.count) return trv_count(ts, sc, rays, N, counts, ngeoms, st);
+    CUDA_TRY(cudaMemsetAsync(stash.count, 0, sizeof(unsigned long long), st));
+    TraceArgs a{};
+    a.sc = sc; a.src.kind = 0; a.src.rays = rays; a.N = N; a.row_len = 0; a.nslots = N;
+    a.counts = counts; a.depth = depth; a.multi_geom = ngeoms > 1; a.set_cap = set_cap;
+    a.st_base = stash.base; a.st_t = stash.t; a.st_geom = stash.geom; a.st_prim = stash.prim; a.st_uv = reinterpret_cast<float2 *>(stash.uv);
+    a.st_count = stash.count; a.st_cap = stash.cap;
+    if (launch_trace5<6, false>(ts, a, smem, st)) return 1;
+    const int sms = ts.sms ? ts.sms : 148;
+    k_count_fix<<<(unsigned)std::min<uint64_t>(grid_for(N, TR_BLOCK), (uint64_t)sms * 8), TR_BLOCK, 0, st>>>(sc, rays, N, counts);
+    CUDA_TRY(cudaGetLastError());
+    *max_fast_out = set_cap;
+    return 0;
+}
+
+// list_intersections, the output: stash -> CSR arrays at the scanned offsets, each ray's segment in order
+int trv_list_emit(const SceneView &sc, const float *rays, uint64_t N, const int64_t *splits, const ListStash &stash, int max_fast,
+                  int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st)
+{
+    if (N == 0 || sc.ntris == 0) return 0;
+    k_list_finish<<<grid_for(N, TR_BLOCK), TR_BLOCK, 0, st>>>(sc, rays, N, splits, max_fast, stash.base, stash.t, stash.geom, stash.prim,
+                                                            reinterpret_cast<const float2 *>(stash.uv), ray_ids, t_hit, geom, prim,
                                                             reinterpret_cast<float2 *>(uv));
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -33,7 +33,15 @@ int trv_cast_rays(TrvState &ts, const SceneView &sc, const float *rays, uint64_t
                   uint32_t *prim, float *uv, float *nrm, cudaStream_t st);
 int trv_count(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, int32_t *out, uint32_t ngeoms, cudaStream_t st);
 int trv_occluded(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, float tnear, float tfar, uint8_t *out, cudaStream_t st);
-int trv_list_fill(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, const int64_t *splits, uint32_t ngeoms,
+// hit records of one list_intersections batch between its two calls (device memory owned by the caller)
+struct ListStash {
+    long long *base = nullptr;                  // [N]: first record of ray i
+    float *t = nullptr; uint32_t *geom = nullptr, *prim = nullptr; float *uv = nullptr;     // [cap] (uv: [cap][2])
+    unsigned long long *count = nullptr, cap = 0;
+};
+int trv_list_collect(TrvState &ts, const SceneView &sc, const float *rays, uint64_t N, uint32_t ngeoms, int32_t *counts,
+                     const ListStash &stash, int *max_fast_out, cudaStream_t st);
+int trv_list_emit(const SceneView &sc, const float *rays, uint64_t N, const int64_t *splits, const ListStash &stash, int max_fast,
                   int64_t *ray_ids, float *t_hit, uint32_t *geom, uint32_t *prim, float *uv, cudaStream_t st);
 size_t trv_scan_scratch_bytes(uint64_t n);
 int trv_exclusive_scan(const int32_t *in, uint64_t n, int64_t *out, void *scratch, cudaStream_t st);

@@ -119,6 +119,32 @@ def test_c1_list_intersections(c1):
     assert ol["ray_splits"][-1] > 1000
 
 
+def test_list_intersections_many_hits_per_ray(RS, oracle_mod):
+    """list_intersections is ONE all-hits traversal whose records wait in a stash sized for 4 hits per ray; a batch
+    with more (here: 12 plates, every ray crosses all of them, some along the plates' diagonals) is traversed again
+    with exactly the room it needs.  Two geometries, so geometry ids are part of the records."""
+    vs, ts = [], []
+    for k in range(12):
+        z = np.float32(k)
+        vs.append(np.array([[0, 0, z], [10, 0, z], [10, 10, z], [0, 10, z]], np.float32))
+        ts.append(np.array([[0, 1, 2], [0, 2, 3]], np.uint32) + np.uint32(4 * k))
+    v, t = np.concatenate(vs), np.concatenate(ts)
+    o, g = oracle_mod.OracleScene(), RS()
+    for s in (o, g):
+        assert s.add_triangles(v[:24], t[:12]) == 0
+        assert s.add_triangles(v[24:], t[12:] - np.uint32(24)) == 1
+    grid = syn.parallel_ray_grid((0, 0, 0), (10, 10, 11), (0, 0, -1), 400, 300, 0.0)
+    rays = syn.materialize_grid(*grid, 400, 300)
+    rays[::7, 1] = rays[::7, 0]                                   # some rays exactly through the shared diagonals
+    gl = {k: a.numpy() for k, a in g.list_intersections(rays).items()}
+    ol = o.list_intersections(rays, 0)
+    assert ol["ray_splits"][-1] > 4 * len(rays) + 65536           # more records than the first stash holds
+    assert np.array_equal(np.diff(ol["ray_splits"]), np.full(len(rays), 12))
+    for k in ol:
+        assert np.array_equal(gl[k], ol[k]), k
+    assert np.array_equal(g.count_intersections(rays).numpy(), np.full(len(rays), 12, np.int32))
+
+
 def test_c1_vs_brute_force_subsample(c1):
     """GPU BVH traversal against the oracle's brute force (ground truth)."""
     v, t, o, g = c1
