@@ -82,6 +82,7 @@ struct RaySource {
     const float *points, *normals; uint64_t seed; float offset;                     // 2
     uint64_t point_base;                        // 2: index of points[0] in the sample (hash of (seed, point_base + p, k))
     uint32_t dir_begin, dir_count;              // 2: this launch draws directions [dir_begin, dir_begin + dir_count) of each point
+    const uint32_t *perm;                       // 2: the order the points are WORKED in (perm[j] = index of the j-th point; NULL: as stored)
     const float *sweep; uint64_t per_grid_rays, per_grid_slots;                    // 3 (nu as in 1)
 };
 
@@ -118,8 +119,9 @@ __device__ __forceinline__ Ray source_ray(const RaySource &S, uint64_t i, uint32
                  __fmaf_rn(fu, g1.y, __fmaf_rn(fv, g2.x, g0.z)) };
         return make_ray(O, f3{ g2.y, g2.z, g2.w });
     }
-    const uint64_t p = fast_div(i, S.dir_count);
+    uint64_t p = fast_div(i, S.dir_count);
     const uint32_t k = S.dir_begin + (uint32_t)(i - p * S.dir_count);
+    if (S.perm) p = S.perm[p];
     f3 O = { S.points[3 * p], S.points[3 * p + 1], S.points[3 * p + 2] };
     if (S.normals) {
         O.x = __fmaf_rn(S.offset, S.normals[3 * p], O.x);
@@ -265,7 +267,7 @@ k_trace5(const TraceArgs A)
                     unsigned long long key;
                     if (MODE == 3) key = (A.goff ? A.goff[best_geom] : 0ull) + best_prim +
                                          (A.src.kind == 3 && A.accum_stride ? fast_div(ray_i, A.src.per_grid_rays) * A.accum_stride : 0ull);
-                    else key = fast_div(ray_i, A.src.dir_count);
+                    else { key = fast_div(ray_i, A.src.dir_count); if (A.src.perm) key = A.src.perm[key]; }
                     const unsigned grp = __match_any_sync(am, key);
                     if ((grp & lt) == 0u) atomicAdd(&A.accum[key], (uint32_t)__popc(grp));
                 }

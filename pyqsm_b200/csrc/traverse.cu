@@ -1143,13 +1143,44 @@ static RaySource hemisphere_source(const float *points, const float *normals, ui
     return s;
 }
 
+// Morton key of a query point inside the scene's box (10 bits per axis), value = its index: the sky driver works the
+// points in this order, so that the rays in flight at any time start in one region of the scene
+__global__ void __launch_bounds__(256)
+k_point_keys(const float *__restrict__ points, uint64_t n, f3 lo, f3 scale, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
+    if (i >= n) return;
+    const float c[3] = { (points[3 * i] - lo.x) * scale.x, (points[3 * i + 1] - lo.y) * scale.y, (points[3 * i + 2] - lo.z) * scale.z };
+    uint64_t key = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        uint32_t q = (uint32_t)fminf(fmaxf(c[a], 0.0f), 1023.0f);          // NaN -> 0
+        q = (q | (q << 16)) & 0x030000FFu; q = (q | (q << 8)) & 0x0300F00Fu; q = (q | (q << 4)) & 0x030C30C3u; q = (q | (q << 2)) & 0x09249249u;
+        key |= (uint64_t)q << a;
+    }
+    keys[i] = key; vals[i] = (uint32_t)i;
+}
+
+int trv_point_keys(const float *points, uint64_t n, const float lo[3], const float hi[3], uint64_t *keys, uint32_t *vals, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    f3 l{ lo[0], lo[1], lo[2] }, sc;
+    sc.x = hi[0] > lo[0] ? 1024.0f / (hi[0] - lo[0]) : 0.0f; sc.y = hi[1] > lo[1] ? 1024.0f / (hi[1] - lo[1]) : 0.0f;
+    sc.z = hi[2] > lo[2] ? 1024.0f / (hi[2] - lo[2]) : 0.0f;
+    k_point_keys<<<grid_for(n, 256), 256, 0, st>>>(points, n, l, sc, keys, vals);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int trv_sky_visibility(TrvState &ts, const SceneView &sc, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
-                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st)
+                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, const uint32_t *perm, uint32_t *unoccluded,
+                       cudaStream_t st)
 {
     if (n_points == 0 || dir_count == 0) return 0;
     if (ts.opt.variant != 2 || stack_bytes(sc) > 96 * 1024) { qsmrt_set_error("sky_visibility needs the persistent kernel"); return 1; }
     TraceArgs a{};
     a.sc = sc; a.src = hemisphere_source(points, normals, point_base, dir_begin, dir_count, seed, offset);
+    a.src.perm = perm;
     a.N = n_points * (uint64_t)dir_count; a.row_len = 0; a.nslots = a.N;
     a.accum = unoccluded; a.tnear = 0.0f; a.tfar = INFINITY; a.depth = (int)sc.height + 2;
     return launch_trace5<4, false>(ts, a, stack_bytes(sc), st);

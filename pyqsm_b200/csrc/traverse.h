@@ -59,7 +59,9 @@ int trv_sun_exposure(TrvState &ts, const SceneView &sc, uint64_t nu, uint64_t nv
 int trv_sun_exposure_sweep(TrvState &ts, const SceneView &sc, uint32_t n_grids, const float *sweep_dev, uint64_t nu, uint64_t nv,
                            const uint64_t *goff, uint32_t *tri_counts, uint64_t count_stride, cudaStream_t st);
 int trv_sky_visibility(TrvState &ts, const SceneView &sc, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
-                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, uint32_t *unoccluded, cudaStream_t st);
+                       uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, const uint32_t *perm, uint32_t *unoccluded,
+                       cudaStream_t st);
+int trv_point_keys(const float *points, uint64_t n, const float lo[3], const float hi[3], uint64_t *keys, uint32_t *vals, cudaStream_t st);
 int trv_gen_hemisphere(float *rays, const float *points, const float *normals, uint64_t n_points, uint64_t point_base,
                        uint64_t seed, float offset, uint32_t dir_begin, uint32_t dir_count, cudaStream_t st);
 int trv_closest_points(TrvState &ts, const SceneView &sc, const float *pts, uint64_t N, float *closest, float *dist, uint32_t *geom,
