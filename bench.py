@@ -437,7 +437,7 @@ def run_ours(args):
     p0, p1, p2 = v[tri0[:, 0]], v[tri0[:, 1]], v[tri0[:, 2]]
     pn = torch.linalg.cross(p1 - p0, p2 - p0)
     pn = pn / pn.norm(dim=1, keepdim=True)
-    env.sky_gap_fraction(scene, p0[:20000], pn[:20000], n_dirs=100 * world, shard=shard)
+    env.sky_gap_fraction(scene, p0, pn, n_dirs=8 * world, shard=shard)          # warm-up at full size: the point-order scratch is allocated here
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -811,6 +811,7 @@ int qsmrt_scene_set_option(qsmrt_scene *s, int key, double value)
     case QSMRT_OPT_CP_WARP_MAX: t.cp_warp_max = std::max(iv, 0); break;
     case QSMRT_OPT_CTAS_PER_SM: t.ctas_per_sm = std::max(iv, 0); break;
     case QSMRT_OPT_TILE_ORDER: t.tile_order = iv != 0; break;
+    case QSMRT_OPT_POINT_ORDER: t.point_order = iv != 0; break;
     case QSMRT_OPT_COUNT_SET: if (iv < 4 || iv > 32) FAIL("count_set must be in 4..32"); t.count_set = iv; break;
     default: FAIL("unknown option %d", key);
     }
@@ -840,6 +841,7 @@ int qsmrt_scene_get_option(qsmrt_scene *s, int key, double *value)
     case QSMRT_OPT_CP_WARP_MAX: *value = t.cp_warp_max; break;
     case QSMRT_OPT_CTAS_PER_SM: *value = t.ctas_per_sm; break;
     case QSMRT_OPT_TILE_ORDER: *value = t.tile_order; break;
+    case QSMRT_OPT_POINT_ORDER: *value = t.point_order; break;
     case QSMRT_OPT_COUNT_SET: *value = t.count_set; break;
     default: FAIL("unknown option %d", key);
     }
@@ -1157,7 +1159,7 @@ int qsmrt_sky_visibility(qsmrt_scene *s, const float *points, const float *norma
     // own indices): the rays in flight then start in one region of the scene and share their first nodes -- 2.41 ->
     // 2.64 Grays/s on C5, whose leaf vertices come in random spatial order (profiles/r02_tuning.txt).
     const uint32_t *perm = nullptr;
-    if (n_points >= 4096 && n_points < (1ull << 32) && s->ntris) {
+    if (s->trv.opt.point_order && n_points >= 4096 && n_points < (1ull << 32) && s->ntris) {
         qsmrt_scene::SkyOrder &so = s->sky;
         if (so.cap < n_points) {
             SyncedFrees batch;

@@ -13,6 +13,7 @@ struct TrvOptions {
     int node_path = 0;      // 0 LSU 256-bit loads, 1 TEX, 2 half/half (L1 data-pipe experiment)
     int cp_warp_max = 16384;// closest-point batches up to this size run one warp per query
     int ctas_per_sm = 0;    // persistent kernel: resident CTAs per SM (0 = as many as fit)
+    int point_order = 1;    // sky visibility: 1 = query points worked in Morton order (default), 0 = as stored
     int tile_order = 1;     // 2-D batches: 1 = tile rows from the middle of the grid outwards (default), 0 = memory order
     int count_set = 32;     // count / list: per-lane hit-set entries in shared memory (4..32); rays with more go to the exact slow path
 };
