@@ -86,6 +86,28 @@ def test_sky_gap_fraction_equals_occlusion(tree):
     assert torch.equal(parts.to(torch.float32) / n_dirs, gap)
 
 
+def test_sky_point_order_does_not_change_the_answer(tree):
+    """qsmrt_sky_visibility works large point sets in Morton order (a permutation the kernel reads); the sample of a
+    point and where its count lands do not depend on it."""
+    from pyqsm_b200 import environment as env
+    g, o, ntri, n0 = tree
+    rng = np.random.default_rng(9)
+    pts = rng.uniform([-4, -4, 0.1], [6, 6, 12], size=(6000, 3)).astype(np.float32)      # >= 4096 points: the sorted path
+    pts[17] = np.nan                                                                      # a NaN point sorts somewhere and sees nothing
+    try:
+        g.set_option("point_order", 0)
+        a = env.sky_gap_fraction(g, pts, None, n_dirs=32, seed=3)
+        g.set_option("point_order", 1)
+        b = env.sky_gap_fraction(g, pts, None, n_dirs=32, seed=3)
+    finally:
+        g.set_option("point_order", 1)
+    assert torch.equal(a, b) and 0.05 < float(b[torch.isfinite(b)].mean()) < 0.999
+    blk = slice(3000, 3040)                                                               # a block, materialised with its place in the sample
+    rays = env.hemisphere_rays(pts[blk], None, n_dirs=32, seed=3, point_base=3000)
+    occ = o.test_occlusions(rays.cpu().numpy(), mode=1).reshape(40, 32)
+    np.testing.assert_allclose(b[blk].cpu().numpy(), (1.0 - occ.mean(1)).astype(np.float32), rtol=0, atol=1e-7)
+
+
 def test_rain_interception_equals_count(tree):
     from pyqsm_b200 import environment as env
     g, o, ntri, n0 = tree
