@@ -986,7 +986,10 @@ int qsmrt_list_intersections_count(qsmrt_scene *s, const float *rays, uint64_t N
                 dmalloc(&ls.uv, 2 * cap) || dmalloc(&ls.count, 1)) {
                 free_list_stash(s);         // no room for a stash: count only, _fill enumerates the hits of every ray
                 g_err[0] = 0;
-            } else ls.cap = cap;
+            } else {
+                ls.cap = cap;
+                CUDA_TRY(cudaMemsetAsync(ls.count, 0, sizeof(unsigned long long), st));     // also read when no kernel used the stash
+            }
             if (trv_list_collect(s->trv, view_of(s), rays, N, (uint32_t)s->geoms.size(), cnt, ls, &s->list_max_fast, st) ||
                 trv_exclusive_scan(cnt, N, ray_splits, scratch, st)) return 1;
             CUDA_TRY(cudaMemcpyAsync(total_out, ray_splits + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));

@@ -119,6 +119,23 @@ def test_c1_list_intersections(c1):
     assert ol["ray_splits"][-1] > 1000
 
 
+def test_list_and_count_with_the_per_thread_kernels(c1):
+    """traversal_variant 1 (the A/B reference, also the path of trees too deep for the shared-memory stack): no stash
+    of hit records, every ray with hits is enumerated hit by hit -- the same CSR arrays."""
+    v, t, o, g = c1
+    rays = syn.random_rays(v.min(0), v.max(0), 4000, seed=6)
+    ol = o.list_intersections(rays, 1)
+    try:
+        g.set_option("traversal_variant", 1)
+        gl = {k: a.cpu().numpy() for k, a in g.list_intersections(rays).items()}
+        gc = g.count_intersections(torch.from_numpy(rays)).cpu().numpy()
+    finally:
+        g.set_option("traversal_variant", 2)
+    for k in ol:
+        assert np.array_equal(gl[k], ol[k]), k
+    assert np.array_equal(gc, np.diff(ol["ray_splits"]).astype(np.int32))
+
+
 def test_list_intersections_many_hits_per_ray(RS, oracle_mod):
     """list_intersections is ONE all-hits traversal whose records wait in a stash sized for 4 hits per ray; a batch
     with more (here: 12 plates, every ray crosses all of them, some along the plates' diagonals) is traversed again
