@@ -669,8 +669,27 @@ def test_property_gpu_equals_brute_force(case):
     for k in ol:
         assert np.array_equal(gl[k].numpy(), ol[k]), k
     gp, op_ = g.compute_closest_points(rays[:, :3].copy()), o.compute_closest_points(rays[:, :3], 0)
-    for k in gp:
-        assert np.array_equal(gp[k].numpy(), op_[k]), k
+    for k in gp:        # a zero-area triangle can be the closest primitive: its normal is 0/0 = NaN on both sides
+        assert np.array_equal(gp[k].numpy(), op_[k], equal_nan=op_[k].dtype.kind == "f"), k
+
+
+def test_degenerate_triangle_as_closest_primitive(RS, oracle_mod):
+    """The case hypothesis found: a point-triangle [2, 2, 2] sitting on a mesh vertex comes out 1 ulp closer than the
+    real triangles around that vertex (a different branch of the region test), so it is the closest primitive; ids,
+    point, distance and uv agree with the oracle and the normal of the zero-area triangle is NaN (0 / 0) in both."""
+    z = np.float32(62.5)
+    v = np.array([[0, 0, -z], [250, 0, 0], [500, 0, z], [0, 250, z], [250, 250, z], [500, 250, 0], [0, 500, z], [250, 500, z],
+                  [500, 500, -z]], np.float32)
+    t = np.array([[0, 1, 4], [0, 4, 3], [1, 2, 5], [1, 5, 4], [3, 4, 7], [3, 7, 6], [4, 5, 8], [4, 8, 7], [0, 1, 4], [0, 4, 3], [1, 2, 5],
+                  [0, 0, 1], [2, 2, 2]], np.uint32)
+    q = np.array([[107.0203, -950.06494, 1633.9882], [520, -10, 80], [100, 100, 300], [-50, -60, -200]], np.float32)
+    o, g = oracle_mod.OracleScene(), RS()
+    o.add_triangles(v, t)
+    g.add_triangles(v, t)
+    a, r = g.compute_closest_points(q), o.compute_closest_points(q, 0)
+    assert r["primitive_ids"][0] == 12 and np.all(np.isnan(r["primitive_normals"][0]))
+    for k in r:
+        assert np.array_equal(a[k].numpy(), r[k], equal_nan=r[k].dtype.kind == "f"), k
 
 
 def test_far_origins_and_offset_scenes(RS, oracle_mod):

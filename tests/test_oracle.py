@@ -365,5 +365,5 @@ def test_property_brute_equals_bvh(case):
     assert np.array_equal(np.diff(l0["ray_splits"]), c0)
     q = rays[:, :3]
     p0, p1 = s.compute_closest_points(q, 0), s.compute_closest_points(q, 1)
-    for k in p0:
-        assert np.array_equal(p0[k], p1[k]), k
+    for k in p0:        # a zero-area triangle can be the closest primitive: its normal is 0/0 = NaN on both sides
+        assert np.array_equal(p0[k], p1[k], equal_nan=p0[k].dtype.kind == "f"), k
