@@ -17,3 +17,8 @@ def oracle_mod():
     import oracle
     oracle.build_oracle()
     return oracle
+
+
+# Property tests draw the same examples on every run (a red driver run must be reproducible here);
+# QSMRT_HYPOTHESIS_RANDOM=1 explores fresh examples instead.
+HYPOTHESIS_DERANDOMIZE = os.environ.get("QSMRT_HYPOTHESIS_RANDOM", "0") != "1"

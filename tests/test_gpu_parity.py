@@ -647,10 +647,11 @@ def test_add_cylinders_on_device(RS, oracle_mod):
 
 
 from hypothesis import given, settings  # noqa: E402
+from conftest import HYPOTHESIS_DERANDOMIZE  # noqa: E402
 from test_oracle import _mesh_and_rays  # noqa: E402
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=HYPOTHESIS_DERANDOMIZE)
 @given(_mesh_and_rays())
 def test_property_gpu_equals_brute_force(case):
     """Adversarial small meshes (shared edges, slivers, duplicates, degenerates, three scales; rays through

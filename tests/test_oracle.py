@@ -304,6 +304,7 @@ def test_closest_points_oracle(orc):
 
 # ---- property tests (hypothesis): the canonical LBVH is not semantics -- brute force is ----------------
 from hypothesis import given, settings, strategies as st  # noqa: E402
+from conftest import HYPOTHESIS_DERANDOMIZE  # noqa: E402
 
 
 @st.composite
@@ -345,7 +346,7 @@ def _mesh_and_rays(draw):
     return v, tri, rays
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=HYPOTHESIS_DERANDOMIZE)
 @given(_mesh_and_rays())
 def test_property_brute_equals_bvh(case):
     import oracle
