@@ -689,8 +689,9 @@ def test_degenerate_triangle_as_closest_primitive(RS, oracle_mod):
     g.add_triangles(v, t)
     a, r = g.compute_closest_points(q), o.compute_closest_points(q, 0)
     assert r["primitive_ids"][0] == 12 and np.all(np.isnan(r["primitive_normals"][0]))
-    for k in r:
+    for k in a:
         assert np.array_equal(a[k].numpy(), r[k], equal_nan=r[k].dtype.kind == "f"), k
+    assert np.array_equal(g.compute_distance(q).numpy(), r["distance"])
 
 
 def test_far_origins_and_offset_scenes(RS, oracle_mod):
