@@ -88,6 +88,8 @@ enum qsmrt_option {
     QSMRT_OPT_NODE_PATH = 22,          /* node fetch path: 0 = 256-bit LSU loads (default), 1 = texture, 2 = half and half */
     QSMRT_OPT_CP_WARP_MAX = 23,        /* closest-point batches up to this many queries use one warp per query (default 16384) */
     QSMRT_OPT_CTAS_PER_SM = 24,        /* persistent kernel: cap on resident CTAs per SM (0 = as many as fit, the default) */
+    QSMRT_OPT_HOST_CHUNK = 28,         /* *_host calls: rays per stage of the three-stream pipe; 0 (default) = 1M when the results are the larger transfer, 2M when the rays are */
+    QSMRT_OPT_HOST_RAMP = 29,          /* *_host calls: 1 (default) = short stages (chunk/8, /4, /2) at both ends of a long batch, 0 = equal stages */
     QSMRT_OPT_POINT_ORDER = 27,        /* qsmrt_sky_visibility: 1 = query points worked in Morton order (default), 0 = as stored */
     QSMRT_OPT_TILE_ORDER = 26,         /* grid-shaped batches: 1 = tile rows handed out from the middle of the grid outwards (default), 0 = in memory order */
     QSMRT_OPT_COUNT_SET = 25           /* count / list_intersections: entries of the per-lane hit set in shared memory, 4..32 (default 32); rays with more distinct hits are finished exactly by the slow path */

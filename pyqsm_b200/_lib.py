@@ -32,7 +32,7 @@ class Stats(C.Structure):
 OPT = {
     "leaf_max": 1, "keep_binary_nodes": 2, "quant_threshold": 3, "climb_capacity": 4, "sort_variant": 5, "split_max": 6, "split_aspect": 7,
     "quantised_nodes": 16, "traversal_variant": 17, "refill": 18, "want": 19, "tri_min": 20, "counters": 21,
-    "node_path": 22, "cp_warp_max": 23, "ctas_per_sm": 24, "count_set": 25, "tile_order": 26, "point_order": 27,
+    "node_path": 22, "cp_warp_max": 23, "ctas_per_sm": 24, "count_set": 25, "tile_order": 26, "point_order": 27, "host_chunk": 28, "host_ramp": 29,
 }
 SAVE_BVH = 1
 

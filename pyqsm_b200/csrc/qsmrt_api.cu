@@ -81,6 +81,7 @@ struct qsmrt_scene {
     // list_intersections cache between _count and _fill
     const float *list_rays = nullptr; uint64_t list_n = 0;
     ListStash list_stash; int list_max_fast = 0;     // the hit records _count collected for _fill
+    uint64_t host_chunk = 0; int host_ramp = 1;      // QSMRT_OPT_HOST_CHUNK / _RAMP
     HostPipe pipe;
     float *sweep_dev = nullptr; uint32_t sweep_cap = 0;     // per-grid constants of qsmrt_sun_exposure_sweep
     // qsmrt_sky_visibility: Morton order of the query points (keys / values double-buffered for the radix sort)
@@ -566,12 +567,10 @@ int run_host_pipe(qsmrt_scene *s, const float *rays, uint64_t N, const HostOut (
         off_of[k] = stage_bytes;
         if (outs[k].host && !outs[k].keep) { stage_bytes += (outs[k].bytes + 15) & ~(size_t)15; back_bytes += outs[k].bytes; }
     }
-    // rays per pipeline stage (QSMRT_HOST_CHUNK overrides): 1M when the results are the larger transfer, 2M when the
+    // rays per pipeline stage (QSMRT_OPT_HOST_CHUNK overrides): 1M when the results are the larger transfer, 2M when the
     // rays are (measured on C2, profiles/r02_tuning.txt: 1.39 Grays/s with all five results, 1.96 -> 2.11 with t_hit + ids)
-    uint64_t chunk_rays = back_bytes > 24 ? 1ull << 20 : 2ull << 20;
-    if (const char *e = getenv("QSMRT_HOST_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk_rays = (uint64_t)v; }
-    bool ramp = true;                                       // QSMRT_HOST_RAMP=0: equal stages (A/B)
-    if (const char *e = getenv("QSMRT_HOST_RAMP")) ramp = atoi(e) != 0;
+    const uint64_t chunk_rays = s->host_chunk ? s->host_chunk : back_bytes > 24 ? 1ull << 20 : 2ull << 20;
+    const bool ramp = s->host_ramp != 0;
     const uint64_t chunk = std::min<uint64_t>(N, chunk_rays);
     if (ensure_pipe(s, chunk, std::max<size_t>(stage_bytes, 16))) return 1;
     HostPipe &hp = s->pipe;
@@ -812,6 +811,8 @@ int qsmrt_scene_set_option(qsmrt_scene *s, int key, double value)
     case QSMRT_OPT_CTAS_PER_SM: t.ctas_per_sm = std::max(iv, 0); break;
     case QSMRT_OPT_TILE_ORDER: t.tile_order = iv != 0; break;
     case QSMRT_OPT_POINT_ORDER: t.point_order = iv != 0; break;
+    case QSMRT_OPT_HOST_CHUNK: if (iv != 0 && iv < 1024) FAIL("host_chunk must be 0 (automatic) or >= 1024 rays"); s->host_chunk = (uint64_t)iv; break;
+    case QSMRT_OPT_HOST_RAMP: s->host_ramp = iv != 0; break;
     case QSMRT_OPT_COUNT_SET: if (iv < 4 || iv > 32) FAIL("count_set must be in 4..32"); t.count_set = iv; break;
     default: FAIL("unknown option %d", key);
     }
@@ -842,6 +843,8 @@ int qsmrt_scene_get_option(qsmrt_scene *s, int key, double *value)
     case QSMRT_OPT_CTAS_PER_SM: *value = t.ctas_per_sm; break;
     case QSMRT_OPT_TILE_ORDER: *value = t.tile_order; break;
     case QSMRT_OPT_POINT_ORDER: *value = t.point_order; break;
+    case QSMRT_OPT_HOST_CHUNK: *value = (double)s->host_chunk; break;
+    case QSMRT_OPT_HOST_RAMP: *value = s->host_ramp; break;
     case QSMRT_OPT_COUNT_SET: *value = t.count_set; break;
     default: FAIL("unknown option %d", key);
     }

@@ -87,11 +87,20 @@ def test_count_and_occlusion_host_pipes(RS, tree):
     big = np.concatenate([rays] * 5)[: (1 << 20) + 12345]         # > one chunk, ragged tail
     s = RS()
     s.add_triangles(v, t)
-    cnt = s.count_intersections(big)
-    occ = s.test_occlusions(big, tnear=0.5, tfar=9.0)
     dev = torch.from_numpy(big).cuda()
-    assert cnt.device.type == "cpu" and torch.equal(cnt, s.count_intersections(dev))
-    assert occ.dtype == torch.bool and torch.equal(occ, s.test_occlusions(dev, tnear=0.5, tfar=9.0))
+    cnt_dev, occ_dev = s.count_intersections(dev), s.test_occlusions(dev, tnear=0.5, tfar=9.0)
+    # stages of 64k rays with short stages at both ends (8k, 16k, 32k ... 32k, 16k, 8k), equal stages, the default size
+    for chunk, ramp in ((65536, 1), (65536, 0), (0, 1)):
+        s.set_option("host_chunk", chunk)
+        s.set_option("host_ramp", ramp)
+        cnt = s.count_intersections(big)
+        occ = s.test_occlusions(big, tnear=0.5, tfar=9.0)
+        assert cnt.device.type == "cpu" and torch.equal(cnt, cnt_dev), (chunk, ramp)
+        assert occ.dtype == torch.bool and torch.equal(occ, occ_dev), (chunk, ramp)
+        full = s.cast_rays(big[:400_000], outputs="all")
+        assert all(np.array_equal(full[k].numpy()[: rays.shape[0]], o.cast_rays(rays, 1)[k]) for k in ("t_hit", "primitive_ids", "primitive_normals"))
+    with pytest.raises(RuntimeError):
+        s.set_option("host_chunk", 100)
     n = rays.shape[0]
     assert np.array_equal(cnt.numpy()[:n], o.count_intersections(rays, 1))
     assert np.array_equal(occ.numpy()[:n], o.test_occlusions(rays, 0.5, 9.0, 1))

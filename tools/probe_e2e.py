@@ -1,5 +1,5 @@
 """End-to-end cast_rays (pinned host rays in, host results out) on C2 for several pipeline chunk sizes
-(QSMRT_HOST_CHUNK rays per stage of the three-stream host pipe, QSMRT_HOST_RAMP short stages at both ends).  One line per setting; not product code."""
+(scene options host_chunk = rays per stage of the three-stream host pipe, host_ramp = short stages at both ends).  One line per setting; not product code."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -12,7 +12,7 @@ for el, az in ((50, 0), (30, 135)):
     g = syn.parallel_ray_grid(np.asarray(st["scene_lo"], np.float64), np.asarray(st["scene_hi"], np.float64), syn.sun_direction(el, az), G, G)
     rays.append(torch.from_numpy(syn.materialize_grid(*g, G, G).reshape(-1, 6)).pin_memory())
 for chunk, ramp in ((1 << 20, 0), (1 << 20, 1), (1 << 21, 0), (1 << 21, 1), (1 << 22, 1), (3 << 19, 1), (1 << 20, 0), (1 << 21, 1)):
-    os.environ["QSMRT_HOST_CHUNK"] = str(chunk); os.environ["QSMRT_HOST_RAMP"] = str(ramp)
+    s.set_option("host_chunk", chunk); s.set_option("host_ramp", ramp)
     for outputs, name in (("all", "all five"), (None, "t_hit+prim")):
         warm = [s.cast_rays(rays[0], outputs=outputs), s.cast_rays(rays[1], outputs=outputs)]
         a = s.cast_rays(rays[0], outputs=outputs); del warm
