@@ -16,6 +16,12 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *     Query entry points only enqueue work; they do not synchronise unless
  *     they take host pointers or the documentation says so.
+ *   - one scene is used from one thread, and its calls are ordered on one
+ *     stream at a time (as with Open3D's scene): some calls keep scratch in
+ *     the scene between launches (the work cursor of the persistent kernels,
+ *     the sun sweep's grid table, the sky driver's point order, the hit
+ *     records between list_intersections_count and _fill).  Different scenes
+ *     are independent, on any threads and streams.
  *   - rays are N x 6 float32 rows (ox,oy,oz,dx,dy,dz); directions are used
  *     as given (not normalised), so t is in units of |d|.
  *   - there is no CPU fallback: without a CUDA device every call fails.
