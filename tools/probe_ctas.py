@@ -1,3 +1,4 @@
+"""Resident CTAs per SM for small batches (QSMRT_OPT_CTAS_PER_SM): C1 cast_rays at 1M rays with 4..10 CTAs per SM.  Not product code."""
 import ctypes as C, os, sys
 sys.path.insert(0, '/root/repo' if os.path.exists('/root/repo/pyqsm_b200') else os.getcwd())
 import numpy as np, torch
