@@ -5,10 +5,10 @@ hemisphere sweep) at 1/2/4/8 B200, plus the LBVH build time.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step = one solar angle: cast_rays over 16 777 216 rays (+ the per-triangle
+A step = one solar angle: cast_rays over 16 000 000 rays (+ the per-triangle
 exposure accumulation the sweep keeps on the device).  N > 1 (torchrun, one
 rank per GPU): the mesh is broadcast once over NCCL, every rank builds the
-same LBVH and casts one whole solar angle (16 777 216 rays) per step; the angle
+same LBVH and casts one whole solar angle (16 000 000 rays) per step; the angle
 slots are dealt to the ranks longest-processing-time-first on the committed
 per-angle kernel times, so the ranks' totals agree although single angles
 differ by +-15 % (weak scaling, no data-path collective); one all-reduce of
